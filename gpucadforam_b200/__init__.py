@@ -1,0 +1,16 @@
+"""gpucadforam_b200 -- B200-native implicit-field + marching-cubes path of GPUCADforAM.
+
+Python is only the test/bench harness language here: the product is the C-ABI shared library
+`libgpucad_b200.so` (hand-written CUDA for sm_100a, see csrc/ and include/gpucad_b200.h) and
+the C++ host mirror in host/.  This package loads the library through ctypes and mirrors the
+reference's host classes (same method names and argument meaning) on top of torch CUDA tensors,
+which are used purely as device-memory handles.
+
+Importing the package without the built library raises ImportError -- there is no fallback.
+"""
+from . import _capi
+from .api import (Context, Isosurface, Modelling, Fft_lattice, Gratings, File_output, MeshBuffers, Scratch,
+                  svl_lattice, svl_lattice_host, extract_band_raw, svl_field)
+
+__all__ = ["Context", "Isosurface", "Modelling", "Fft_lattice", "Gratings", "File_output", "MeshBuffers", "Scratch",
+           "svl_lattice", "svl_lattice_host", "extract_band_raw", "svl_field", "_capi"]

@@ -1,0 +1,444 @@
+// capi.cu -- extern "C" boundary of libgpucad_b200 (declared in include/gpucad_b200.h).
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace gcb {
+
+int fail(Ctx* c, const char* what, cudaError_t e) {
+    if (c) c->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 1;
+}
+int fail_msg(Ctx* c, const std::string& msg) {
+    if (c) c->err = msg;
+    return 1;
+}
+
+static inline float3 f3(gcb_float3 v) { return make_float3(v.x, v.y, v.z); }
+
+// Legacy extraction: optional byte-granular memset of Isosurface.cu:120-121, then the fused kernel.
+static int run_legacy(Ctx* c, McArgs& a, void* pos, void* norm, unsigned maxVerts, unsigned* d_verts, unsigned* d_vertsScan, unsigned* d_occ,
+                      unsigned* d_occScan, unsigned* d_comp, unsigned* activeVoxels, unsigned* totalVerts, bool memset_out) {
+    a.pos = (float4*)pos;
+    a.norm = (float4*)norm;
+    a.max_verts = maxVerts;
+    a.comp = d_comp;
+    a.gz0 = 0;
+    a.gnz = a.nz;
+    a.count_only = 0;
+    const bool fill = (c->options & GCB_OPT_FILL_STAGE_ARRAYS) && d_verts && d_vertsScan && d_occ && d_occScan;
+    a.st_verts = fill ? d_verts : nullptr;
+    a.st_occ = fill ? d_occ : nullptr;
+    a.st_verts_scan = fill ? d_vertsScan : nullptr;
+    a.st_occ_scan = fill ? d_occScan : nullptr;
+    if (memset_out && (c->options & GCB_OPT_LEGACY_MEMSET)) {
+        // The reference clears maxVerts BYTES (not vertices) of both buffers after it knows activeVoxels > 0.
+        // Clearing before the kernel is equivalent: every byte the kernel does not overwrite is identical.
+        // (When activeVoxels == 0 the reference leaves the buffers untouched; consumers honour totalVerts.)
+        GCB_CHECK(c, cudaMemsetAsync(pos, 0, maxVerts, c->stream));
+        GCB_CHECK(c, cudaMemsetAsync(norm, 0, maxVerts, c->stream));
+    }
+    unsigned long long act = 0, verts = 0;
+    if (int r = launch_extract(c, a, &act, &verts)) return r;
+    if (activeVoxels) *activeVoxels = (unsigned)act;
+    if (totalVerts) *totalVerts = (unsigned)verts;
+    return 0;
+}
+
+static void base_args(McArgs& a, int mode, gcb_uint3 gridSize, gcb_float3 voxelSize, gcb_float3 gridcenter, float iso) {
+    memset(&a, 0, sizeof a);
+    a.mode = mode;
+    a.nx = gridSize.x; a.ny = gridSize.y; a.nz = gridSize.z;
+    a.voxel = f3(voxelSize);
+    a.center = f3(gridcenter);
+    a.iso = iso;
+}
+
+} // namespace gcb
+
+using namespace gcb;
+
+#define CTX(c) Ctx* C = reinterpret_cast<Ctx*>(c); if (!C) return 1
+
+extern "C" {
+
+int gcb_create(gcb_ctx** out, int device, void* stream) {
+    if (!out) return 1;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device >= n) return 2;  // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return 2;
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return 1;
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    bool ok = cudaMalloc(&c->d_tile_counter, 16) == cudaSuccess && cudaMalloc(&c->d_totals, 16) == cudaSuccess &&
+              cudaMallocHost(&c->h_totals, 16) == cudaSuccess && cudaMalloc(&c->d_minmax, 16) == cudaSuccess &&
+              cudaMallocHost(&c->h_minmax, 16) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    if (!ok) { delete c; return 3; }
+    *out = reinterpret_cast<gcb_ctx*>(c);
+    return 0;
+}
+int gcb_destroy(gcb_ctx* ctx) {
+    CTX(ctx);
+    cudaSetDevice(C->device);
+    cudaFree(C->d_status); cudaFree(C->d_tile_counter); cudaFree(C->d_totals); cudaFreeHost(C->h_totals);
+    cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef);
+    cudaFree(C->d_tri); cudaFree(C->d_nverts);
+    for (int i = 0; i < 4; ++i) if (C->ev[i]) cudaEventDestroy(C->ev[i]);
+    delete C;
+    return 0;
+}
+const char* gcb_last_error(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); return C ? C->err.c_str() : "null context"; }
+int gcb_set_stream(gcb_ctx* ctx, void* stream) { CTX(ctx); C->stream = (cudaStream_t)stream; return 0; }
+int gcb_set_options(gcb_ctx* ctx, unsigned int flags) { CTX(ctx); C->options = flags; return 0; }
+unsigned long long gcb_launch_count(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); return C ? C->launches : 0; }
+void gcb_reset_launch_count(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); if (C) C->launches = 0; }
+int gcb_enable_kernel_timing(gcb_ctx* ctx, int on) { CTX(ctx); C->timing = on != 0; return 0; }
+float gcb_last_extract_kernel_ms(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); return C ? C->last_extract_ms : -1.f; }
+float gcb_last_field_kernel_ms(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); return C ? C->last_field_ms : -1.f; }
+
+void gcb_tables(unsigned int* tri, unsigned int* nverts) { host_tables(tri, nverts); }
+
+int gcb_allocateTextures_s(gcb_ctx* ctx, unsigned int** d_triTable, unsigned int** d_numVertsTable) {
+    CTX(ctx);
+    unsigned tri[256 * 16], nv[256];
+    host_tables(tri, nv);
+    if (!C->d_tri) {
+        GCB_CHECK(C, cudaMalloc(&C->d_tri, sizeof tri));
+        GCB_CHECK(C, cudaMalloc(&C->d_nverts, sizeof nv));
+    }
+    GCB_CHECK(C, cudaMemcpy(C->d_tri, tri, sizeof tri, cudaMemcpyHostToDevice));
+    GCB_CHECK(C, cudaMemcpy(C->d_nverts, nv, sizeof nv, cudaMemcpyHostToDevice));
+    if (d_triTable) *d_triTable = C->d_tri;
+    if (d_numVertsTable) *d_numVertsTable = C->d_nverts;
+    return 0;
+}
+int gcb_destroyAllTextureObjects(gcb_ctx* ctx) { CTX(ctx); return 0; }
+
+// ------------------------------------------------------------------ extraction, legacy signatures
+int gcb_computeIsosurface(gcb_ctx* ctx, float* vol, gcb_uint3 raster_grid, void* pos, void* norm, float isoValue, unsigned int numVoxels,
+                          unsigned int* d_voxelVerts, unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan,
+                          gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter,
+                          unsigned int* activeVoxels, unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts,
+                          gcb_grid_points* primitive_fixed, float* primitive_dynamic, float* topo_field, float* lattice_field, float iso1, float iso2,
+                          int obj_union, int obj_diff, int obj_intersect, int primitive, int topo, int compute_lattice, int fixed, int dynamic,
+                          int make_region, size_t* nfacets) {
+    CTX(ctx);
+    // dead parameters of the reference kernel: vol, raster_grid, topo_field, primitive, topo, compute_lattice
+    (void)vol; (void)raster_grid; (void)numVoxels; (void)gridSizeShift; (void)gridSizeMask; (void)topo_field; (void)primitive; (void)topo; (void)compute_lattice;
+    McArgs a;
+    base_args(a, M_CSG, gridSize, voxelSize, gridcenter, isoValue);
+    a.iso1 = iso1; a.iso2 = iso2;
+    a.flags = (obj_union ? F_UNION : 0) | (obj_diff ? F_DIFF : 0) | (obj_intersect ? F_INTERSECT : 0) | (fixed ? F_FIXED : 0) | (dynamic ? F_DYNAMIC : 0) |
+              (make_region ? F_MAKE_REGION : 0);
+    a.f0 = primitive_dynamic;
+    a.f1 = lattice_field;
+    a.gp = (const GridPoint*)primitive_fixed;
+    unsigned tv = 0;
+    int r = run_legacy(C, a, pos, norm, maxVerts, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, d_compVoxelArray, activeVoxels, &tv, true);
+    if (r) return r;
+    if (totalVerts) *totalVerts = tv;
+    if (nfacets && tv) *nfacets = tv / 3;  // Isosurface.cu:115-116 (not written on the early-out path)
+    return 0;
+}
+
+static int lattice_common(Ctx* C, int mode, float* vol, void* pos, void* norm, float isoValue, unsigned* d_voxelVerts, unsigned* d_voxelVertsScan,
+                          unsigned* d_voxelOccupied, unsigned* d_voxelOccupiedScan, gcb_uint3 gridSize, gcb_float3 voxelSize, gcb_float3 gridcenter,
+                          unsigned* activeVoxels, unsigned* totalVerts, unsigned* d_compVoxelArray, unsigned maxVerts, float* vol_one, float* vol_two,
+                          float isovalue1, float isovalue2, float iso1, float iso2) {
+    McArgs a;
+    base_args(a, mode, gridSize, voxelSize, gridcenter, isoValue);
+    a.iso1 = isovalue1; a.iso2 = isovalue2; a.iso1b = iso1; a.iso2b = iso2;
+    a.f0 = vol_one;  // k: interpolation field, TMA-staged
+    a.f1 = vol;      // mask: classification field
+    a.f2 = vol_two;
+    // the lattice variants have no memset in the reference (Isosurface.cu:401-572)
+    return run_legacy(C, a, pos, norm, maxVerts, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, d_compVoxelArray, activeVoxels, totalVerts,
+                      false);
+}
+
+int gcb_computeIsosurface_lattice(gcb_ctx* ctx, float* vol, void* pos, void* norm, float isoValue, unsigned int numVoxels, unsigned int* d_voxelVerts,
+                                  unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan, gcb_uint3 gridSize,
+                                  gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter, unsigned int* activeVoxels,
+                                  unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts, float* vol_one, float* vol_two,
+                                  float isovalue1, float isovalue2, float iso1, float iso2) {
+    CTX(ctx);
+    (void)numVoxels; (void)gridSizeShift; (void)gridSizeMask;
+    if (!vol || !vol_one || !vol_two) return fail_msg(C, "computeIsosurface_lattice: null field");
+    return lattice_common(C, M_LATTICE, vol, pos, norm, isoValue, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, gridSize, voxelSize,
+                          gridcenter, activeVoxels, totalVerts, d_compVoxelArray, maxVerts, vol_one, vol_two, isovalue1, isovalue2, iso1, iso2);
+}
+int gcb_computeIsosurface_latticeone(gcb_ctx* ctx, float* vol, void* pos, void* norm, float isoValue, unsigned int numVoxels, unsigned int* d_voxelVerts,
+                                     unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan, gcb_uint3 gridSize,
+                                     gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter,
+                                     unsigned int* activeVoxels, unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts,
+                                     float* vol_one, float isovalue1, float isovalue2) {
+    CTX(ctx);
+    (void)numVoxels; (void)gridSizeShift; (void)gridSizeMask;
+    if (!vol || !vol_one) return fail_msg(C, "computeIsosurface_latticeone: null field");
+    return lattice_common(C, M_LATTICE_ONE, vol, pos, norm, isoValue, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, gridSize, voxelSize,
+                          gridcenter, activeVoxels, totalVerts, d_compVoxelArray, maxVerts, vol_one, nullptr, isovalue1, isovalue2, 0.f, 0.f);
+}
+
+static int topo_common(Ctx* C, void* pos, void* norm, float isoValue, unsigned* d_voxelVerts, unsigned* d_voxelVertsScan, unsigned* d_voxelOccupied,
+                       unsigned* d_voxelOccupiedScan, gcb_uint3 gridSize, gcb_float3 voxelSize, gcb_float3 gridcenter, unsigned* activeVoxels,
+                       unsigned* totalVerts, unsigned* d_compVoxelArray, unsigned maxVerts, gcb_grid_points* vol_topo, float* vol_two, float isovalue1,
+                       float* d_result, int disp, void* disp_two) {
+    if (!vol_two) return fail_msg(C, "computeIsosurface_topo/_2: null density field");
+    McArgs a;
+    base_args(a, M_TOPO, gridSize, voxelSize, gridcenter, isoValue);
+    a.iso1 = isovalue1;
+    a.f0 = vol_two;
+    a.f1 = d_result;
+    a.gp = (const GridPoint*)vol_topo;
+    a.disp = (const float4*)disp_two;
+    a.flags = (disp && disp_two) ? F_DISP : 0;
+    return run_legacy(C, a, pos, norm, maxVerts, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, d_compVoxelArray, activeVoxels, totalVerts,
+                      false);
+}
+int gcb_computeIsosurface_2(gcb_ctx* ctx, void* pos, void* norm, float isoValue, unsigned int numVoxels, unsigned int* d_voxelVerts,
+                            unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan, gcb_uint3 gridSize,
+                            gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter, unsigned int* activeVoxels,
+                            unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts, gcb_grid_points* vol_topo,
+                            gcb_grid_points* vol_one, float* vol_two, float* d_solid, float isovalue1, float* d_result, void* triangle_data) {
+    CTX(ctx);
+    (void)numVoxels; (void)gridSizeShift; (void)gridSizeMask; (void)vol_one; (void)d_solid; (void)triangle_data;  // dead in the reference kernels (A-15)
+    return topo_common(C, pos, norm, isoValue, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, gridSize, voxelSize, gridcenter,
+                       activeVoxels, totalVerts, d_compVoxelArray, maxVerts, vol_topo, vol_two, isovalue1, d_result, 0, nullptr);
+}
+int gcb_computeIsosurface_topo(gcb_ctx* ctx, void* pos, void* norm, float isoValue, unsigned int numVoxels, unsigned int* d_voxelVerts,
+                               unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan, gcb_uint3 gridSize,
+                               gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter, unsigned int* activeVoxels,
+                               unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts, gcb_grid_points* vol_topo,
+                               gcb_grid_points* vol_one, float* vol_two, float* d_solid, float isovalue1, float* d_result, void* triangle_data, int disp,
+                               void* disp_two) {
+    CTX(ctx);
+    (void)numVoxels; (void)gridSizeShift; (void)gridSizeMask; (void)vol_one; (void)d_solid; (void)triangle_data;
+    return topo_common(C, pos, norm, isoValue, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, gridSize, voxelSize, gridcenter,
+                       activeVoxels, totalVerts, d_compVoxelArray, maxVerts, vol_topo, vol_two, isovalue1, d_result, disp, disp_two);
+}
+
+int gcb_copy_parameter(gcb_ctx* ctx, unsigned int* voxel_verts, float isoValue, gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask,
+                       gcb_float3 voxelSize, unsigned int numVoxels, gcb_grid_points* vol_one, float* vol_two, float* vol_lattice, int fixed, int dynamic,
+                       float iso1, float iso2, int obj_union, int obj_diff, int obj_intersect) {
+    CTX(ctx);
+    (void)voxel_verts; (void)gridSizeShift; (void)gridSizeMask; (void)voxelSize; (void)numVoxels; (void)fixed;
+    int r = k_copy_parameter(C, (GridPoint*)vol_one, vol_two, vol_lattice, dynamic != 0, iso1, iso2, gridSize.x, gridSize.y, gridSize.z, isoValue,
+                             obj_union != 0, obj_diff != 0, obj_intersect != 0);
+    if (r) return r;
+    GCB_CHECK(C, cudaStreamSynchronize(C->stream));  // the reference wrapper ends in cudaDeviceSynchronize (:458)
+    return 0;
+}
+int gcb_patch_topo_field(gcb_ctx* ctx, float* d_vec1, int Nx, int Ny, int Nz, gcb_grid_points* vol_one) {
+    CTX(ctx);
+    if (int r = k_patch_topo_field(C, d_vec1, Nx, Ny, Nz, (const GridPoint*)vol_one)) return r;
+    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ fields, legacy signatures
+#define SYNC_RET(expr)                                   \
+    do {                                                 \
+        if (int r_ = (expr)) return r_;                  \
+        GCB_CHECK(C, cudaStreamSynchronize(C->stream));  \
+        return 0;                                        \
+    } while (0)
+
+int gcb_distance_from_line(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 axis, float radius_1, float thickness_radial, float thickness_axial, int Nx,
+                           int Ny, int Nz, float dx, float dy, float dz, int disc) {
+    CTX(ctx);
+    SYNC_RET(k_line(C, d, f3(center), f3(axis), radius_1, thickness_radial, thickness_axial, Nx, Ny, Nz, dx, dy, dz, disc != 0));
+}
+int gcb_sphere_with_center(gcb_ctx* ctx, float* d, gcb_float3 center, float radius_1, float thickness_wall, int Nx, int Ny, int Nz, float dx, float dy, float dz,
+                           int shell) {
+    CTX(ctx);
+    SYNC_RET(k_sphere(C, d, f3(center), radius_1, thickness_wall, Nx, Ny, Nz, dx, dy, dz, shell != 0));
+}
+int gcb_cuboid(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 angles, float xw, float yw, float zw, int Nx, int Ny, int Nz, float dx, float dy, float dz) {
+    CTX(ctx);
+    SYNC_RET(k_cuboid(C, d, f3(center), f3(angles), xw, yw, zw, Nx, Ny, Nz, dx, dy, dz));
+}
+int gcb_cuboid_shell(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 angles, float xw, float yw, float zw, float thickness, int Nx, int Ny, int Nz,
+                     float dx, float dy, float dz) {
+    CTX(ctx);
+    SYNC_RET(k_cuboid_shell(C, d, f3(center), f3(angles), xw, yw, zw, thickness, Nx, Ny, Nz, dx, dy, dz));
+}
+int gcb_torus_with_center(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 angles, float torus_radius, float torus_circle_radius, int Nx, int Ny, int Nz,
+                          float dx, float dy, float dz) {
+    CTX(ctx);
+    SYNC_RET(k_torus(C, d, f3(center), f3(angles), torus_radius, torus_circle_radius, Nx, Ny, Nz, dx, dy, dz));
+}
+int gcb_cone_with_base_radius_height(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 angles, float base_radius, float cone_height, int Nx, int Ny, int Nz,
+                                     float dx, float dy, float dz) {
+    CTX(ctx);
+    SYNC_RET(k_cone(C, d, f3(center), f3(angles), base_radius, cone_height, Nx, Ny, Nz, dx, dy, dz));
+}
+int gcb_cone_frustum(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 angles, float top_radius, float bottom_radius, float h, int Nx, int Ny, int Nz,
+                     float dx, float dy, float dz) {
+    CTX(ctx);
+    SYNC_RET(k_cone_frustum(C, d, f3(center), f3(angles), top_radius, bottom_radius, h, Nx, Ny, Nz, dx, dy, dz));
+}
+int gcb_pyramid_frustum(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 angles, float xb, float xt, float yh, float zb, float zt, int Nx, int Ny, int Nz,
+                        float dx, float dy, float dz) {
+    CTX(ctx);
+    SYNC_RET(k_pyramid_frustum(C, d, f3(center), f3(angles), xb, xt, yh, zb, zt, Nx, Ny, Nz, dx, dy, dz));
+}
+int gcb_create_lattice(gcb_ctx* ctx, float* d, unsigned int NX, unsigned int NY, unsigned int NZ, unsigned int size, unsigned int type) {
+    CTX(ctx);
+    (void)size;
+    SYNC_RET(k_create_lattice(C, d, NX, NY, NZ, type));
+}
+int gcb_GPU_buffer_normalise_buffer(gcb_ctx* ctx, float* d_vec1, float* d_vec2, int n) {
+    CTX(ctx);
+    float a, b;
+    if (int r = k_minmax(C, d_vec1, (size_t)n, &a, &b)) return r;
+    SYNC_RET(k_normalise(C, d_vec1, d_vec2, (size_t)n, a, b));
+}
+int gcb_GPU_buffer_normalise_four(gcb_ctx* ctx, float* dataone, float* datatwo, float* datathree, size_t size, int Nx, int Ny, int Nz, float isoval_1,
+                                  float isoval_2) {
+    CTX(ctx);
+    float a, b;
+    if (int r = k_minmax(C, dataone, size, &a, &b)) return r;
+    SYNC_RET(k_normalise_four(C, dataone, datatwo, datathree, Nx, Ny, Nz, a, b, isoval_1, isoval_2));
+}
+int gcb_minmax(gcb_ctx* ctx, const float* d_in, size_t n, float* lo, float* hi) { CTX(ctx); return k_minmax(C, d_in, n, lo, hi); }
+
+int gcb_grating(gcb_ctx* ctx, void* dvol, int NX2, int NY2, int NZ2, float dx2, float dy2, float dz2) {
+    CTX(ctx);
+    if (!C->d_tex) return fail_msg(C, "grating: setupTexture/updateTexture not called");
+    SYNC_RET(k_grating(C, C->d_tex, C->tex_x, C->tex_y, C->tex_z, (float2*)dvol, NX2, NY2, NZ2, dx2, dy2, dz2));
+}
+int gcb_refine(gcb_ctx* ctx, float* dvol, int NX2, int NY2, int NZ2, float dx, float dy, float dz) {
+    CTX(ctx);
+    if (!C->d_tex) return fail_msg(C, "refine: setupTexture/updateTexture not called");
+    SYNC_RET(k_refine(C, C->d_tex, C->tex_x, C->tex_y, C->tex_z, dvol, NX2, NY2, NZ2, dx, dy, dz));
+}
+int gcb_svl(gcb_ctx* ctx, float* d_svl, void* d_grating, int NX, int NY, int NZ, int indxx, void* data_fft) {
+    CTX(ctx);
+    SYNC_RET(k_svl(C, d_svl, (const float2*)d_grating, (size_t)NX * NY * NZ, indxx, (const float2*)data_fft));
+}
+int gcb_topo_field(gcb_ctx* ctx, float* topo_field, float* isosurf, float volfrac, int NX, int NY, int NZ) {
+    CTX(ctx);
+    SYNC_RET(k_topo_field(C, topo_field, isosurf, volfrac, (size_t)(unsigned)(NX * NY * NZ)));
+}
+int gcb_primitive_field(gcb_ctx* ctx, gcb_grid_points* primitive_field, float* primitive_active, float* isosurf, float isoval, int fixed, int active, int NX,
+                        int NY, int NZ) {
+    CTX(ctx);
+    (void)isoval;
+    SYNC_RET(k_primitive_field(C, (const GridPoint*)primitive_field, primitive_active, isosurf, (size_t)(unsigned)(NX * NY * NZ), fixed != 0, active != 0));
+}
+
+int gcb_setupTexture(gcb_ctx* ctx, int dx, int dy, int dz) {
+    CTX(ctx);
+    if (C->d_tex) { cudaFree(C->d_tex); C->d_tex = nullptr; }
+    C->tex_x = dx; C->tex_y = dy; C->tex_z = dz;
+    GCB_CHECK(C, cudaMalloc(&C->d_tex, (size_t)dx * dy * dz * sizeof(float)));
+    return 0;
+}
+int gcb_copytotexture(gcb_ctx* ctx, float* d_phi, gcb_pitched_ptr data_ptr, int NX, int NY, int NZ) {
+    CTX(ctx);
+    SYNC_RET(k_copy_to_pitched(C, d_phi, data_ptr, NX, NY, NZ));
+}
+int gcb_updateTexture(gcb_ctx* ctx, gcb_pitched_ptr p) {
+    CTX(ctx);
+    if (!C->d_tex) return fail_msg(C, "updateTexture: setupTexture not called");
+    cudaMemcpy3DParms prm;
+    memset(&prm, 0, sizeof prm);
+    prm.srcPtr = make_cudaPitchedPtr(p.ptr, p.pitch, p.xsize, p.ysize);
+    prm.dstPtr = make_cudaPitchedPtr(C->d_tex, (size_t)C->tex_x * sizeof(float), (size_t)C->tex_x * sizeof(float), C->tex_y);
+    prm.extent = make_cudaExtent((size_t)C->tex_x * sizeof(float), C->tex_y, C->tex_z);
+    prm.kind = cudaMemcpyDeviceToDevice;
+    GCB_CHECK(C, cudaMemcpy3DAsync(&prm, C->stream));
+    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
+    return 0;
+}
+int gcb_deleteTexture(gcb_ctx* ctx) {
+    CTX(ctx);
+    if (C->d_tex) { cudaFree(C->d_tex); C->d_tex = nullptr; }
+    return 0;
+}
+
+int gcb_file_write_obj(gcb_ctx* ctx, void* d_pos, unsigned int totalVerts, const char* filename) {
+    CTX(ctx);
+    float* h = nullptr;
+    if (totalVerts) {
+        GCB_CHECK(C, cudaMallocHost(&h, (size_t)totalVerts * 16));
+        cudaError_t e = cudaMemcpyAsync(h, d_pos, (size_t)totalVerts * 16, cudaMemcpyDeviceToHost, C->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(C->stream);
+        if (e != cudaSuccess) { cudaFreeHost(h); return fail(C, "file_write_obj D2H", e); }
+    }
+    int r = write_obj_host(h, totalVerts, filename);
+    if (h) cudaFreeHost(h);
+    if (r) return fail_msg(C, std::string("file_write_obj: cannot write ") + filename);
+    return 0;
+}
+
+// ------------------------------------------------------------------ fused entry points
+int gcb_svl_field(gcb_ctx* ctx, float* d_svl, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz_local, int cz0, int NX2, int NY2,
+                  int NZ2_local, gcb_slab slab, float dx, float dy, float dz, int accumulate, float* d_minmax) {
+    CTX(ctx);
+    if (d_minmax) if (int r = k_minmax_init(C, C->d_minmax)) return r;
+    if (C->timing) cudaEventRecord(C->ev[2], C->stream);
+    if (int r = k_svl_field(C, d_svl, d_phi, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, NZ2_local, slab.z0, dx, dy, dz, accumulate,
+                            d_minmax ? C->d_minmax : nullptr))
+        return r;
+    if (C->timing) cudaEventRecord(C->ev[3], C->stream);
+    if (d_minmax) if (int r = k_minmax_decode(C, C->d_minmax, d_minmax)) return r;
+    if (C->timing) { GCB_CHECK(C, cudaStreamSynchronize(C->stream)); cudaEventElapsedTime(&C->last_field_ms, C->ev[2], C->ev[3]); }
+    return 0;
+}
+
+int gcb_extract_band_raw(gcb_ctx* ctx, const float* d_field, float a, float b, float isoValue, float isovalue1, float isovalue2, gcb_uint3 gridSizeLocal,
+                         gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
+                         unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels, unsigned long long* totalVerts) {
+    CTX(ctx);
+    if (!d_field) return fail_msg(C, "extract_band_raw: null field");
+    McArgs A;
+    base_args(A, M_BAND_RAW, gridSizeLocal, voxelSize, gridcenter, isoValue);
+    A.iso1 = isovalue1; A.iso2 = isovalue2;
+    A.f0 = d_field;
+    A.na = a; A.nb = b;
+    A.gz0 = slab.z0;
+    A.gnz = slab.gnz ? slab.gnz : gridSizeLocal.z;
+    A.pos = (float4*)pos; A.norm = (float4*)norm;
+    A.max_verts = maxVerts;
+    A.comp = d_compVoxelArray;
+    A.count_only = count_only;
+    unsigned long long act = 0, verts = 0;
+    if (int r = launch_extract(C, A, &act, &verts)) return r;
+    if (activeVoxels) *activeVoxels = act;
+    if (totalVerts) *totalVerts = count_only ? C->h_totals[1] : verts;
+    return 0;
+}
+
+int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz, int NX2, int NY2, int NZ2,
+                    float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos,
+                    void* norm, unsigned long long maxVerts, unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out) {
+    CTX(ctx);
+    gcb_slab slab{0u, (unsigned)NZ2};
+    if (int r = gcb_svl_field(ctx, d_svl_scratch, d_phi, nh, coef_host, cx, cy, cz, 0, NX2, NY2, NZ2, slab, dx, dy, dz, 0, C->d_minmax)) return r;
+    GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
+    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
+    const float a = C->h_minmax[0], b = C->h_minmax[1];
+    if (minmax_out) { minmax_out[0] = a; minmax_out[1] = b; }
+    gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
+    return gcb_extract_band_raw(ctx, d_svl_scratch, a, b, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts, nullptr, 0,
+                                activeVoxels, totalVerts);
+}
+
+int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host, int cx, int cy, int cz,
+                         int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2, gcb_float3 voxelSize,
+                         gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned long long* activeVoxels,
+                         unsigned long long* totalVerts, float* minmax_out) {
+    CTX(ctx);
+    GCB_CHECK(C, cudaMemcpyAsync(d_phi_scratch, h_phi, (size_t)nh * cx * cy * cz * sizeof(float), cudaMemcpyHostToDevice, C->stream));
+    return gcb_svl_lattice(ctx, d_svl_scratch, d_phi_scratch, nh, coef_host, cx, cy, cz, NX2, NY2, NZ2, dx, dy, dz, isoValue, isovalue1, isovalue2, voxelSize,
+                           gridcenter, pos, norm, maxVerts, activeVoxels, totalVerts, minmax_out);
+}
+
+} // extern "C"

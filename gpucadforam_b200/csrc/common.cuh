@@ -1,0 +1,134 @@
+// common.cuh -- shared internals of libgpucad_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gpucad_b200.h"
+
+namespace gcb {
+
+// 16-byte AoS CSG state; reference src/MarchingCubes_kernel.h:12-18
+struct __align__(16) GridPoint { int val; float t_x, t_y, t_z; };
+static_assert(sizeof(GridPoint) == sizeof(gcb_grid_points), "layout");
+
+enum Mode : int {
+    M_LATTICE_ONE = 0,  // computeIsosurface_latticeone  (mask `vol` + k `vol_one`)
+    M_LATTICE = 1,      // computeIsosurface_lattice     (+ vol_two, iso1/iso2)
+    M_CSG = 2,          // computeIsosurface             (grid_points + dynamic + lattice)
+    M_TOPO = 3,         // computeIsosurface_2 / _topo   (vol_topo + density + result [+disp])
+    M_BAND_RAW = 4      // fused: raw field -> normalise + domain faces + band mask -> latticeone
+};
+enum : uint32_t {
+    F_UNION = 1, F_DIFF = 2, F_INTERSECT = 4, F_FIXED = 8, F_DYNAMIC = 16, F_MAKE_REGION = 32, F_DISP = 64
+};
+
+// Arguments of the fused extraction kernel (by value, < 4 KB).
+struct McArgs {
+    int mode;
+    uint32_t nx, ny, nz;   // grid POINTS held by this rank (slab incl. +z halo plane)
+    uint32_t cx, cy, cz;   // cells
+    float3 voxel, center;
+    float iso, iso1, iso2, iso1b, iso2b;
+    uint32_t flags;
+    unsigned long long max_verts;
+    const float* f0;       // TMA-staged interpolation field (k | dynamic | density | raw)
+    const float* f1;       // mask (lattice) | lattice_field (CSG) | d_result (topo)
+    const float* f2;       // vol_two (M_LATTICE)
+    const GridPoint* gp;   // primitive_fixed (CSG) | vol_topo (topo)
+    const float4* disp;    // topo displaced positions
+    float na, nb;          // M_BAND_RAW: k = (f - na) / (nb - na)
+    uint32_t gz0, gnz;     // global z offset of local point layer 0, global number of point layers
+    float4* pos;
+    float4* norm;
+    uint32_t* comp;        // compacted active cell ids (global linear id), may be null
+    uint32_t* st_verts;    // optional stage arrays (GCB_OPT_FILL_STAGE_ARRAYS)
+    uint32_t* st_occ;
+    uint32_t* st_verts_scan;
+    uint32_t* st_occ_scan;
+    unsigned long long* status_a;  // decoupled look-back: [flag:2 | active prefix:62] per tile
+    unsigned long long* status_v;  // [flag:2 | vertex prefix:62] per tile
+    uint32_t* tile_counter;
+    unsigned long long* totals;    // [0]=active cells, [1]=vertices
+    uint32_t rows_per_tile, tiles_per_slice, num_tiles;
+    uint32_t prow_stride;          // floats between the two staged slices in smem ( (R+1)*nx rounded )
+    int use_tma;
+    int count_only;
+    uint32_t magic_cx_mul, magic_cx_shift;  // unused (kept for layout stability)
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    unsigned int options = GCB_OPT_LEGACY_MEMSET;
+    std::string err;
+    unsigned long long launches = 0;
+    int num_sms = 148;
+    // extraction scratch
+    unsigned long long* d_status = nullptr;  // 2 * status_cap words
+    size_t status_cap = 0;
+    uint32_t* d_tile_counter = nullptr;
+    unsigned long long* d_totals = nullptr;  // 2 words
+    unsigned long long* h_totals = nullptr;  // pinned
+    // reductions
+    float* d_minmax = nullptr;               // 2 floats (ordered-int encoded during reduction)
+    float* h_minmax = nullptr;               // pinned
+    // control grid ("texture")
+    float* d_tex = nullptr;
+    int tex_x = 0, tex_y = 0, tex_z = 0;
+    // SVL coefficient staging
+    float* d_coef = nullptr; size_t coef_cap = 0;
+    // legacy table copies
+    unsigned int* d_tri = nullptr; unsigned int* d_nverts = nullptr;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_extract_ms = -1.f, last_field_ms = -1.f;
+};
+
+int fail(Ctx* c, const char* what, cudaError_t e);
+int fail_msg(Ctx* c, const std::string& msg);
+#define GCB_CHECK(c, call)                                          \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return gcb::fail((c), #call, e_);    \
+    } while (0)
+
+// ---- launchers implemented in the .cu files ----
+int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts);
+void host_tables(unsigned int* tri, unsigned int* nverts);
+int upload_tables_legacy(Ctx* c);
+
+// fields.cu
+int k_create_lattice(Ctx* c, float* out, unsigned nx, unsigned ny, unsigned nz, unsigned type);
+int k_sphere(Ctx* c, float* out, float3 center, float radius, float thickness, int nx, int ny, int nz, float dx, float dy, float dz, bool shell);
+int k_line(Ctx* c, float* out, float3 center, float3 axis, float radius, float tr, float ta, int nx, int ny, int nz, float dx, float dy, float dz, bool disc);
+int k_cuboid(Ctx* c, float* out, float3 center, float3 ang, float xw, float yw, float zw, int nx, int ny, int nz, float dx, float dy, float dz);
+int k_cuboid_shell(Ctx* c, float* out, float3 center, float3 ang, float xw, float yw, float zw, float th, int nx, int ny, int nz, float dx, float dy, float dz);
+int k_torus(Ctx* c, float* out, float3 center, float3 ang, float R, float rc, int nx, int ny, int nz, float dx, float dy, float dz);
+int k_cone(Ctx* c, float* out, float3 center, float3 ang, float br, float h, int nx, int ny, int nz, float dx, float dy, float dz);
+int k_cone_frustum(Ctx* c, float* out, float3 center, float3 ang, float tr, float br, float h, int nx, int ny, int nz, float dx, float dy, float dz);
+int k_pyramid_frustum(Ctx* c, float* out, float3 center, float3 ang, float xb, float xt, float yh, float zb, float zt, int nx, int ny, int nz, float dx, float dy, float dz);
+int k_minmax(Ctx* c, const float* in, size_t n, float* lo, float* hi);           // host results, reference semantics
+int k_minmax_device(Ctx* c, const float* in, size_t n);                          // leaves decoded result in c->d_minmax
+int k_normalise(Ctx* c, const float* in, float* out, size_t n, float a, float b);
+int k_normalise_four(Ctx* c, const float* in, float* mask, float* k, int nx, int ny, int nz, float a, float b, float iso1, float iso2);
+int k_refine(Ctx* c, const float* tex, int cx, int cy, int cz, float* out, int nx2, int ny2, int nz2, float dx, float dy, float dz);
+int k_grating(Ctx* c, const float* tex, int cx, int cy, int cz, float2* out, int nx2, int ny2, int nz2, float dx, float dy, float dz);
+int k_svl(Ctx* c, float* svl, const float2* grating, size_t n, int idx, const float2* coef);
+int k_svl_field(Ctx* c, float* svl, const float* phi, int nh, const float* d_coef, int cx, int cy, int czl, int cz0, int nx2, int ny2, int nz2l,
+                unsigned z0, float dx, float dy, float dz, int accumulate, float* d_minmax_raw);
+int k_minmax_init(Ctx* c, float* d_minmax_raw);
+int k_minmax_decode(Ctx* c, float* d_minmax_raw, float* d_out);
+int k_copy_parameter(Ctx* c, GridPoint* vol_one, const float* vol_two, const float* vol_lattice, bool dynamic, float iso1, float iso2,
+                     unsigned nx, unsigned ny, unsigned nz, float iso, bool u, bool d, bool i);
+int k_primitive_field(Ctx* c, const GridPoint* prim, const float* active, float* isosurf, size_t n, bool fixed, bool dynamic);
+int k_topo_field(Ctx* c, const float* topo, float* isosurf, float volfrac, size_t n);
+int k_patch_topo_field(Ctx* c, float* d, int nx, int ny, int nz, const GridPoint* vol_one);
+int k_copy_to_pitched(Ctx* c, const float* src, gcb_pitched_ptr dst, int nx, int ny, int nz);
+
+// obj_writer.cpp
+int write_obj_host(const float* pos4, unsigned int total_verts, const char* filename);
+
+} // namespace gcb

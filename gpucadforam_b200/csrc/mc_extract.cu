@@ -1,0 +1,626 @@
+// mc_extract.cu -- fused marching-cubes extraction for sm_100a.
+//
+// ONE persistent kernel replaces the reference's classify -> thrust scan -> D2H -> compact ->
+// thrust scan -> D2H -> memset -> generate sequence (src/Isosurface.cu:44-134 and its four
+// siblings; kernels src/MarchingCubes_kernel.cu:869-1063, :1427-1511, :1594-1608, :1865-2200,
+// :2625-3017, :3207-3249, :3424-3817).
+//
+// Work decomposition.  The reference orders output vertices by ascending linear cell id
+// (x fastest, then y, then z; `index = numVertsScanned[voxel] + j`, MarchingCubes_kernel.cu:2160).
+// A tile is R consecutive y-rows of one z-slice = a CONTIGUOUS range of R*(Nx-1) linear cell ids,
+// and tiles are numbered in the same linear order.  Per tile:
+//   1. stage-in : the interpolation field rows [y0, y0+R] of point slices z and z+1 are copied
+//                 global -> shared with TMA bulk copies (cp.async.bulk + mbarrier); each staged
+//                 point is turned into {value, inside-bit, id-class} (mode specific);
+//   2. classify : cube index per cell from the staged bits, vertex count from the table (smem
+//                 copy of the __constant__ table: per-lane indices diverge), warp/block totals;
+//   3. look-back: single-pass decoupled look-back over tiles publishes {active, vertex} prefixes,
+//                 so offsets are exactly the reference's exclusive scans;
+//   4. emit     : active cells append their triangles to a per-warp queue; the warp drains the
+//                 queue 32 triangles at a time (one triangle per lane, vertices interpolated from
+//                 the STAGED field) and writes float4 pos/norm at the reference's indices.
+// The field is read from HBM once; no per-cell scratch arrays are written (the reference moves
+// 36-56 B/cell through them).
+#include "common.cuh"
+
+namespace gcb {
+
+// ---------------------------------------------------------------- tables
+// Bourke triTable, 16 nibbles per case, 0xF terminator (tools/pack_mc_tables.py).
+// Reference: src/tables.h:49-307; numVertsTable (:311-569) is derived = popcount of used nibbles.
+__constant__ unsigned long long c_tri_packed[256] = {
+#include "mc_tables_packed.inc"
+};
+static const unsigned long long h_tri_packed[256] = {
+#include "mc_tables_packed.inc"
+};
+
+void host_tables(unsigned int* tri, unsigned int* nverts) {
+    for (int c = 0; c < 256; ++c) {
+        unsigned n = 0;
+        for (int j = 0; j < 16; ++j) {
+            unsigned e = (unsigned)((h_tri_packed[c] >> (4 * j)) & 15ull);
+            if (tri) tri[c * 16 + j] = (e == 15u) ? 255u : e;
+            if (e != 15u) ++n;
+        }
+        if (nverts) nverts[c] = n;
+    }
+}
+
+// ---------------------------------------------------------------- PTX helpers (TMA bulk copy + mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------- constants
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kQueue = 256;  // per-warp triangle ring (power of two, >= 31 + 32*5)
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValMask = (1ull << 62) - 1;
+
+// corner c -> (dx,dy,dz) as 3 bits; MarchingCubes_kernel.cu:889-896
+__device__ __forceinline__ uint32_t corner_bits(uint32_t c) {
+    // c: 0(000) 1(100) 2(110) 3(010) 4(001) 5(101) 6(111) 7(011)   bits: x=1,y=2,z=4
+    return (0x67542310u >> (4 * c)) & 7u;
+}
+// edge -> endpoints (a | b<<4).  lattice variants: :3751-3762 ; owner variants: :2140-2151
+__device__ __forceinline__ uint32_t edge_lat(uint32_t e) {
+    // a: 0 1 2 3 4 5 6 7 0 1 2 3   b: 1 2 3 0 5 6 7 4 4 5 6 7
+    const unsigned long long A = 0x321076543210ull, B = 0x765447650321ull;
+    return (uint32_t)((A >> (4 * e)) & 15ull) | ((uint32_t)((B >> (4 * e)) & 15ull) << 4);
+}
+__device__ __forceinline__ uint32_t edge_own(uint32_t e) {
+    // a: 0 1 3 0 4 5 7 4 0 1 2 3   b: 1 2 2 3 5 6 6 7 4 5 6 7   (first endpoint owns t_x/t_y/t_z)
+    const unsigned long long A = 0x321047540310ull, B = 0x765476653221ull;
+    return (uint32_t)((A >> (4 * e)) & 15ull) | ((uint32_t)((B >> (4 * e)) & 15ull) << 4);
+}
+// axis of the stored crossing parameter used by edge e: 0=t_x 1=t_y 2=t_z
+__device__ __forceinline__ uint32_t edge_axis(uint32_t e) { return e >= 8 ? 2u : (e & 1u); }
+
+struct Smem {
+    float* val[2];
+    unsigned char* bit[2];
+    unsigned char* cube;
+    unsigned long long* tri;
+    unsigned char* nv;
+    uint32_t* queue;      // kWarps * kQueue
+    uint32_t* warp_tot;   // kWarps * 2
+    unsigned long long* prefix;  // [0]=active prefix, [1]=vertex prefix (exclusive, for this tile)
+    uint32_t* tile_id;
+    uint64_t* mbar;
+};
+
+__device__ __forceinline__ float3 lerp3(float3 a, float3 b, float t) {
+    // commons/helper_math.h:1145-1148 `a + t*(b-a)`; the reference build (sm_100a SASS) evaluates it as
+    // FADD d=b-a ; FFMA d*t+a.  Spelled with intrinsics so no other contraction can be chosen here.
+    return make_float3(__fmaf_rn(__fsub_rn(b.x, a.x), t, a.x), __fmaf_rn(__fsub_rn(b.y, a.y), t, a.y), __fmaf_rn(__fsub_rn(b.z, a.z), t, a.z));
+}
+__device__ __forceinline__ float3 sub3(float3 a, float3 b) { return make_float3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) {  // helper_math.h:1427-1430
+    // reference SASS: FMUL second product, FFMA first product minus it
+    return make_float3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+
+// vertexInterp2_new (MarchingCubes_kernel.cu:3593-3674); t = 0 where the reference leaves it unset
+__device__ __forceinline__ float3 interp_band(float l1, float l2, float3 p0, float3 p1, float f0, float f1, uint32_t id0, uint32_t id1) {
+    float t = 0.f;
+    if ((id0 == 1u && id1 == 0u) || (id0 == 0u && id1 == 1u)) {
+        if (f1 < f0) { float3 tp = p1; p1 = p0; p0 = tp; float tf = f1; f1 = f0; f0 = tf; }
+        if ((f1 >= l1) && (f0 <= l1)) {
+            if (fabs(l1 - f0) < 0.0005) return p0;
+            if (fabs(l1 - f1) < 0.0005) return p1;
+            if (fabs(f1 - f0) < 0.0005) return p0;
+            t = __fdiv_rn(__fsub_rn(l1, f0), __fsub_rn(f1, f0));
+        } else if ((f1 >= l2) && (f0 <= l2)) {
+            if (fabs(l2 - f0) < 0.0005) return p0;
+            if (fabs(l2 - f1) < 0.0005) return p1;
+            if (fabs(f1 - f0) < 0.0005) return p0;
+            t = __fdiv_rn(__fsub_rn(l2, f0), __fsub_rn(f1, f0));
+        } else if ((f1 == f0) && (p0.z == 0.0)) t = 1;
+        else if (f1 == f0) t = 0;
+    }
+    return lerp3(p0, p1, t);
+}
+// second half of vertexInterp3_new (:3347-3413): band on the vol_two pair when ids are {2,0}
+__device__ __forceinline__ bool interp_band_two(float m1, float m2, float3& p0, float3& p1, float f2, float f3, float& t, float3& out) {
+    if (f3 < f2) { float3 tp = p1; p1 = p0; p0 = tp; float tf = f3; f3 = f2; f2 = tf; }
+    if ((f3 >= m1) && (f2 <= m1)) {
+        if (fabs(m1 - f2) < 0.0005) { out = p0; return true; }
+        if (fabs(m1 - f3) < 0.0005) { out = p1; return true; }
+        if (fabs(f3 - f2) < 0.0005) { out = p0; return true; }
+        t = __fdiv_rn(__fsub_rn(m1, f2), __fsub_rn(f3, f2));
+    } else if ((f3 >= m2) && (f2 <= m2)) {
+        if (fabs(m2 - f2) < 0.0005) { out = p0; return true; }
+        if (fabs(m2 - f3) < 0.0005) { out = p1; return true; }
+        if (fabs(f3 - f2) < 0.0005) { out = p0; return true; }
+        t = __fdiv_rn(__fsub_rn(m2, f2), __fsub_rn(f3, f2));
+    } else if ((f3 == f2) && (p0.z == 0.0)) t = 1;
+    else if (f3 == f2) t = 0;
+    return false;
+}
+__device__ __forceinline__ float blend_t(float t1, float t2, float t) {  // :1657-1668
+    if ((t1 > 0) && (t2 > 0)) t = (t1 + t2) * 0.5;
+    else if ((t1 > 0) && (t2 == 0)) t = t1;
+    else if ((t2 > 0) && (t1 == 0)) t = t2;
+    return t;
+}
+__device__ __forceinline__ float t_primitive(float iso, float f0, float f1, float et) {  // :1640-1672
+    float t2 = 0.0;
+    if (((f1 >= iso) && (f0 <= iso)) || ((f0 >= iso) && (f1 <= iso))) t2 = __fdiv_rn(__fsub_rn(iso, f0), __fsub_rn(f1, f0));
+    return blend_t(et, t2, 0);
+}
+__device__ __forceinline__ float t_primitive_one(float l1, float l2, float f0, float f1, float et) {  // :1675-1724
+    float t2 = 0.0, t3 = 0.0;
+    if (((f1 >= l1) && (f0 <= l1)) || ((f0 >= l1) && (f1 <= l1))) t2 = __fdiv_rn(__fsub_rn(l1, f0), __fsub_rn(f1, f0));
+    float t = blend_t(et, t2, 0);
+    if (((f1 >= l2) && (f0 <= l2)) || ((f0 >= l2) && (f1 <= l2))) t3 = __fdiv_rn(__fsub_rn(l2, f0), __fsub_rn(f1, f0));
+    return blend_t(et, t3, t);
+}
+__device__ __forceinline__ float t_fixed(float iso, float l1, float l2, float f0, float f1, float f2, float f3) {  // :1727-1784
+    float t1 = 0.0f, t2 = 0.0f, t3 = 0.0f, t = 0.0f;
+    if (((f0 < iso) && (f1 >= iso)) || ((f1 < iso) && (f0 >= iso))) t1 = __fdiv_rn(__fsub_rn(iso, f0), __fsub_rn(f1, f0));
+    if (((f2 < l1) && (f3 >= l1)) || ((f3 < l1) && (f2 >= l1))) t2 = __fdiv_rn(__fsub_rn(l1, f2), __fsub_rn(f3, f2));
+    if (((f2 < l2) && (f3 >= l2)) || ((f3 < l2) && (f2 >= l2))) t3 = __fdiv_rn(__fsub_rn(l2, f2), __fsub_rn(f3, f2));
+    if ((t1 > 0.0f) && (t2 > 0.0f) && (t3 == 0.0)) t = (t1 + t2) * 0.5;
+    else if ((t1 > 0.0f) && (t3 > 0.0f) && (t2 == 0.0f)) t = (t1 + t3) * 0.5;
+    else if ((t1 > 0.0) && (t2 == 0.0) && (t3 == 0.0)) t = t1;
+    else if ((t2 > 0.0) && (t1 == 0.0) && (t3 == 0.0)) t = t2;
+    else if ((t3 > 0.0) && (t1 == 0.0) && (t2 == 0.0)) t = t3;
+    return t;
+}
+__device__ __forceinline__ float t_analysis(float iso, float f0, float f1, float et) {  // :1787-1820
+    float t2 = 0.0;
+    if (((f1 >= iso) && (f0 < iso)) || ((f0 >= iso) && (f1 < iso))) t2 = __fdiv_rn(__fsub_rn(iso, f0), __fsub_rn(f1, f0));
+    return blend_t(et, t2, 0);
+}
+
+// ---------------------------------------------------------------- stage-in: one grid point -> {value, bits}
+// bits: [1:0] id class of the mask value (0:==0, 1:==1, 2:==2, 3:other), [2] inside flag.
+template <int MODE>
+__device__ __forceinline__ void stage_point(const McArgs& A, size_t gi, uint32_t x, uint32_t y, uint32_t zl, float raw, float& val,
+                                            uint32_t& bits) {
+    if (MODE == M_LATTICE_ONE || MODE == M_LATTICE) {
+        const float m = __ldg(A.f1 + gi);  // mask `vol`; classifyVoxel_new :3232-3239
+        uint32_t id = (m == 1.f) ? 1u : (m == 0.f) ? 0u : (m == 2.f) ? 2u : 3u;
+        bits = id | ((m < A.iso) ? 4u : 0u);
+        val = raw;  // k `vol_one`
+    } else if (MODE == M_BAND_RAW) {
+        // device_bufferfour (Gratings.cu:1089-1134) fused; domain faces use GLOBAL coordinates
+        float k = __fdiv_rn(__fsub_rn(raw, A.na), __fsub_rn(A.nb, A.na));
+        float m;
+        const uint32_t gz = zl + A.gz0;
+        if (x == 0 || x == A.nx - 1 || y == 0 || y == A.ny - 1 || gz == 0 || gz == A.gnz - 1) { m = 0.0f; k = 0.0f; }
+        else m = ((k >= A.iso1) && (k <= A.iso2)) ? 1.0f : 0.0f;
+        bits = (m == 1.f ? 1u : 0u) | ((m < A.iso) ? 4u : 0u);
+        val = k;
+    } else if (MODE == M_TOPO) {
+        // classifyVoxel_kernel_topo :1492-1499
+        const float fx = A.gp ? (float)A.gp[gi].val : 0.f;
+        bits = ((fx < A.iso1) | (raw >= A.iso)) ? 4u : 0u;
+        val = raw;
+    } else {  // M_CSG  classifyVoxel :922-1052
+        const float iso = A.iso;
+        const float fx = A.gp ? (float)A.gp[gi].val : 0.f;
+        const float dy = raw;
+        const bool fixed = A.flags & F_FIXED, dyn = A.flags & F_DYNAMIC;
+        float la = 0.f;
+        if ((fixed || dyn) && A.f1) la = __ldg(A.f1 + gi);
+        const bool inb = (la > A.iso1) & (la < A.iso2);
+        bool b = false;
+        if (A.flags & F_MAKE_REGION) b = fx < iso;
+        else if (A.flags & F_UNION) b = fixed ? ((dy < iso) | inb) : dyn ? ((fx < iso) | inb) : ((fx < iso) | (dy < iso));
+        else if (A.flags & F_DIFF) b = fixed ? ((dy >= iso) & inb) : dyn ? ((fx < iso) & ((la < A.iso1) | (la > A.iso2))) : ((dy >= iso) & (fx < iso));
+        else if (A.flags & F_INTERSECT) b = fixed ? ((dy < iso) & inb) : dyn ? ((fx < iso) & inb) : ((fx < iso) & (dy < iso));
+        bits = b ? 4u : 0u;
+        val = raw;
+    }
+}
+
+// ---------------------------------------------------------------- one triangle
+template <int MODE>
+__device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, uint32_t z, uint32_t y0, uint32_t c, uint32_t j,
+                                              unsigned long long vidx) {
+    const uint32_t r = c / A.cx, x = c - r * A.cx;
+    const uint32_t cube = S.cube[c];
+    const unsigned long long tri = S.tri[cube];
+    const uint32_t y = y0 + r;
+    // MarchingCubes_kernel.cu:1888-1890 : (uint -> float) - center, times voxel
+    const float3 p = make_float3(__fmul_rn(__fsub_rn((float)x, A.center.x), A.voxel.x), __fmul_rn(__fsub_rn((float)y, A.center.y), A.voxel.y),
+                                 __fmul_rn(__fsub_rn((float)(z + A.gz0), A.center.z), A.voxel.z));  // global z under slab sharding
+
+    float3 v[3];
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t e = (uint32_t)(tri >> (4 * (3 * j + k))) & 15u;
+        const bool own = (MODE == M_TOPO) || (MODE == M_CSG && !(A.flags & F_FIXED));
+        const uint32_t ab = own ? edge_own(e) : edge_lat(e);
+        const uint32_t ca = corner_bits(ab & 15u), cb = corner_bits(ab >> 4);
+        // corner positions: v[0] = p, v[i] = p + (voxel or 0) per component (:1892-1900)
+        float3 pa = p, pb = p;
+        if (ca) pa = make_float3(__fadd_rn(p.x, (ca & 1u) ? A.voxel.x : 0.f), __fadd_rn(p.y, (ca & 2u) ? A.voxel.y : 0.f), __fadd_rn(p.z, (ca & 4u) ? A.voxel.z : 0.f));
+        if (cb) pb = make_float3(__fadd_rn(p.x, (cb & 1u) ? A.voxel.x : 0.f), __fadd_rn(p.y, (cb & 2u) ? A.voxel.y : 0.f), __fadd_rn(p.z, (cb & 4u) ? A.voxel.z : 0.f));
+        const uint32_t sa = (r + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u), sb = (r + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
+        const uint32_t za = (ca >> 2) & 1u, zb = (cb >> 2) & 1u;
+        const float fa = (za ? S.val[1] : S.val[0])[sa], fb = (zb ? S.val[1] : S.val[0])[sb];
+        w[k] = 0.f;
+        if (MODE == M_LATTICE_ONE || MODE == M_BAND_RAW) {
+            v[k] = interp_band(A.iso1, A.iso2, pa, pb, fa, fb, ((za ? S.bit[1] : S.bit[0])[sa] & 3u), ((zb ? S.bit[1] : S.bit[0])[sb] & 3u));
+        } else if (MODE == M_LATTICE) {
+            const uint32_t ida = ((za ? S.bit[1] : S.bit[0])[sa] & 3u), idb = ((zb ? S.bit[1] : S.bit[0])[sb] & 3u);
+            if ((ida == 2u && idb == 0u) || (idb == 2u && ida == 0u)) {
+                // ids {2,0}: first block of vertexInterp3_new does not fire, second one does
+                const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
+                const size_t gb = ((size_t)(z + zb) * A.ny + y + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
+                float t = 0.f;
+                float3 out;
+                float3 q0 = pa, q1 = pb;
+                if (interp_band_two(A.iso1b, A.iso2b, q0, q1, __ldg(A.f2 + ga), __ldg(A.f2 + gb), t, out)) v[k] = out;
+                else v[k] = lerp3(q0, q1, t);
+            } else v[k] = interp_band(A.iso1, A.iso2, pa, pb, fa, fb, ida, idb);
+        } else {
+            const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
+            const size_t gb = ((size_t)(z + zb) * A.ny + y + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
+            float et = 0.f;
+            if (own && A.gp) {
+                const GridPoint g = A.gp[ga];
+                const uint32_t ax = edge_axis(e);
+                et = ax == 0 ? g.t_x : ax == 1 ? g.t_y : g.t_z;
+            }
+            float t;
+            if (MODE == M_TOPO) {
+                t = t_analysis(A.iso, fa, fb, et);
+                w[k] = A.f1 ? __ldg(A.f1 + ga) : 0.f;  // *field_val = r0 (:1797)
+                if (A.flags & F_DISP) {
+                    const float4 d0 = A.disp[ga], d1 = A.disp[gb];
+                    pa = make_float3(d0.x, d0.y, d0.z);
+                    pb = make_float3(d1.x, d1.y, d1.z);
+                }
+            } else if (A.flags & F_MAKE_REGION) t = et;
+            else if (A.flags & F_FIXED) t = t_fixed(A.iso, A.iso1, A.iso2, fa, fb, __ldg(A.f1 + ga), __ldg(A.f1 + gb));
+            else if (A.flags & F_DYNAMIC) t = t_primitive_one(A.iso1, A.iso2, __ldg(A.f1 + ga), __ldg(A.f1 + gb), et);
+            else t = t_primitive(A.iso, fa, fb, et);
+            v[k] = lerp3(pa, pb, t);
+        }
+    }
+    float3 n;
+    if (MODE == M_CSG) {  // calcNormal(ver0, ver2, ver1), w = 0.5 (:2178-2185)
+        n = cross3(sub3(v[2], v[0]), sub3(v[1], v[0]));
+        w[0] = w[1] = w[2] = 0.5f;
+    } else {
+        n = cross3(sub3(v[1], v[0]), sub3(v[2], v[0]));
+    }
+    const unsigned long long limit = (unsigned long long)((unsigned int)A.max_verts - 3u);  // uint wrap as :2181
+    const bool ok = (A.max_verts > 0xffffffffull) ? (vidx + 3 <= A.max_verts) : (vidx < limit);
+    if (ok) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            __stcs(A.pos + vidx + k, make_float4(v[k].x, v[k].y, v[k].z, 1.0f));
+            __stcs(A.norm + vidx + k, make_float4(n.x, n.y, n.z, w[k]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem S;
+    {
+        unsigned char* p = smem_raw;
+        S.val[0] = (float*)p; p += (size_t)A.prow_stride * 4;
+        S.val[1] = (float*)p; p += (size_t)A.prow_stride * 4;
+        S.tri = (unsigned long long*)p; p += 256 * 8;
+        S.prefix = (unsigned long long*)p; p += 16;
+        S.mbar = (uint64_t*)p; p += 8;
+        S.tile_id = (uint32_t*)p; p += 8;
+        S.queue = (uint32_t*)p; p += kWarps * kQueue * 4;
+        S.warp_tot = (uint32_t*)p; p += kWarps * 2 * 4;
+        S.nv = p; p += 256;
+        S.bit[0] = p; p += A.prow_stride;
+        S.bit[1] = p; p += A.prow_stride;
+        S.cube = p;
+    }
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    for (uint32_t i = tid; i < 256; i += kThreads) {
+        const unsigned long long t = c_tri_packed[i];
+        S.tri[i] = t;
+        // number of used nibbles = numVertsTable[i]
+        unsigned long long u = ~t;                      // used nibble != 0xF  <=> ~nibble != 0
+        u = (u | (u >> 1) | (u >> 2) | (u >> 3)) & 0x1111111111111111ull;
+        S.nv[i] = (unsigned char)__popcll(u);
+    }
+    if (tid == 0) { mbar_init(S.mbar, 1); fence_mbar_init(); }
+    __syncthreads();
+
+    uint32_t parity = 0;
+    const uint32_t slice_pts = A.nx * A.ny;
+
+    for (;;) {
+        if (tid == 0) *S.tile_id = atomicAdd(A.tile_counter, 1u);
+        __syncthreads();  // also orders the previous tile's smem reads before this tile's writes
+        const uint32_t tile = *S.tile_id;
+        if (tile >= A.num_tiles) break;
+        const uint32_t z = tile / A.tiles_per_slice, ty = tile - z * A.tiles_per_slice;
+        const uint32_t y0 = ty * A.rows_per_tile;
+        const uint32_t rows = min(A.rows_per_tile, A.cy - y0);
+        const uint32_t npts = (rows + 1) * A.nx;   // staged points per slice
+        const uint32_t ncell = rows * A.cx;
+        const size_t g0 = (size_t)z * slice_pts + (size_t)y0 * A.nx;  // first staged point, slice z
+
+        // ---- 1. stage-in
+        if (A.use_tma && A.f0) {
+            if (tid == 0) {
+                fence_proxy_async();  // generic-proxy accesses of the previous tile precede the async writes
+                mbar_expect_tx(S.mbar, 2u * npts * 4u);
+                tma_bulk_g2s(S.val[0], A.f0 + g0, npts * 4u, S.mbar);
+                tma_bulk_g2s(S.val[1], A.f0 + g0 + slice_pts, npts * 4u, S.mbar);
+            }
+            mbar_wait(S.mbar, parity);
+            parity ^= 1u;
+        }
+#pragma unroll 1
+        for (uint32_t s = 0; s < 2; ++s) {
+            float* sv = s ? S.val[1] : S.val[0];
+            unsigned char* sb = s ? S.bit[1] : S.bit[0];
+            const size_t gs = g0 + (size_t)s * slice_pts;
+            for (uint32_t pnt = tid; pnt < npts; pnt += kThreads) {
+                const uint32_t rr = pnt / A.nx, x = pnt - rr * A.nx;
+                float raw;
+                if (A.use_tma && A.f0) raw = sv[pnt];
+                else raw = A.f0 ? __ldg(A.f0 + gs + pnt) : 0.f;
+                float val;
+                uint32_t bits;
+                stage_point<MODE>(A, gs + pnt, x, y0 + rr, z + s, raw, val, bits);
+                sv[pnt] = val;
+                sb[pnt] = (unsigned char)bits;
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. classify: cube index + counts.  Warp w owns a contiguous cell range of the tile.
+        const uint32_t seg = (((ncell + kWarps - 1) / kWarps) + 31u) & ~31u;
+        const uint32_t cbeg = min(warp * seg, ncell), cend = min(cbeg + seg, ncell);
+        uint32_t my_verts = 0, my_act = 0;
+        {
+            uint32_t c = cbeg + lane;
+            uint32_t r = c / A.cx, x = c - r * A.cx;
+            for (; c < cend; c += 32) {
+                const uint32_t pi = r * A.nx + x;
+                const unsigned char* b0 = S.bit[0] + pi;
+                const unsigned char* b1 = S.bit[1] + pi;
+                uint32_t cube = ((b0[0] >> 2) & 1u) | (((b0[1] >> 2) & 1u) << 1) | (((b0[A.nx + 1] >> 2) & 1u) << 2) | (((b0[A.nx] >> 2) & 1u) << 3) |
+                                (((b1[0] >> 2) & 1u) << 4) | (((b1[1] >> 2) & 1u) << 5) | (((b1[A.nx + 1] >> 2) & 1u) << 6) | (((b1[A.nx] >> 2) & 1u) << 7);
+                S.cube[c] = (unsigned char)cube;
+                const uint32_t nv = S.nv[cube];
+                my_verts += nv;
+                my_act += nv > 0;
+                x += 32;
+                while (x >= A.cx) { x -= A.cx; ++r; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            my_verts += __shfl_xor_sync(0xffffffffu, my_verts, o);
+            my_act += __shfl_xor_sync(0xffffffffu, my_act, o);
+        }
+        if (lane == 0) { S.warp_tot[2 * warp] = my_verts; S.warp_tot[2 * warp + 1] = my_act; }
+        __syncthreads();
+
+        // ---- 3. decoupled look-back (warp 0)
+        if (warp == 0) {
+            uint32_t tv = 0, ta = 0;
+            for (int w2 = 0; w2 < kWarps; ++w2) { tv += S.warp_tot[2 * w2]; ta += S.warp_tot[2 * w2 + 1]; }
+            if (A.count_only) {
+                if (lane == 0 && (tv | ta)) { atomicAdd(A.totals, (unsigned long long)ta); atomicAdd(A.totals + 1, (unsigned long long)tv); }
+            } else {
+                unsigned long long pa = 0, pv = 0;  // exclusive prefixes
+                if (tile > 0) {
+                    if (lane == 0) { st_relaxed(A.status_a + tile, kFlagAgg | ta); st_relaxed(A.status_v + tile, kFlagAgg | tv); }
+                    int64_t base = (int64_t)tile - 1;
+                    for (;;) {
+                        const int64_t idx = base - lane;
+                        unsigned long long wa, wv;
+                        if (idx >= 0) {
+                            do {
+                                wa = ld_relaxed(A.status_a + idx);
+                                wv = ld_relaxed(A.status_v + idx);
+                            } while ((wa >> 62) == 0ull || (wa >> 62) != (wv >> 62));
+                        } else { wa = kFlagIncl; wv = kFlagIncl; }  // before tile 0: inclusive prefix 0
+                        const uint32_t incl = __ballot_sync(0xffffffffu, (wa >> 62) == 2ull);
+                        const uint32_t upto = incl ? (uint32_t)__ffs(incl) : 32u;  // lanes [0, upto) contribute
+                        unsigned long long ca = (lane < upto) ? (wa & kValMask) : 0ull, cv = (lane < upto) ? (wv & kValMask) : 0ull;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            ca += __shfl_xor_sync(0xffffffffu, ca, o);
+                            cv += __shfl_xor_sync(0xffffffffu, cv, o);
+                        }
+                        pa += ca; pv += cv;
+                        if (incl) break;
+                        base -= 32;
+                    }
+                }
+                if (lane == 0) {
+                    st_relaxed(A.status_a + tile, kFlagIncl | (pa + ta));
+                    st_relaxed(A.status_v + tile, kFlagIncl | (pv + tv));
+                    S.prefix[0] = pa; S.prefix[1] = pv;
+                    if (tile == A.num_tiles - 1) { A.totals[0] = pa + ta; A.totals[1] = pv + tv; }
+                }
+            }
+        }
+        if (A.count_only) continue;  // next iteration's first __syncthreads orders smem reuse
+        __syncthreads();
+
+        // ---- 4. emit
+        unsigned long long act_base = S.prefix[0], vert_base = S.prefix[1];
+        for (uint32_t w2 = 0; w2 < warp; ++w2) { vert_base += S.warp_tot[2 * w2]; act_base += S.warp_tot[2 * w2 + 1]; }
+        if (S.warp_tot[2 * warp] != 0 || A.st_verts) {
+            uint32_t* q = S.queue + warp * kQueue;
+            uint32_t head = 0, tail = 0, act_run = 0;  // triangles consumed / enqueued, active cells seen
+            const size_t cell0 = (size_t)z * A.cx * A.cy + (size_t)y0 * A.cx;  // global id of tile cell 0 (local slab)
+            for (uint32_t cb = cbeg; cb < cend; cb += 32) {
+                const uint32_t c = cb + lane;
+                const bool valid = c < cend;
+                const uint32_t nv = valid ? S.nv[S.cube[c]] : 0u;
+                const uint32_t nt = (nv * 11u) >> 5;  // nv / 3 for nv in {0,3,..,15}
+                uint32_t incl = nt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t n2 = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (uint32_t)o) incl += n2;
+                }
+                const uint32_t excl = incl - nt;
+                const uint32_t step_tris = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t amask = __ballot_sync(0xffffffffu, nv > 0);
+                const uint32_t rank = __popc(amask & ((1u << lane) - 1u));
+                if (nv > 0 && A.comp) A.comp[act_base + act_run + rank] = (uint32_t)(cell0 + c) + A.gz0 * A.cx * A.cy;
+                if (A.st_verts && valid) {
+                    const size_t gc = cell0 + c;
+                    A.st_verts[gc] = nv;
+                    A.st_occ[gc] = nv > 0;
+                    A.st_verts_scan[gc] = (uint32_t)(vert_base + 3ull * (tail + excl));
+                    A.st_occ_scan[gc] = (uint32_t)(act_base + act_run + rank);
+                }
+                for (uint32_t jj = 0; jj < nt; ++jj) q[(tail + excl + jj) & (kQueue - 1)] = (jj << 28) | c;
+                tail += step_tris;
+                act_run += __popc(amask);
+                __syncwarp();
+                while (tail - head >= 32u) {
+                    const uint32_t ent = q[(head + lane) & (kQueue - 1)];
+                    emit_triangle<MODE>(A, S, z, y0, ent & 0x0fffffffu, ent >> 28, vert_base + 3ull * (head + lane));
+                    head += 32u;
+                }
+                __syncwarp();
+            }
+            if (lane < tail - head) {
+                const uint32_t ent = q[(head + lane) & (kQueue - 1)];
+                emit_triangle<MODE>(A, S, z, y0, ent & 0x0fffffffu, ent >> 28, vert_base + 3ull * (head + lane));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+template <int MODE>
+static cudaError_t launch_mode(const McArgs& a, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(mc_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    mc_fused_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static int occupancy(size_t smem) {
+    int n = 0;
+    cudaFuncSetAttribute(mc_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_fused_kernel<MODE>, kThreads, smem);
+    return n;
+}
+
+int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts) {
+    if (a.nx < 2 || a.ny < 2 || a.nz < 2) { *active = 0; *verts = 0; return 0; }
+    a.cx = a.nx - 1; a.cy = a.ny - 1; a.cz = a.nz - 1;
+    // tile height: ~4096 cells per tile, staged rows must fit in shared memory
+    uint32_t R = 4096u / a.cx;
+    if (R < 1) R = 1;
+    if (R > a.cy) R = a.cy;
+    const size_t fixed_bytes = 256 * 8 + 16 + 8 + 8 + kWarps * kQueue * 4 + kWarps * 8 + 256 + 256 /*slack*/;
+    auto smem_for = [&](uint32_t r) {
+        const size_t stride = (((size_t)(r + 1) * a.nx) + 15) & ~(size_t)15;
+        return stride * 4 * 2 + stride * 2 + (size_t)r * a.cx + 16 + fixed_bytes;
+    };
+    while (R > 1 && smem_for(R) > 100 * 1024) --R;
+    const size_t smem = smem_for(R);
+    if (smem > 227 * 1024) return fail_msg(c, "grid row too wide for one shared-memory tile (nx too large)");
+    if ((size_t)R * a.cx >= (1u << 28)) return fail_msg(c, "tile too large");
+    a.rows_per_tile = R;
+    a.tiles_per_slice = (a.cy + R - 1) / R;
+    const unsigned long long nt = (unsigned long long)a.tiles_per_slice * a.cz;
+    if (nt >= 0xffffffffull) return fail_msg(c, "too many tiles");
+    a.num_tiles = (uint32_t)nt;
+    a.prow_stride = (uint32_t)((((size_t)(R + 1) * a.nx) + 15) & ~(size_t)15);
+    // TMA bulk copies need 16-byte aligned global addresses and sizes
+    a.use_tma = !(c->options & GCB_OPT_NO_TMA) && a.f0 && (a.nx % 4 == 0) && (((uintptr_t)a.f0 & 15) == 0);
+
+    if (c->status_cap < a.num_tiles) {
+        if (c->d_status) cudaFree(c->d_status);
+        c->status_cap = (size_t)a.num_tiles + 1024;
+        GCB_CHECK(c, cudaMalloc(&c->d_status, c->status_cap * 2 * sizeof(unsigned long long)));
+    }
+    a.status_a = c->d_status;
+    a.status_v = c->d_status + c->status_cap;
+    a.tile_counter = c->d_tile_counter;
+    a.totals = c->d_totals;
+    if (!a.count_only) {
+        GCB_CHECK(c, cudaMemsetAsync(a.status_a, 0, (size_t)a.num_tiles * 8, c->stream));
+        GCB_CHECK(c, cudaMemsetAsync(a.status_v, 0, (size_t)a.num_tiles * 8, c->stream));
+    }
+    GCB_CHECK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), c->stream));
+    GCB_CHECK(c, cudaMemsetAsync(c->d_totals, 0, 2 * sizeof(unsigned long long), c->stream));
+
+    int occ = 1;
+    switch (a.mode) {
+    case M_LATTICE_ONE: occ = occupancy<M_LATTICE_ONE>(smem); break;
+    case M_LATTICE: occ = occupancy<M_LATTICE>(smem); break;
+    case M_CSG: occ = occupancy<M_CSG>(smem); break;
+    case M_TOPO: occ = occupancy<M_TOPO>(smem); break;
+    case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem); break;
+    default: return fail_msg(c, "bad mode");
+    }
+    if (occ < 1) return fail_msg(c, "extraction kernel does not fit on an SM");
+    // persistent grid: every CTA resident (required by the look-back's forward progress)
+    long long grid = (long long)occ * c->num_sms;
+    if (grid > (long long)a.num_tiles) grid = a.num_tiles;
+
+    if (c->timing) cudaEventRecord(c->ev[0], c->stream);
+    cudaError_t e;
+    switch (a.mode) {
+    case M_LATTICE_ONE: e = launch_mode<M_LATTICE_ONE>(a, (int)grid, smem, c->stream); break;
+    case M_LATTICE: e = launch_mode<M_LATTICE>(a, (int)grid, smem, c->stream); break;
+    case M_CSG: e = launch_mode<M_CSG>(a, (int)grid, smem, c->stream); break;
+    case M_TOPO: e = launch_mode<M_TOPO>(a, (int)grid, smem, c->stream); break;
+    default: e = launch_mode<M_BAND_RAW>(a, (int)grid, smem, c->stream); break;
+    }
+    if (e != cudaSuccess) return fail(c, "mc_fused_kernel launch", e);
+    c->launches++;
+    if (c->timing) cudaEventRecord(c->ev[1], c->stream);
+    GCB_CHECK(c, cudaMemcpyAsync(c->h_totals, c->d_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    GCB_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->timing) cudaEventElapsedTime(&c->last_extract_ms, c->ev[0], c->ev[1]);
+    *active = c->h_totals[0];
+    *verts = c->h_totals[0] ? c->h_totals[1] : 0;  // early-out of Isosurface.cu:83-87
+    return 0;
+}
+
+} // namespace gcb

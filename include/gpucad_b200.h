@@ -1,0 +1,211 @@
+/*
+ * gpucad_b200.h -- C ABI of the B200-native implicit-field + marching-cubes engine.
+ *
+ * Drop-in boundary for ONE path of DESIGN4ADDITIVE/GPUCADforAM: implicit field on a voxel grid
+ * -> classify -> scan -> compact -> triangles + normals (-> .obj).  The reference has no FFI
+ * layer; its boundary is the set of C++ member functions `Multitopo` (src/main.cu) calls with
+ * raw device pointers.  Every "legacy" entry point below keeps the parameter ORDER, buffer
+ * LAYOUTS and result semantics of the reference method it replaces (cited per function), with
+ * CUDA vector types replaced by layout-identical PODs and `bool` by int.  All pointers named
+ * d_* / documented "device" are CUDA device pointers owned by the caller; the library never
+ * frees or reallocates them.  Results the reference returns through host pointers
+ * (activeVoxels, totalVerts, nfacets) are written to host pointers here as well.
+ *
+ * Errors: every function returns 0 on success, non-zero on failure (gcb_last_error() gives the
+ * text).  The reference prints and exit(1)s (commons/helper_cuda.h:583-612); a C++ shim that
+ * wants that behaviour wraps the return code.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GPUCAD_B200_H
+#define GPUCAD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* layout-identical to CUDA's uint3 / float3 / float2 / float4 / cudaPitchedPtr */
+typedef struct gcb_uint3 { unsigned int x, y, z; } gcb_uint3;
+typedef struct gcb_float3 { float x, y, z; } gcb_float3;
+typedef struct gcb_pitched_ptr { void* ptr; size_t pitch, xsize, ysize; } gcb_pitched_ptr;
+/* reference: struct grid_points, src/MarchingCubes_kernel.h:12-18 (16-byte AoS) */
+typedef struct gcb_grid_points { int val; float t_x, t_y, t_z; } gcb_grid_points;
+
+typedef struct gcb_ctx gcb_ctx;
+
+/* ------------------------------------------------------------------ context */
+/* stream: a cudaStream_t (NULL = legacy default stream, as the reference uses). */
+int gcb_create(gcb_ctx** ctx, int device, void* stream);
+int gcb_destroy(gcb_ctx* ctx);
+const char* gcb_last_error(gcb_ctx* ctx);
+int gcb_set_stream(gcb_ctx* ctx, void* stream);
+/* option flags */
+enum {
+    GCB_OPT_FILL_STAGE_ARRAYS = 1, /* also write d_voxelVerts/_Scan/d_voxelOccupied/_Scan (parity tests) */
+    GCB_OPT_LEGACY_MEMSET = 2,     /* cudaMemset(pos/norm, 0, maxVerts BYTES) as Isosurface.cu:120-121 (default on) */
+    GCB_OPT_NO_TMA = 4             /* force the LDG stage-in path (debug / A-B measurement) */
+};
+int gcb_set_options(gcb_ctx* ctx, unsigned int flags);
+/* number of kernels this library launched on the context since creation / last reset */
+unsigned long long gcb_launch_count(gcb_ctx* ctx);
+void gcb_reset_launch_count(gcb_ctx* ctx);
+/* device time (ms) of the extraction kernel of the last extraction call, measured with CUDA
+ * events on the context's stream; < 0 if timing was not enabled */
+int gcb_enable_kernel_timing(gcb_ctx* ctx, int on);
+float gcb_last_extract_kernel_ms(gcb_ctx* ctx);
+float gcb_last_field_kernel_ms(gcb_ctx* ctx);
+
+/* MarchingCubeCuda::allocateTextures_s / destroyAllTextureObjects (MarchingCubes_kernel.cu:24-75).
+ * The tables live in __constant__ memory of this library; these exist for call-sequence parity
+ * and additionally hand back device copies in the reference's uint32 layout. */
+int gcb_allocateTextures_s(gcb_ctx* ctx, unsigned int** d_triTable, unsigned int** d_numVertsTable);
+int gcb_destroyAllTextureObjects(gcb_ctx* ctx);
+/* host copies of the tables: tri[256*16] (255 = end), nverts[256] */
+void gcb_tables(unsigned int* tri, unsigned int* nverts);
+
+/* ------------------------------------------------------------------ extraction (legacy signatures) */
+/* Isosurface::computeIsosurface  (src/Isosurface.h:28-33, Isosurface.cu:44-134) -- CSG / primitives */
+int gcb_computeIsosurface(gcb_ctx* ctx, float* vol, gcb_uint3 raster_grid, void* pos, void* norm, float isoValue,
+    unsigned int numVoxels, unsigned int* d_voxelVerts, unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied,
+    unsigned int* d_voxelOccupiedScan, gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask,
+    gcb_float3 voxelSize, gcb_float3 gridcenter, unsigned int* activeVoxels, unsigned int* totalVerts,
+    unsigned int* d_compVoxelArray, unsigned int maxVerts, gcb_grid_points* primitive_fixed, float* primitive_dynamic,
+    float* topo_field, float* lattice_field, float iso1, float iso2, int obj_union, int obj_diff, int obj_intersect,
+    int primitive, int topo, int compute_lattice, int fixed, int dynamic, int make_region, size_t* nfacets);
+
+/* Isosurface::computeIsosurface_lattice  (Isosurface.h:60-64, Isosurface.cu:401-486) */
+int gcb_computeIsosurface_lattice(gcb_ctx* ctx, float* vol, void* pos, void* norm, float isoValue, unsigned int numVoxels,
+    unsigned int* d_voxelVerts, unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan,
+    gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter,
+    unsigned int* activeVoxels, unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts,
+    float* vol_one, float* vol_two, float isovalue1, float isovalue2, float iso1, float iso2);
+
+/* Isosurface::computeIsosurface_latticeone  (Isosurface.h:66-70, Isosurface.cu:488-572) */
+int gcb_computeIsosurface_latticeone(gcb_ctx* ctx, float* vol, void* pos, void* norm, float isoValue, unsigned int numVoxels,
+    unsigned int* d_voxelVerts, unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan,
+    gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter,
+    unsigned int* activeVoxels, unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts,
+    float* vol_one, float isovalue1, float isovalue2);
+
+/* Isosurface::computeIsosurface_2  (Isosurface.h:46-50, Isosurface.cu:323-398) */
+int gcb_computeIsosurface_2(gcb_ctx* ctx, void* pos, void* norm, float isoValue, unsigned int numVoxels,
+    unsigned int* d_voxelVerts, unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan,
+    gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter,
+    unsigned int* activeVoxels, unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts,
+    gcb_grid_points* vol_topo, gcb_grid_points* vol_one, float* vol_two, float* d_solid, float isovalue1, float* d_result,
+    void* triangle_data);
+
+/* Isosurface::computeIsosurface_topo  (Isosurface.h:53-58, Isosurface.cu:243-320) */
+int gcb_computeIsosurface_topo(gcb_ctx* ctx, void* pos, void* norm, float isoValue, unsigned int numVoxels,
+    unsigned int* d_voxelVerts, unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan,
+    gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter,
+    unsigned int* activeVoxels, unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts,
+    gcb_grid_points* vol_topo, gcb_grid_points* vol_one, float* vol_two, float* d_solid, float isovalue1, float* d_result,
+    void* triangle_data, int disp, void* disp_two);
+
+/* Isosurface::copy_parameter  (Isosurface.h:19-21, Isosurface.cu:15-27; kernel MarchingCubes_kernel.cu:158-447) */
+int gcb_copy_parameter(gcb_ctx* ctx, unsigned int* voxel_verts, float isoValue, gcb_uint3 gridSize, gcb_uint3 gridSizeShift,
+    gcb_uint3 gridSizeMask, gcb_float3 voxelSize, unsigned int numVoxels, gcb_grid_points* vol_one, float* vol_two,
+    float* vol_lattice, int fixed, int dynamic, float iso1, float iso2, int obj_union, int obj_diff, int obj_intersect);
+
+/* Isosurface::patch_topo_field  (Isosurface.h:74, Isosurface.cu:674-722) */
+int gcb_patch_topo_field(gcb_ctx* ctx, float* d_vec1, int Nx, int Ny, int Nz, gcb_grid_points* vol_one);
+
+/* ------------------------------------------------------------------ field producers (legacy signatures) */
+/* Modelling::* (src/Modelling.h:26-40, kernels Modelling.cu:244-750) */
+int gcb_distance_from_line(gcb_ctx* ctx, float* data_1, gcb_float3 center, gcb_float3 axis, float radius_1, float thickness_radial,
+    float thickness_axial, int Nx, int Ny, int Nz, float dx, float dy, float dz, int cylind_disc_selected);
+int gcb_sphere_with_center(gcb_ctx* ctx, float* data_1, gcb_float3 center, float radius_1, float thickness_wall, int Nx, int Ny, int Nz,
+    float dx, float dy, float dz, int sphere_shell_selected);
+int gcb_cuboid(gcb_ctx* ctx, float* data_1, gcb_float3 center, gcb_float3 angles, float x_width, float y_width, float z_width,
+    int Nx, int Ny, int Nz, float dx, float dy, float dz);
+int gcb_cuboid_shell(gcb_ctx* ctx, float* data_1, gcb_float3 center, gcb_float3 angles, float x_width, float y_width, float z_width,
+    float thickness, int Nx, int Ny, int Nz, float dx, float dy, float dz);
+int gcb_torus_with_center(gcb_ctx* ctx, float* data_1, gcb_float3 center, gcb_float3 angles, float torus_radius,
+    float torus_circle_radius, int Nx, int Ny, int Nz, float dx, float dy, float dz);
+int gcb_cone_with_base_radius_height(gcb_ctx* ctx, float* data_1, gcb_float3 center, gcb_float3 angles, float base_radius,
+    float cone_height, int Nx, int Ny, int Nz, float dx, float dy, float dz);
+int gcb_cone_frustum(gcb_ctx* ctx, float* data_1, gcb_float3 center, gcb_float3 angles, float top_radius, float bottom_radius,
+    float cone_frustum_height, int Nx, int Ny, int Nz, float dx, float dy, float dz);
+int gcb_pyramid_frustum(gcb_ctx* ctx, float* data_1, gcb_float3 center, gcb_float3 angles, float x_width_base, float x_width_top,
+    float y_height, float z_width_base, float z_width_top, int Nx, int Ny, int Nz, float dx, float dy, float dz);
+
+/* Fft_lattice::create_lattice (lattice_files/Fft_lattice.h:15, Fft_lattice.cu:12-74) */
+int gcb_create_lattice(gcb_ctx* ctx, float* d_latticevol, unsigned int NX, unsigned int NY, unsigned int NZ, unsigned int size,
+    unsigned int lattice_type_index);
+
+/* Gratings::* (lattice_files/Gratings.h:46-77) */
+int gcb_GPU_buffer_normalise_buffer(gcb_ctx* ctx, float* d_vec1, float* d_vec2, int n);               /* Gratings.cu:1500-1537 */
+int gcb_GPU_buffer_normalise_four(gcb_ctx* ctx, float* dataone, float* datatwo, float* datathree, size_t size, int Nx, int Ny,
+    int Nz, float isoval_1, float isoval_2);                                                            /* Gratings.cu:1579-1617 */
+int gcb_grating(gcb_ctx* ctx, void* dvol /*float2*/, int NX2, int NY2, int NZ2, float dx2, float dy2, float dz2); /* :976-982 */
+int gcb_refine(gcb_ctx* ctx, float* dvol, int NX2, int NY2, int NZ2, float dx, float dy, float dz);   /* :984-990 */
+int gcb_svl(gcb_ctx* ctx, float* d_svl, void* d_grating /*float2*/, int NX, int NY, int NZ, int indxx, void* data_fft /*float2*/); /* :992-998 */
+int gcb_topo_field(gcb_ctx* ctx, float* topo_field, float* isosurf, float volfrac, int NX, int NY, int NZ); /* :1685-1692 */
+int gcb_primitive_field(gcb_ctx* ctx, gcb_grid_points* primitive_field, float* primitive_active, float* isosurf, float isoval,
+    int fixed, int active, int NX, int NY, int NZ);                                                     /* :1727-1735 */
+
+/* Interpolations::* (src/Interpolations.h:18-32, Interpolations.cu:16-107).  The "texture" is a
+ * context-owned linear control grid sampled by a software trilinear fetch with the texture unit's
+ * addressing rules (unnormalised coordinates, clamp, 8-bit fractional weights). */
+int gcb_setupTexture(gcb_ctx* ctx, int dx, int dy, int dz);
+int gcb_copytotexture(gcb_ctx* ctx, float* d_phi, gcb_pitched_ptr data_ptr, int NX, int NY, int NZ);
+int gcb_updateTexture(gcb_ctx* ctx, gcb_pitched_ptr data_ptr);
+int gcb_deleteTexture(gcb_ctx* ctx);
+
+/* File_output::file_write_obj (src/File_output.h:38, File_output.cu:5-81): d_pos device float4[totalVerts] */
+int gcb_file_write_obj(gcb_ctx* ctx, void* d_pos, unsigned int totalVerts, const char* filename);
+
+/* ------------------------------------------------------------------ fused entry points (no reference twin) */
+/* Each is validated against the composition of the legacy calls it replaces. */
+
+/* Slab geometry for multi-GPU z-slab sharding.  A rank owns cell layers
+ * [z0, z0 + nz_local - 1) of a global grid of gnz point layers and holds nz_local point layers
+ * (its cells' +z halo plane included).  Single GPU: z0 = 0, gnz = nz_local. */
+typedef struct gcb_slab { unsigned int z0, gnz; } gcb_slab;
+
+/* SVL field: for h in [0,nh): svl += cos(phi_h)*re_h - sin(phi_h)*im_h, phi_h trilinear from the
+ * control grid (replaces nh x {copytotexture, updateTexture, grating, svl}; main.cu:3949-3970).
+ * d_phi: nh control grids of (cx,cy,cz_local) floats back to back; the control slab must cover the
+ * coarse planes the fine slab samples: control plane index = floor((z0+z)*dz) - cz0 (and +1).
+ * coef: nh float2 on the HOST.  If accumulate == 0 the field starts from 0 (cudaMemset in
+ * check_lattice, main.cu:4058).  d_minmax (device float[2], optional) receives min/max of the
+ * slab's field exactly as the reference's reduction defines them (seeded with 0). */
+int gcb_svl_field(gcb_ctx* ctx, float* d_svl, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz_local,
+    int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, int accumulate, float* d_minmax);
+
+/* min/max of a device array with the reference's semantics (result on host). */
+int gcb_minmax(gcb_ctx* ctx, const float* d_in, size_t n, float* lo, float* hi);
+
+/* Band-lattice extraction straight from the raw field: fuses device_bufferfour
+ * (k = (f-a)/(b-a), domain faces forced to 0, band mask) into the marching-cubes kernel.
+ * Equivalent to GPU_buffer_normalise_four + computeIsosurface_lattice(one) with vol_two = 0,
+ * iso1 = iso2 = 0.  a, b: global min/max.  pos/norm: device float4[maxVerts].
+ * d_compVoxelArray may be NULL.  Counts are 64-bit; vertex order is ascending global cell id.
+ * count_only != 0: classify and count only (no mesh written). */
+int gcb_extract_band_raw(gcb_ctx* ctx, const float* d_field, float a, float b, float isoValue, float isovalue1, float isovalue2,
+    gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
+    unsigned long long maxVerts, unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels,
+    unsigned long long* totalVerts);
+
+/* Whole config-3/4 pipeline on one rank, device-resident inputs: gcb_svl_field -> (a,b given by
+ * caller or computed locally when use_local_minmax != 0) -> gcb_extract_band_raw. */
+int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz,
+    int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2,
+    gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
+    unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out);
+
+/* Same pipeline with HOST inputs (pinned or pageable): copies the control grids host->device
+ * into d_phi_scratch, runs gcb_svl_lattice, returns the counts.  This is the end-to-end call
+ * bench.py times as `e2e`. */
+int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host,
+    int cx, int cy, int cz, int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1,
+    float isovalue2, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
+    unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUCAD_B200_H */

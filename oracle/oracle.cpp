@@ -1,0 +1,786 @@
+/*
+ * oracle.cpp -- CPU restatement (C++17 / OpenMP) of the reference's implicit-field +
+ * marching-cubes path.
+ *
+ * TEST INFRASTRUCTURE ONLY -- see oracle.h.  Every function cites the reference source it
+ * follows (paths relative to /root/reference/src).  The reference has no CPU path, no tests and
+ * no golden vectors: parity of this file is pinned by running the
+ * reference's own CUDA kernels (oracle/_ref) on identical inputs on the GPU box.
+ *
+ * Floating point: built with -ffp-contract=off; every place where nvcc/ptxas fuses a
+ * multiply-add in the reference build (checked in the sm_100a SASS of the unmodified
+ * sources) is written as an explicit fmaf() here:
+ *     lerp(a,b,t)        = fmaf(b-a, t, a)                (commons/helper_math.h:1145-1148)
+ *     x*y - z*w          = fmaf(x, y, -(z*w))             (cross products, svl_kernel)
+ */
+#include "oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+/* ------------------------------------------------------------------------------------------
+ * Tables: Bourke triTable packed 16 nibbles / case (tools/pack_mc_tables.py), numVerts derived.
+ * Reference: tables.h:49-307 (triTable), :311-569 (numVertsTable).
+ * ---------------------------------------------------------------------------------------- */
+const uint64_t kTriPacked[256] = {
+#include "../gpucadforam_b200/csrc/mc_tables_packed.inc"
+};
+
+struct Tables {
+    uint8_t tri[256][16];
+    uint8_t nverts[256];
+    Tables() {
+        for (int c = 0; c < 256; ++c) {
+            int n = 0;
+            for (int j = 0; j < 16; ++j) {
+                unsigned e = (unsigned)((kTriPacked[c] >> (4 * j)) & 15u);
+                tri[c][j] = e == 15u ? 255 : (uint8_t)e;
+                if (e != 15u) ++n;
+            }
+            nverts[c] = (uint8_t)n;
+        }
+    }
+};
+const Tables& T() { static Tables t; return t; }
+
+struct f3 { float x, y, z; };
+inline f3 operator-(f3 a, f3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline f3 operator+(f3 a, f3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+
+/* helper_math.h:1145-1148, contracted by ptxas to FFMA (b-a)*t + a */
+inline f3 lerp3(f3 a, f3 b, float t) {
+    return {fmaf(b.x - a.x, t, a.x), fmaf(b.y - a.y, t, a.y), fmaf(b.z - a.z, t, a.z)};
+}
+/* helper_math.h:1427-1430; SASS: FMUL second product, FFMA first product minus it */
+inline f3 cross3(f3 a, f3 b) {
+    return {fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))};
+}
+
+/* corner offsets 0..7: MarchingCubes_kernel.cu:889-896 */
+const int kCorner[8][3] = {{0,0,0},{1,0,0},{1,1,0},{0,1,0},{0,0,1},{1,0,1},{1,1,1},{0,1,1}};
+/* edge endpoints, lattice variants: MarchingCubes_kernel.cu:3751-3762 */
+const int kEdgeLat[12][2] = {{0,1},{1,2},{2,3},{3,0},{4,5},{5,6},{6,7},{7,4},{0,4},{1,5},{2,6},{3,7}};
+/* edge endpoints, CSG/topo variants (first endpoint owns the stored t): :2140-2151 */
+const int kEdgeOwn[12][2] = {{0,1},{1,2},{3,2},{0,3},{4,5},{5,6},{7,6},{4,7},{0,4},{1,5},{2,6},{3,7}};
+/* which stored parameter of the owner the edge uses: 0=t_x 1=t_y 2=t_z */
+const int kEdgeAxis[12] = {0, 1, 0, 1, 0, 1, 0, 1, 2, 2, 2, 2};
+
+struct Grid {
+    uint32_t nx, ny, nz, cx, cy, cz; /* points, cells */
+    size_t idx(uint32_t x, uint32_t y, uint32_t z) const { return ((size_t)z * ny + y) * nx + x; }
+};
+
+/* calcGridPos: MarchingCubes_kernel.cu:120-136 (divisors, not shifts) */
+inline void cell_pos(const Grid& g, uint32_t i, uint32_t& x, uint32_t& y, uint32_t& z) {
+    uint32_t slab = g.cx * g.cy;
+    z = i / slab;
+    uint32_t r = i % slab;
+    y = r / g.cx;
+    x = r % g.cx;
+}
+
+inline bool band(float v, float lo, float hi) { return (v > lo) & (v < hi); }
+
+/* cube index of cell (x,y,z) for each mode */
+inline uint32_t cube_index(const orc_mc_params& p, const Grid& g, uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t ci = 0;
+    const float iso = p.iso;
+    for (int c = 0; c < 8; ++c) {
+        size_t i = g.idx(x + kCorner[c][0], y + kCorner[c][1], z + kCorner[c][2]);
+        bool b = false;
+        switch (p.mode) {
+        case ORC_MODE_LATTICE_ONE:
+        case ORC_MODE_LATTICE: /* classifyVoxel_new :3207-3249 */
+            b = p.f0[i] < iso;
+            break;
+        case ORC_MODE_TOPO: /* classifyVoxel_kernel_topo :1492-1499 / classifyVoxel_2 :1323-1407 */
+            b = ((float)p.gp[i].val < p.iso1) | (p.f0[i] >= iso);
+            break;
+        case ORC_MODE_CSG: { /* classifyVoxel :922-1052 */
+            const float fx = (float)p.gp[i].val; /* sampleVolume_2 :98-108 */
+            const float dy = p.f0 ? p.f0[i] : 0.f;
+            const float la = p.f1 ? p.f1[i] : 0.f;
+            const bool fixed = p.flags & ORC_F_FIXED, dyn = p.flags & ORC_F_DYNAMIC;
+            if (p.flags & ORC_F_MAKE_REGION) b = fx < iso;
+            else if (p.flags & ORC_F_UNION) {
+                if (fixed) b = (dy < iso) | band(la, p.iso1, p.iso2);
+                else if (dyn) b = (fx < iso) | band(la, p.iso1, p.iso2);
+                else b = (fx < iso) | (dy < iso);
+            } else if (p.flags & ORC_F_DIFF) {
+                if (fixed) b = (dy >= iso) & band(la, p.iso1, p.iso2);
+                else if (dyn) b = (fx < iso) & ((la < p.iso1) | (la > p.iso2));
+                else b = (dy >= iso) & (fx < iso);
+            } else if (p.flags & ORC_F_INTERSECT) {
+                if (fixed) b = (dy < iso) & band(la, p.iso1, p.iso2);
+                else if (dyn) b = (fx < iso) & band(la, p.iso1, p.iso2);
+                else b = (fx < iso) & (dy < iso);
+            }
+            break;
+        }
+        }
+        ci |= (uint32_t)b << c;
+    }
+    return ci;
+}
+
+/* vertexInterp2_new :3593-3674 (t left undefined by the reference on non-crossing edges; 0 here) */
+inline f3 interp_band(float l1, float l2, f3 p0, f3 p1, float f0, float f1, float id0, float id1) {
+    float t = 0.f;
+    if (((id0 == 1) && (id1 == 0)) || ((id0 == 0) && (id1 == 1))) {
+        if (f1 < f0) { std::swap(p0, p1); std::swap(f0, f1); }
+        if ((f1 >= l1) && (f0 <= l1)) {
+            if ((double)fabsf(l1 - f0) < 0.0005) return p0;
+            if ((double)fabsf(l1 - f1) < 0.0005) return p1;
+            if ((double)fabsf(f1 - f0) < 0.0005) return p0;
+            t = (l1 - f0) / (f1 - f0);
+        } else if ((f1 >= l2) && (f0 <= l2)) {
+            if ((double)fabsf(l2 - f0) < 0.0005) return p0;
+            if ((double)fabsf(l2 - f1) < 0.0005) return p1;
+            if ((double)fabsf(f1 - f0) < 0.0005) return p0;
+            t = (l2 - f0) / (f1 - f0);
+        } else if ((f1 == f0) && (p0.z == 0.0f)) t = 1.f;
+        else if (f1 == f0) t = 0.f;
+    }
+    return lerp3(p0, p1, t);
+}
+
+/* vertexInterp3_new :3269-3416: band on (f0,f1) when ids are {1,0}; band on (f2,f3) when ids are {2,0} */
+inline f3 interp_band2(float l1, float l2, f3 p0, f3 p1, float f0, float f1, float f2, float f3v,
+                       float m1, float m2, float id0, float id1) {
+    float t = 0.f;
+    if (((id0 == 1) && (id1 == 0)) || ((id0 == 0) && (id1 == 1))) {
+        if (f1 < f0) { std::swap(p0, p1); std::swap(f0, f1); }
+        if ((f1 >= l1) && (f0 <= l1)) {
+            if ((double)fabsf(l1 - f0) < 0.0005) return p0;
+            if ((double)fabsf(l1 - f1) < 0.0005) return p1;
+            if ((double)fabsf(f1 - f0) < 0.0005) return p0;
+            t = (l1 - f0) / (f1 - f0);
+        } else if ((f1 >= l2) && (f0 <= l2)) {
+            if ((double)fabsf(l2 - f0) < 0.0005) return p0;
+            if ((double)fabsf(l2 - f1) < 0.0005) return p1;
+            if ((double)fabsf(f1 - f0) < 0.0005) return p0;
+            t = (l2 - f0) / (f1 - f0);
+        } else if ((f1 == f0) && (p0.z == 0.0f)) t = 1.f;
+        else if (f1 == f0) t = 0.f;
+    }
+    if (((id0 == 2) && (id1 == 0)) || ((id1 == 2) && (id0 == 0))) {
+        if (f3v < f2) { std::swap(p0, p1); std::swap(f2, f3v); }
+        if ((f3v >= m1) && (f2 <= m1)) {
+            if ((double)fabsf(m1 - f2) < 0.0005) return p0;
+            if ((double)fabsf(m1 - f3v) < 0.0005) return p1;
+            if ((double)fabsf(f3v - f2) < 0.0005) return p0;
+            t = (m1 - f2) / (f3v - f2);
+        } else if ((f3v >= m2) && (f2 <= m2)) {
+            if ((double)fabsf(m2 - f2) < 0.0005) return p0;
+            if ((double)fabsf(m2 - f3v) < 0.0005) return p1;
+            if ((double)fabsf(f3v - f2) < 0.0005) return p0;
+            t = (m2 - f2) / (f3v - f2);
+        } else if ((f3v == f2) && (p0.z == 0.0f)) t = 1.f;
+        else if (f3v == f2) t = 0.f;
+    }
+    return lerp3(p0, p1, t);
+}
+
+inline float blend_t(float t1, float t2, float t) { /* shared tail of :1657-1668 */
+    if ((t1 > 0) && (t2 > 0)) t = (t1 + t2) * 0.5f;
+    else if ((t1 > 0) && (t2 == 0)) t = t1;
+    else if ((t2 > 0) && (t1 == 0)) t = t2;
+    return t;
+}
+
+/* vertexInterp_primitive :1640-1672 */
+inline float t_primitive(float iso, float f0, float f1, float edge_t) {
+    float t2 = 0.f;
+    if (((f1 >= iso) && (f0 <= iso)) || ((f0 >= iso) && (f1 <= iso))) t2 = (iso - f0) / (f1 - f0);
+    return blend_t(edge_t, t2, 0.f);
+}
+/* vertexInterp_primitive_one :1675-1724 */
+inline float t_primitive_one(float l1, float l2, float f0, float f1, float edge_t) {
+    float t2 = 0.f, t3 = 0.f;
+    if (((f1 >= l1) && (f0 <= l1)) || ((f0 >= l1) && (f1 <= l1))) t2 = (l1 - f0) / (f1 - f0);
+    float t = blend_t(edge_t, t2, 0.f);
+    if (((f1 >= l2) && (f0 <= l2)) || ((f0 >= l2) && (f1 <= l2))) t3 = (l2 - f0) / (f1 - f0);
+    return blend_t(edge_t, t3, t);
+}
+/* vertexInterp_new :1727-1784 */
+inline float t_fixed(float iso, float l1, float l2, float f0, float f1, float f2, float f3v) {
+    float t1 = 0.f, t2 = 0.f, t3 = 0.f, t = 0.f;
+    if (((f0 < iso) && (f1 >= iso)) || ((f1 < iso) && (f0 >= iso))) t1 = (iso - f0) / (f1 - f0);
+    if (((f2 < l1) && (f3v >= l1)) || ((f3v < l1) && (f2 >= l1))) t2 = (l1 - f2) / (f3v - f2);
+    if (((f2 < l2) && (f3v >= l2)) || ((f3v < l2) && (f2 >= l2))) t3 = (l2 - f2) / (f3v - f2);
+    if ((t1 > 0.0f) && (t2 > 0.0f) && (t3 == 0.0f)) t = (t1 + t2) * 0.5f;
+    else if ((t1 > 0.0f) && (t3 > 0.0f) && (t2 == 0.0f)) t = (t1 + t3) * 0.5f;
+    else if ((t1 > 0.0f) && (t2 == 0.0f) && (t3 == 0.0f)) t = t1;
+    else if ((t2 > 0.0f) && (t1 == 0.0f) && (t3 == 0.0f)) t = t2;
+    else if ((t3 > 0.0f) && (t1 == 0.0f) && (t2 == 0.0f)) t = t3;
+    return t;
+}
+/* vertexInterp_analysis :1787-1820 (note the strict '<' on the low side) */
+inline float t_analysis(float iso, float f0, float f1, float edge_t) {
+    float t2 = 0.f;
+    if (((f1 >= iso) && (f0 < iso)) || ((f0 >= iso) && (f1 < iso))) t2 = (iso - f0) / (f1 - f0);
+    return blend_t(edge_t, t2, 0.f);
+}
+
+inline float gp_t(const orc_grid_point& g, int axis) { return axis == 0 ? g.t_x : axis == 1 ? g.t_y : g.t_z; }
+
+/* triangles of one active cell: generateTriangles_* kernels (:1865-2200, :2625-2794, :2816-3017,
+ * :3424-3570, :3678-3817) */
+void emit_cell(const orc_mc_params& p, const Grid& g, uint32_t voxel, uint32_t base, float* pos, float* norm) {
+    uint32_t x, y, z;
+    cell_pos(g, voxel, x, y, z);
+    const uint32_t ci = cube_index(p, g, x, y, z);
+    const int nv = T().nverts[ci];
+    if (nv == 0) return;
+
+    f3 pp = {((float)x - p.center[0]) * p.voxel[0], ((float)y - p.center[1]) * p.voxel[1],
+             ((float)z - p.center[2]) * p.voxel[2]};
+    f3 v[8];
+    size_t pi[8];
+    for (int c = 0; c < 8; ++c) {
+        f3 off = {kCorner[c][0] ? p.voxel[0] : 0.f, kCorner[c][1] ? p.voxel[1] : 0.f,
+                  kCorner[c][2] ? p.voxel[2] : 0.f};
+        v[c] = c == 0 ? pp : pp + off;
+        pi[c] = g.idx(x + kCorner[c][0], y + kCorner[c][1], z + kCorner[c][2]);
+    }
+
+    f3 vert[12];
+    float col[12];
+    bool have[12] = {false};
+    auto edge_vertex = [&](int e) {
+        if (have[e]) return;
+        have[e] = true;
+        col[e] = 0.f;
+        switch (p.mode) {
+        case ORC_MODE_LATTICE_ONE: {
+            int a = kEdgeLat[e][0], b = kEdgeLat[e][1];
+            vert[e] = interp_band(p.iso1, p.iso2, v[a], v[b], p.f1[pi[a]], p.f1[pi[b]], p.f0[pi[a]], p.f0[pi[b]]);
+            break;
+        }
+        case ORC_MODE_LATTICE: {
+            int a = kEdgeLat[e][0], b = kEdgeLat[e][1];
+            vert[e] = interp_band2(p.iso1, p.iso2, v[a], v[b], p.f1[pi[a]], p.f1[pi[b]], p.f2[pi[a]],
+                                   p.f2[pi[b]], p.iso1b, p.iso2b, p.f0[pi[a]], p.f0[pi[b]]);
+            break;
+        }
+        case ORC_MODE_CSG: {
+            if (p.flags & ORC_F_MAKE_REGION) {
+                int a = kEdgeOwn[e][0], b = kEdgeOwn[e][1];
+                vert[e] = lerp3(v[a], v[b], gp_t(p.gp[pi[a]], kEdgeAxis[e]));
+            } else if (p.flags & ORC_F_FIXED) {
+                int a = kEdgeLat[e][0], b = kEdgeLat[e][1];
+                float t = t_fixed(p.iso, p.iso1, p.iso2, p.f0[pi[a]], p.f0[pi[b]], p.f1[pi[a]], p.f1[pi[b]]);
+                vert[e] = lerp3(v[a], v[b], t);
+            } else if (p.flags & ORC_F_DYNAMIC) {
+                int a = kEdgeOwn[e][0], b = kEdgeOwn[e][1];
+                float t = t_primitive_one(p.iso1, p.iso2, p.f1[pi[a]], p.f1[pi[b]], gp_t(p.gp[pi[a]], kEdgeAxis[e]));
+                vert[e] = lerp3(v[a], v[b], t);
+            } else {
+                int a = kEdgeOwn[e][0], b = kEdgeOwn[e][1];
+                float t = t_primitive(p.iso, p.f0[pi[a]], p.f0[pi[b]], gp_t(p.gp[pi[a]], kEdgeAxis[e]));
+                vert[e] = lerp3(v[a], v[b], t);
+            }
+            break;
+        }
+        case ORC_MODE_TOPO: {
+            int a = kEdgeOwn[e][0], b = kEdgeOwn[e][1];
+            float t = t_analysis(p.iso, p.f0[pi[a]], p.f0[pi[b]], gp_t(p.gp[pi[a]], kEdgeAxis[e]));
+            col[e] = p.f1 ? p.f1[pi[a]] : 0.f; /* *field_val = r0 :1797 */
+            if (p.flags & ORC_F_DISP) {
+                f3 d0 = {p.disp[4 * pi[a]], p.disp[4 * pi[a] + 1], p.disp[4 * pi[a] + 2]};
+                f3 d1 = {p.disp[4 * pi[b]], p.disp[4 * pi[b] + 1], p.disp[4 * pi[b] + 2]};
+                vert[e] = lerp3(d0, d1, t);
+            } else vert[e] = lerp3(v[a], v[b], t);
+            break;
+        }
+        }
+    };
+
+    for (int j = 0; j < nv; j += 3) {
+        const uint32_t index = base + (uint32_t)j;
+        int e0 = T().tri[ci][j], e1 = T().tri[ci][j + 1], e2 = T().tri[ci][j + 2];
+        edge_vertex(e0); edge_vertex(e1); edge_vertex(e2);
+        f3 n;
+        float w[3];
+        if (p.mode == ORC_MODE_CSG) { /* calcNormal(ver0, ver2, ver1) :2178, w = 0.5 :2185 */
+            n = cross3(vert[e2] - vert[e0], vert[e1] - vert[e0]);
+            w[0] = w[1] = w[2] = 0.5f;
+        } else {
+            n = cross3(vert[e1] - vert[e0], vert[e2] - vert[e0]);
+            if (p.mode == ORC_MODE_TOPO) { w[0] = col[e0]; w[1] = col[e1]; w[2] = col[e2]; }
+            else w[0] = w[1] = w[2] = 0.f;
+        }
+        if (index < (p.max_verts - 3u)) { /* :2181 */
+            const int es[3] = {e0, e1, e2};
+            for (int k = 0; k < 3; ++k) {
+                float* P = pos + 4 * (size_t)(index + k);
+                float* N = norm + 4 * (size_t)(index + k);
+                P[0] = vert[es[k]].x; P[1] = vert[es[k]].y; P[2] = vert[es[k]].z; P[3] = 1.0f;
+                N[0] = n.x; N[1] = n.y; N[2] = n.z; N[3] = w[k];
+            }
+        }
+    }
+}
+
+Grid make_grid(const orc_mc_params& p) {
+    Grid g;
+    g.nx = p.nx; g.ny = p.ny; g.nz = p.nz;
+    g.cx = p.nx - 1; g.cy = p.ny - 1; g.cz = p.nz - 1;
+    return g;
+}
+
+/* Euler rotation rows shared by the rotated primitives: Modelling.cu:401-407 */
+struct Rot { f3 px, py, pz; };
+Rot make_rot(const float a[3]) {
+    float cx = cosf(a[0]), sx = sinf(a[0]), cy = cosf(a[1]), sy = sinf(a[1]), cz = cosf(a[2]), sz = sinf(a[2]);
+    Rot r;
+    r.px = {cz * cy, fmaf(cz * sy, sx, -(sz * cx)), fmaf(cz * sy, cx, sz * sx)};
+    r.py = {sz * cy, fmaf(sz * sy, sx, cz * cx), fmaf(sz * sy, cx, -(cz * sx))};
+    r.pz = {-1.0f * sy, cy * sx, cy * cx};
+    return r;
+}
+inline float dot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+
+template <class F>
+void for_points(int nx, int ny, int nz, float dx, float dy, float dz, const float c[3], F f) {
+    const float mx = (float)((nx - 1) / 2.0), my = (float)((ny - 1) / 2.0), mz = (float)((nz - 1) / 2.0);
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                f3 v = {fmaf((float)x - mx, dx, -c[0]), fmaf((float)y - my, dy, -c[1]), fmaf((float)z - mz, dz, -c[2])};
+                f(((size_t)z * ny + y) * nx + x, v);
+            }
+}
+
+/* software model of tex3D<float> with cudaFilterModeLinear, unnormalised coords, clamp
+ * (Interpolations.cu:79-107, Gratings.cu:676/712; CUDA programming guide "Linear Filtering":
+ * xB = x - 0.5, i = floor(xB), alpha = frac(xB) kept to 8 fractional bits). */
+struct TexAxis { int i0, i1; float a; };
+inline TexAxis tex_axis(float coord, int n) {
+    float xb = coord - 0.5f;
+    float fl = floorf(xb);
+    float a = roundf((xb - fl) * 256.0f) / 256.0f;
+    int i = (int)fl;
+    if (a >= 1.0f) { a = 0.f; i += 1; }
+    TexAxis t;
+    t.i0 = std::min(std::max(i, 0), n - 1);
+    t.i1 = std::min(std::max(i + 1, 0), n - 1);
+    t.a = a;
+    return t;
+}
+inline float tex3d(const float* c, int cx, int cy, int cz, float x, float y, float z) {
+    TexAxis X = tex_axis(x, cx), Y = tex_axis(y, cy), Z = tex_axis(z, cz);
+    auto at = [&](int i, int j, int k) { return (double)c[((size_t)k * cy + j) * cx + i]; };
+    double a = X.a, b = Y.a, g = Z.a;
+    double r = (1 - a) * (1 - b) * (1 - g) * at(X.i0, Y.i0, Z.i0) + a * (1 - b) * (1 - g) * at(X.i1, Y.i0, Z.i0) +
+               (1 - a) * b * (1 - g) * at(X.i0, Y.i1, Z.i0) + a * b * (1 - g) * at(X.i1, Y.i1, Z.i0) +
+               (1 - a) * (1 - b) * g * at(X.i0, Y.i0, Z.i1) + a * (1 - b) * g * at(X.i1, Y.i0, Z.i1) +
+               (1 - a) * b * g * at(X.i0, Y.i1, Z.i1) + a * b * g * at(X.i1, Y.i1, Z.i1);
+    return (float)r;
+}
+
+} // namespace
+
+extern "C" {
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void orc_tables(uint32_t* tri, uint32_t* nverts) {
+    for (int c = 0; c < 256; ++c) {
+        for (int j = 0; j < 16; ++j) tri[c * 16 + j] = T().tri[c][j];
+        nverts[c] = T().nverts[c];
+    }
+}
+
+int orc_count(const orc_mc_params* pp, uint64_t* active_voxels, uint64_t* total_verts) {
+    const orc_mc_params& p = *pp;
+    const Grid g = make_grid(p);
+    uint64_t act = 0, tot = 0;
+#pragma omp parallel for schedule(static) reduction(+ : act, tot)
+    for (int64_t z = 0; z < (int64_t)g.cz; ++z)
+        for (uint32_t y = 0; y < g.cy; ++y)
+            for (uint32_t x = 0; x < g.cx; ++x) {
+                uint32_t nv = T().nverts[cube_index(p, g, x, y, (uint32_t)z)];
+                act += nv > 0;
+                tot += nv;
+            }
+    *active_voxels = act;
+    *total_verts = tot;
+    return 0;
+}
+
+/* Isosurface::computeIsosurface* sequencing: Isosurface.cu:44-134 and siblings */
+int orc_extract(const orc_mc_params* pp, uint32_t* voxel_verts, uint32_t* voxel_occupied,
+                uint32_t* voxel_verts_scan, uint32_t* voxel_occupied_scan, uint32_t* comp_voxel_array,
+                float* pos, float* norm, uint32_t* active_voxels, uint32_t* total_verts) {
+    const orc_mc_params& p = *pp;
+    const Grid g = make_grid(p);
+    const size_t ncell = (size_t)g.cx * g.cy * g.cz;
+    std::vector<uint8_t> nv(ncell);
+#pragma omp parallel for schedule(static)
+    for (int64_t z = 0; z < (int64_t)g.cz; ++z)
+        for (uint32_t y = 0; y < g.cy; ++y)
+            for (uint32_t x = 0; x < g.cx; ++x)
+                nv[((size_t)z * g.cy + y) * g.cx + x] = T().nverts[cube_index(p, g, x, y, (uint32_t)z)];
+
+    /* thrust::exclusive_scan x2 (:3198-3203) + compactVoxels (:1594-1608) */
+    std::vector<uint32_t> comp, voff;
+    uint32_t occ = 0, verts = 0;
+    for (size_t i = 0; i < ncell; ++i) {
+        if (voxel_verts) voxel_verts[i] = nv[i];
+        if (voxel_occupied) voxel_occupied[i] = nv[i] > 0;
+        if (voxel_verts_scan) voxel_verts_scan[i] = verts;
+        if (voxel_occupied_scan) voxel_occupied_scan[i] = occ;
+        if (nv[i]) { comp.push_back((uint32_t)i); voff.push_back(verts); ++occ; }
+        verts += nv[i];
+    }
+    *active_voxels = occ;
+    *total_verts = occ ? verts : 0; /* early-out :83-87 */
+    if (comp_voxel_array) std::copy(comp.begin(), comp.end(), comp_voxel_array);
+    if (!occ || !pos || !norm) return 0;
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t a = 0; a < (int64_t)comp.size(); ++a) emit_cell(p, g, comp[a], voff[a], pos, norm);
+    return 0;
+}
+
+/* ---------------- field producers ---------------- */
+
+/* create_lattice_kernel: lattice_files/Fft_lattice.cu:12-66 (3.14 literal, coordinates in double) */
+void orc_create_lattice(float* out, uint32_t NX, uint32_t NY, uint32_t NZ, uint32_t type) {
+#pragma omp parallel for schedule(static)
+    for (int64_t z = 0; z < (int64_t)NZ; ++z)
+        for (uint32_t y = 0; y < NY; ++y)
+            for (uint32_t x = 0; x < NX; ++x) {
+                float xx = (float)((((int)x * 1.0) / (NX - 1) - 0.5) / 0.5);
+                float yy = (float)((((int)y * 1.0) / (NY - 1) - 0.5) / 0.5);
+                float zz = (float)((((int)z * 1.0) / (NZ - 1) - 0.5) / 0.5);
+                /* `3.14 * xx` is a double product narrowed to float by the cosf/sinf call */
+                float ax = (float)(3.14 * xx), ay = (float)(3.14 * yy), az = (float)(3.14 * zz);
+                float aa = 0.f;
+                if (type == 0) aa = fmaf(cosf(az), sinf(ax), fmaf(cosf(ax), sinf(ay), cosf(ay) * sinf(az)));
+                else if (type == 1) aa = cosf(ax) + cosf(ay) + cosf(az);
+                else if (type == 2) {
+                    float s = fmaf(cosf(2 * zz), cosf(2 * xx), fmaf(cosf(2 * xx), cosf(2 * yy), cosf(2 * yy) * cosf(2 * zz)));
+                    aa = fmaf(4.f, cosf(xx) * cosf(yy) * cosf(zz), -s);
+                } else if (type == 3) {
+                    float s = fmaf(cosf(az), cosf(ax), fmaf(cosf(ax), cosf(ay), cosf(ay) * cosf(az)));
+                    float q = cosf((float)(2 * 3.14 * xx)) + cosf((float)(2 * 3.14 * yy)) + cosf((float)(2 * 3.14 * zz));
+                    aa = fmaf(2.f, s, -q);
+                } else if (type == 4) {
+                    double a = (double)(xx * xx) + (double)yy * yy, b = (double)yy * yy + (double)zz * zz,
+                           c = (double)zz * zz + (double)xx * xx;
+                    aa = (float)std::min(std::min(a, b), c);
+                } else if (type == 5) {
+                    double d = cos(3.14 * xx) * (double)cosf(ay) * (double)cosf(az) -
+                               (double)(sinf(ax) * sinf(ay) * sinf(az));
+                    aa = (float)d;
+                }
+                out[((size_t)z * NY + y) * NX + x] = aa;
+            }
+}
+
+/* implicit_sphere_kernel: Modelling.cu:314-361 */
+void orc_sphere(float* out, const float c[3], float radius, float thickness, int nx, int ny, int nz,
+                float dx, float dy, float dz, int shell) {
+    const float td = (float)(thickness / 2.0);
+    for_points(nx, ny, nz, dx, dy, dz, c, [&](size_t i, f3 v) {
+        float r2 = fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x));
+        if (shell) {
+            float f1 = r2 - (radius - td) * (radius - td);
+            float f2 = r2 - (radius + td) * (radius + td);
+            out[i] = (float)std::max((double)f1 * -1.0, (double)f2);
+        } else out[i] = r2 - radius * radius;
+    });
+}
+
+/* distance_from_line_kernel: Modelling.cu:244-302 */
+void orc_distance_from_line(float* out, const float c[3], const float axis_in[3], float radius,
+                            float thickness_radial, float thickness_axial, int nx, int ny, int nz,
+                            float dx, float dy, float dz, int disc) {
+    const float td = (float)(thickness_radial / 2.0), tda = (float)(thickness_axial / 2.0);
+    float mag = sqrtf(fmaf(axis_in[2], axis_in[2], fmaf(axis_in[1], axis_in[1], axis_in[0] * axis_in[0])));
+    f3 ax = {axis_in[0] / mag, axis_in[1] / mag, axis_in[2] / mag};
+    f3 cen = {c[0], c[1], c[2]};
+    f3 end = ax + cen;
+    const float zero[3] = {0.f, 0.f, 0.f};
+    for_points(nx, ny, nz, dx, dy, dz, zero, [&](size_t i, f3 fv) {
+        f3 w1 = fv - cen, w2 = fv - end, w3 = end - cen;
+        f3 d = cross3(w1, w2);
+        float e = sqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x)));
+        float dis = sqrtf(fmaf(w3.z, w3.z, fmaf(w3.y, w3.y, w3.x * w3.x)));
+        float f = e / dis;
+        float gg = fmaf(fv.z - cen.z, ax.z, fmaf(fv.y - cen.y, ax.y, (fv.x - cen.x) * ax.x));
+        float fld1 = std::max(gg - tda, (gg + tda) * -1.f);
+        float fld2;
+        if (disc) fld2 = (float)std::max((double)(f - (radius + td)), (double)(f - (radius - td)) * -1.0);
+        else fld2 = f - radius;
+        out[i] = std::max(fld1, fld2);
+    });
+}
+
+/* implicit_cuboid_kernel: Modelling.cu:375-421 */
+void orc_cuboid(float* out, const float c[3], const float ang[3], float xw, float yw, float zw, int nx,
+                int ny, int nz, float dx, float dy, float dz) {
+    const Rot r = make_rot(ang);
+    const float hx = (float)(xw / 2.0), hy = (float)(yw / 2.0), hz = (float)(zw / 2.0);
+    for_points(nx, ny, nz, dx, dy, dz, c, [&](size_t i, f3 v) {
+        float f1 = fabsf(dot3(v, r.px)) - hx, f2 = fabsf(dot3(v, r.py)) - hy, f3v = fabsf(dot3(v, r.pz)) - hz;
+        out[i] = std::max(std::max(f1, f2), f3v);
+    });
+}
+
+/* implicit_cuboid_shell_kernel: Modelling.cu:435-487 */
+void orc_cuboid_shell(float* out, const float c[3], const float ang[3], float xw, float yw, float zw,
+                      float th, int nx, int ny, int nz, float dx, float dy, float dz) {
+    const Rot r = make_rot(ang);
+    const float hx = (float)(xw / 2.0), hy = (float)(yw / 2.0), hz = (float)(zw / 2.0);
+    for_points(nx, ny, nz, dx, dy, dz, c, [&](size_t i, f3 v) {
+        float a1 = fabsf(dot3(v, r.px)), a2 = fabsf(dot3(v, r.py)), a3 = fabsf(dot3(v, r.pz));
+        float f11 = a1 - hx, f12 = a1 - (hx - th), f21 = a2 - hy, f22 = a2 - (hy - th), f3v = a3 - hz;
+        double inner = (double)std::max(f12, f22) * -1.0;
+        double m = std::max((double)std::max(f11, f21), inner);
+        out[i] = (float)std::max(m, (double)f3v);
+    });
+}
+
+/* implicit_torus_kernel: Modelling.cu:569-616 */
+void orc_torus(float* out, const float c[3], const float ang[3], float R, float rc, int nx, int ny, int nz,
+               float dx, float dy, float dz) {
+    const Rot r = make_rot(ang);
+    for_points(nx, ny, nz, dx, dy, dz, c, [&](size_t i, f3 v) {
+        float vx = dot3(v, r.px), vy = dot3(v, r.py), vz = dot3(v, r.pz);
+        float side = R - sqrtf(fmaf(vy, vy, vx * vx));
+        out[i] = fmaf(side, side, fmaf(vz, vz, -(rc * rc)));
+    });
+}
+
+/* implicit_cone_kernel: Modelling.cu:631-683 */
+void orc_cone(float* out, const float c[3], const float ang[3], float br, float h, int nx, int ny, int nz,
+              float dx, float dy, float dz) {
+    const Rot r = make_rot(ang);
+    const float k = (h / br) * (h / br);
+    for_points(nx, ny, nz, dx, dy, dz, c, [&](size_t i, f3 v) {
+        float vx = dot3(v, r.px), vy = dot3(v, r.py), vz = dot3(v, r.pz);
+        float gg = (float)(vy - (h / 2.0));
+        double hh = std::max((double)(float)((gg - (h / 2.0)) * 100), (double)(float)((gg + (h / 2.0)) * 100) * -1.0);
+        float q = vy - h;
+        float f1 = fmaf(fmaf(vz, vz, vx * vx), k, -(q * q));
+        out[i] = (float)std::max((double)f1, hh);
+    });
+}
+
+/* implicit_cone_frustum_kernel: Modelling.cu:698-750 */
+void orc_cone_frustum(float* out, const float c[3], const float ang[3], float tr, float brad, float h, int nx,
+                      int ny, int nz, float dx, float dy, float dz) {
+    const Rot r = make_rot(ang);
+    for_points(nx, ny, nz, dx, dy, dz, c, [&](size_t i, f3 v) {
+        float vx = dot3(v, r.px), vy = dot3(v, r.py), vz = dot3(v, r.pz);
+        float rd = ((h - vy) / h) * (brad - tr);
+        float gg = (float)(vy - (h / 2.0));
+        double hh = std::max((double)(float)((gg - (h / 2.0)) * 100), (double)(float)((gg + (h / 2.0)) * 100) * -1.0);
+        double q = (double)(rd + tr);
+        float f1 = (float)((double)fmaf(vz, vz, vx * vx) - q * q);
+        out[i] = (float)std::max((double)f1, hh);
+    });
+}
+
+/* implicit_pyramid_frustum_kernel: Modelling.cu:501-557 */
+void orc_pyramid_frustum(float* out, const float c[3], const float ang[3], float xwb, float xwt, float yh,
+                         float zwb, float zwt, int nx, int ny, int nz, float dx, float dy, float dz) {
+    const Rot r = make_rot(ang);
+    const float xb = (float)(xwb / 2.0), xt = (float)(xwt / 2.0), zb = (float)(zwb / 2.0), zt = (float)(zwt / 2.0);
+    for_points(nx, ny, nz, dx, dy, dz, c, [&](size_t i, f3 v) {
+        float f1 = dot3(v, r.px), f2 = dot3(v, r.py), f3v = dot3(v, r.pz);
+        float ratio = (yh - f2) / yh;
+        float xw = fmaf(ratio, xb - xt, xt);
+        f1 = fabsf(f1) - xw;
+        f2 = fabsf(f2 - (yh / 2)) - (yh / 2);
+        float zw = fmaf(ratio, zb - zt, zt);
+        f3v = fabsf(f3v) - zw;
+        out[i] = std::max(std::max(f1, f2), f3v);
+    });
+}
+
+/* GPUScalar_normalise_kernel_lattice + Min_reduction_lattice: Gratings.cu:1394-1495.
+ * The second stage seeds every lane with {0,0} and folds with min/max, so the result is
+ * min(0, min f) and max(0, max f). */
+void orc_minmax(const float* f, size_t n, float* lo, float* hi) {
+    float a = 0.f, b = 0.f;
+#pragma omp parallel for reduction(min : a) reduction(max : b)
+    for (int64_t i = 0; i < (int64_t)n; ++i) { a = std::min(a, f[i]); b = std::max(b, f[i]); }
+    *lo = a; *hi = b;
+}
+
+/* GPU_buffer_normalise_buffer + device_buffer: Gratings.cu:1500-1537, :1052-1068 */
+void orc_normalise_buffer(const float* in, float* out, size_t n) {
+    float a, b;
+    orc_minmax(in, n, &a, &b);
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = (in[i] - a) / (b - a);
+}
+
+/* device_bufferfour: Gratings.cu:1089-1134 */
+void orc_normalise_four_ab(const float* in, float* mask, float* k, int nx, int ny, int nz, float iso1,
+                           float iso2, float a, float b) {
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                size_t i = ((size_t)z * ny + y) * nx + x;
+                float kk = (in[i] - a) / (b - a), m;
+                if (x == 0 || x == nx - 1 || y == 0 || y == ny - 1 || z == 0 || z == nz - 1) { m = 0.f; kk = 0.f; }
+                else m = ((kk >= iso1) && (kk <= iso2)) ? 1.f : 0.f;
+                mask[i] = m;
+                k[i] = kk;
+            }
+}
+/* GPU_buffer_normalise_four: Gratings.cu:1579-1617 */
+void orc_normalise_four(const float* in, float* mask, float* k, int nx, int ny, int nz, float iso1, float iso2) {
+    float a, b;
+    orc_minmax(in, (size_t)nx * ny * nz, &a, &b);
+    orc_normalise_four_ab(in, mask, k, nx, ny, nz, iso1, iso2, a, b);
+}
+
+/* refine_kernel: Gratings.cu:689-722 */
+void orc_refine(const float* coarse, int cx, int cy, int cz, float* fine, int nx2, int ny2, int nz2, float dx,
+                float dy, float dz) {
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < nz2; ++z)
+        for (int y = 0; y < ny2; ++y)
+            for (int x = 0; x < nx2; ++x)
+                fine[((size_t)z * ny2 + y) * nx2 + x] =
+                    tex3d(coarse, cx, cy, cz, (float)(x * dx + 0.5), (float)(y * dy + 0.5), (float)(z * dz + 0.5));
+}
+
+/* grating_kernel + svl_kernel: Gratings.cu:653-687, :724-752 */
+void orc_svl_accumulate(float* svl, const float* phi, int cx, int cy, int cz, int nx2, int ny2, int nz2, float dx,
+                        float dy, float dz, float re, float im) {
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < nz2; ++z)
+        for (int y = 0; y < ny2; ++y)
+            for (int x = 0; x < nx2; ++x) {
+                size_t i = ((size_t)z * ny2 + y) * nx2 + x;
+                float b = tex3d(phi, cx, cy, cz, (float)(x * dx + 0.5), (float)(y * dy + 0.5), (float)(z * dz + 0.5));
+                float c = cosf(b), s = sinf(b);
+                float d = fmaf(c, re, -(s * im));
+                svl[i] = svl[i] + d;
+            }
+}
+
+/* classify_copy_Voxel: MarchingCubes_kernel.cu:158-447 */
+void orc_copy_parameter(orc_grid_point* vol_one, const float* vol_two, const float* vol_lattice, int dynamic,
+                        float iso1, float iso2, int nx, int ny, int nz, float iso, int obj_union, int obj_diff,
+                        int obj_intersect) {
+    const size_t n = (size_t)nx * ny * nz;
+    auto upd = [](float& tt, float t) { tt = (tt > 0) ? (tt + t) * 0.5f : t; };
+#pragma omp parallel for schedule(static)
+    for (int64_t ii = 0; ii < (int64_t)n - 1; ++ii) { /* guard i < N-1 :169 */
+        size_t i = (size_t)ii;
+        int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((size_t)nx * ny));
+        orc_grid_point g = vol_one[i];
+        float v = vol_two ? vol_two[i] : 0.f, vl = vol_lattice ? vol_lattice[i] : 0.f;
+        bool inband = (vl > iso1) & (vl < iso2);
+        bool fx = (float)g.val < iso;
+        if (obj_union) g.val = (dynamic ? (inband | fx) : ((v < iso) | fx)) ? -1 : 1;
+        else if (obj_diff) g.val = (dynamic ? (inband & ((float)g.val >= iso)) : ((v >= iso) & fx)) ? -1 : 1;
+        else if (obj_intersect) g.val = (dynamic ? (inband & fx) : ((v < iso) & fx)) ? -1 : 1;
+        const size_t step[3] = {1, (size_t)nx, (size_t)nx * ny};
+        const bool ok[3] = {x < nx - 1, y < ny - 1, z < nz - 1};
+        float* tp[3] = {&g.t_x, &g.t_y, &g.t_z};
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!ok[ax]) continue;
+            if (dynamic) {
+                float o = vol_lattice[i + step[ax]];
+                if (((o < iso1) && (vl >= iso1)) || ((o >= iso1) && (vl < iso1))) upd(*tp[ax], (iso1 - vl) / (o - vl));
+                else if (((o < iso2) && (vl >= iso2)) || ((o >= iso2) && (vl < iso2))) upd(*tp[ax], (iso2 - vl) / (o - vl));
+            } else {
+                float o = vol_two[i + step[ax]];
+                if (((o < iso) && (v >= iso)) || ((o >= iso) && (v < iso))) upd(*tp[ax], (iso - v) / (o - v));
+            }
+        }
+        vol_one[i] = g;
+    }
+}
+
+/* primitive_field_kernel: Gratings.cu:1695-1725 */
+void orc_primitive_field(const orc_grid_point* prim, const float* active, float* isosurf, size_t n, int fixed,
+                         int dynamic) {
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        if (fixed) { if ((float)prim[i].val > -1) isosurf[i] = __FLT_MAX__; }
+        else if (dynamic) { if (active[i] >= 0) isosurf[i] = __FLT_MAX__; }
+    }
+}
+/* topo_field_kernel: Gratings.cu:1666-1681 */
+void orc_topo_field(const float* topo, float* isosurf, float volfrac, size_t n) {
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; ++i) if (topo[i] < volfrac) isosurf[i] = 0.f;
+}
+/* patch_topo_field_kernel: Isosurface.cu:674-707.  Its index decomposition is wrong
+ * (x = tx/(Nx*Ny), y = x/Nx, z = x%Nx) and only acts as a guard; restated literally. */
+void orc_patch_topo_field(float* d, int nx, int ny, int nz, const orc_grid_point* vol_one) {
+    const size_t n = (size_t)nx * ny * nz;
+#pragma omp parallel for
+    for (int64_t tx = 0; tx < (int64_t)n; ++tx) {
+        uint32_t gx = (uint32_t)(tx / ((int64_t)nx * ny)), gy = gx / (uint32_t)nx, gz = gx % (uint32_t)nx;
+        if (gx < (uint32_t)nx && gy < (uint32_t)ny && gz < (uint32_t)nz)
+            if ((float)vol_one[tx].val == 1) d[tx] = 0.f;
+    }
+}
+
+/* File_output::file_write_obj: File_output.cu:5-81 */
+int orc_write_obj(const float* pos, uint32_t total_verts, const char* filename) {
+    std::ofstream out(filename, std::ios::out);
+    if (!out) return -1;
+    out << "##Sample latttice new Obj \n";
+    out << "o Solid \n";
+    std::map<std::vector<float>, int> seen;
+    std::vector<uint32_t> faces;
+    int index = 0;
+    for (uint32_t i = 0; i < total_verts; ++i) {
+        float vx = (float)(int(pos[4 * (size_t)i] * 1000) * 0.001);
+        float vy = (float)(int(pos[4 * (size_t)i + 1] * 1000) * 0.001);
+        float vz = (float)(int(pos[4 * (size_t)i + 2] * 1000) * 0.001);
+        std::vector<float> key = {vx, vy, vz};
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            ++index;
+            seen[key] = index;
+            faces.push_back(index);
+            out << "v " << vx << " " << vy << " " << vz << "\n";
+        } else faces.push_back(it->second);
+    }
+    out << "\n";
+    out << "\n";
+    std::map<std::vector<uint32_t>, int> fseen;
+    for (size_t i = 0; i + 2 < faces.size(); i += 3) {
+        if (faces[i] != faces[i + 1] && faces[i] != faces[i + 2] && faces[i + 1] != faces[i + 2]) {
+            std::vector<uint32_t> key = {faces[i], faces[i + 1], faces[i + 2]};
+            if (!fseen.count(key)) {
+                fseen[key] = 1;
+                out << " f  " << faces[i] << " " << faces[i + 2] << " " << faces[i + 1] << "\n";
+            }
+        }
+    }
+    out.close();
+    return 0;
+}
+
+} // extern "C"

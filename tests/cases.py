@@ -1,0 +1,42 @@
+"""Small, deterministic test cases shared by the golden generator (tests/golden/make_golden.py, runs the
+reference CUDA kernels on the GPU box), the CPU oracle tests and the GPU parity tests.  Sizes are
+chosen so the CPU oracle finishes in well under a second."""
+import numpy as np
+
+# reference UI defaults: bound_isoVal / bound_isoValone / bound_isoValtwo (ImguiApp.cpp:103-105)
+ISO_MASK, BAND_LO, BAND_HI = 0.25, 0.20, 0.30
+
+GYROID = dict(n=32, type=0)                     # config 1 in miniature (create_lattice -> normalise -> band -> latticeone)
+TPMS_TYPES = [0, 1, 2, 3, 4, 5]
+
+# config 2 in miniature: fine grid 48^3, dx2 = 0.5 (coarse 24^3)
+CSG = dict(dims=(48, 48, 48), d=(0.5, 0.5, 0.5),
+           sphere=dict(center=(0.0, 0.0, 0.0), radius=7.5, thickness=2.0),
+           cuboid=dict(center=(1.0, 0.5, -0.5), angles=(0.3, 0.2, 0.1), xw=17.0, yw=9.0, zw=11.0),
+           cylinder=dict(center=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), radius=3.4, tr=2.0, ta=40.0))
+
+PRIMS = dict(dims=(40, 36, 44), d=(0.5, 0.5, 0.5), center=(0.7, -0.4, 0.3), angles=(0.3, 0.2, 0.1))
+
+# configs 3/4 in miniature: control 12^3 -> fine 24^3 (ratio 2, the app's own), and control 8^3 -> fine 32^3 (ratio 4)
+SVL = dict(cdims=(12, 12, 12), fdims=(24, 24, 24), d=(0.5, 0.5, 0.5), nh=10)
+SVL4 = dict(cdims=(8, 8, 8), fdims=(32, 32, 32), d=(0.25, 0.25, 0.25), nh=6)
+
+# config 5 in miniature: coarse 24x12x12 -> fine 48x24x24, iso = VolumeFraction 0.4
+TOPO = dict(cdims=(24, 12, 12), fdims=(48, 24, 24), d=(0.5, 0.5, 0.5), iso=0.4)
+
+
+def svl_inputs(cfg):
+    from gpucadforam_b200 import synth
+    cx, cy, cz = cfg["cdims"]
+    phi = synth.phase_grids(cx, cy, cz, periods=3.0, harmonics=synth.HARMONICS[20:20 + cfg["nh"]]).numpy()
+    coef = synth.gyroid_coefficients()[20:20 + cfg["nh"]]
+    # make sure no coefficient is exactly zero so every harmonic contributes
+    coef = [(c[0] + 0.05 * ((i % 3) - 1), c[1] + 0.03 * ((i % 2) * 2 - 1)) for i, c in enumerate(coef)]
+    coef = [(float(np.float32(a)), float(np.float32(b))) for a, b in coef]
+    return phi, coef
+
+
+def topo_coarse(cfg):
+    from gpucadforam_b200 import synth
+    cx, cy, cz = cfg["cdims"]
+    return synth.cantilever_density(cx, cy, cz, struts=12, sigma=1.0).numpy()

@@ -1,0 +1,161 @@
+"""ctypes wrapper of oracle/_ref/libgpucad_ref.so: the UNMODIFIED reference CUDA kernels behind the
+headless harness oracle/ref_harness.cu.  TEST / BASELINE INFRASTRUCTURE ONLY (needs a GPU)."""
+import ctypes as C
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATH = os.path.join(ROOT, "oracle", "_ref", "libgpucad_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(PATH)
+        assert _lib.ref_init() == 0
+    return _lib
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+F = C.c_float
+
+
+def _ok(rc):
+    assert rc == 0, "reference harness call failed"
+
+
+def create_lattice(out, nx, ny, nz, typ):
+    _ok(lib().ref_create_lattice(_p(out), C.c_uint(nx), C.c_uint(ny), C.c_uint(nz), C.c_uint(typ)))
+
+
+def sphere(out, center, r, t, dims, d, shell):
+    _ok(lib().ref_sphere(_p(out), F(center[0]), F(center[1]), F(center[2]), F(r), F(t), dims[0], dims[1], dims[2], F(d[0]), F(d[1]), F(d[2]), int(shell)))
+
+
+def distance_from_line(out, center, axis, r, tr, ta, dims, d, disc):
+    _ok(lib().ref_distance_from_line(_p(out), F(center[0]), F(center[1]), F(center[2]), F(axis[0]), F(axis[1]), F(axis[2]), F(r), F(tr), F(ta), dims[0],
+                                     dims[1], dims[2], F(d[0]), F(d[1]), F(d[2]), int(disc)))
+
+
+def _rot(fn, out, center, ang, params, dims, d):
+    _ok(getattr(lib(), fn)(_p(out), F(center[0]), F(center[1]), F(center[2]), F(ang[0]), F(ang[1]), F(ang[2]), *[F(p) for p in params], dims[0], dims[1],
+                           dims[2], F(d[0]), F(d[1]), F(d[2])))
+
+
+def cuboid(out, center, ang, xw, yw, zw, dims, d):
+    _rot("ref_cuboid", out, center, ang, (xw, yw, zw), dims, d)
+
+
+def cuboid_shell(out, center, ang, xw, yw, zw, th, dims, d):
+    _rot("ref_cuboid_shell", out, center, ang, (xw, yw, zw, th), dims, d)
+
+
+def torus(out, center, ang, R, rc, dims, d):
+    _rot("ref_torus", out, center, ang, (R, rc), dims, d)
+
+
+def cone(out, center, ang, br, h, dims, d):
+    _rot("ref_cone", out, center, ang, (br, h), dims, d)
+
+
+def cone_frustum(out, center, ang, tr, br, h, dims, d):
+    _rot("ref_cone_frustum", out, center, ang, (tr, br, h), dims, d)
+
+
+def pyramid_frustum(out, center, ang, xb, xt, yh, zb, zt, dims, d):
+    _rot("ref_pyramid_frustum", out, center, ang, (xb, xt, yh, zb, zt), dims, d)
+
+
+def normalise_buffer(inp, out, n):
+    _ok(lib().ref_normalise_buffer(_p(inp), _p(out), int(n)))
+
+
+def normalise_four(inp, mask, k, dims, iso1, iso2):
+    _ok(lib().ref_normalise_four(_p(inp), _p(mask), _p(k), C.c_size_t(dims[0] * dims[1] * dims[2]), dims[0], dims[1], dims[2], F(iso1), F(iso2)))
+
+
+def setup_texture(cx, cy, cz):
+    _ok(lib().ref_setup_texture(cx, cy, cz))
+
+
+def upload_texture(phi, cx, cy, cz):
+    _ok(lib().ref_upload_texture(_p(phi), cx, cy, cz))
+
+
+def delete_texture():
+    _ok(lib().ref_delete_texture())
+
+
+def refine(out, fdims, d):
+    _ok(lib().ref_refine(_p(out), fdims[0], fdims[1], fdims[2], F(d[0]), F(d[1]), F(d[2])))
+
+
+def svl_field(svl, ga, phi, nh, coef_dev, cdims, fdims, d):
+    _ok(lib().ref_svl_field(_p(svl), _p(ga), _p(phi), nh, _p(coef_dev), cdims[0], cdims[1], cdims[2], fdims[0], fdims[1], fdims[2], F(d[0]), F(d[1]),
+                            F(d[2])))
+
+
+def copy_parameter(vol_one, vol_two, vol_lattice, dims, voxel, iso, fixed=False, dynamic=False, iso1=0.2, iso2=0.3, obj_union=True, obj_diff=False,
+                   obj_intersect=False):
+    _ok(lib().ref_copy_parameter(None, F(iso), C.c_uint(dims[0]), C.c_uint(dims[1]), C.c_uint(dims[2]), F(voxel[0]), F(voxel[1]), F(voxel[2]),
+                                 _p(vol_one), _p(vol_two), _p(vol_lattice), int(fixed), int(dynamic), F(iso1), F(iso2), int(obj_union), int(obj_diff),
+                                 int(obj_intersect)))
+
+
+def primitive_field(prim, active, isosurf, fixed, dynamic, dims):
+    _ok(lib().ref_primitive_field(_p(prim), _p(active), _p(isosurf), int(fixed), int(dynamic), dims[0], dims[1], dims[2]))
+
+
+def topo_field(topo, isosurf, volfrac, dims):
+    _ok(lib().ref_topo_field(_p(topo), _p(isosurf), F(volfrac), dims[0], dims[1], dims[2]))
+
+
+def patch_topo_field(d, dims, vol_one):
+    _ok(lib().ref_patch_topo_field(_p(d), dims[0], dims[1], dims[2], _p(vol_one)))
+
+
+def _scr(s):
+    return [_p(s.voxelVerts), _p(s.voxelVertsScan), _p(s.voxelOccupied), _p(s.voxelOccupiedScan), _p(s.compVoxelArray)]
+
+
+def isosurface_lattice(one, fix_grid, vol, pos, norm, iso, dims, voxel, center, s, max_verts, vol_one, vol_two, isovalue1, isovalue2, iso1=0.0, iso2=0.0):
+    act, tot = C.c_uint(0), C.c_uint(0)
+    _ok(lib().ref_isosurface_lattice(int(one), int(fix_grid), _p(vol), _p(pos), _p(norm), F(iso), C.c_uint(dims[0]), C.c_uint(dims[1]), C.c_uint(dims[2]),
+                                     F(voxel[0]), F(voxel[1]), F(voxel[2]), F(center[0]), F(center[1]), F(center[2]), *_scr(s), C.c_uint(max_verts),
+                                     _p(vol_one), _p(vol_two), F(isovalue1), F(isovalue2), F(iso1), F(iso2), C.byref(act), C.byref(tot)))
+    return act.value, tot.value
+
+
+def isosurface_csg(fix_grid, pos, norm, iso, dims, voxel, center, s, max_verts, fixed_f, dynamic_f, lattice_f, iso1=0.2, iso2=0.3, obj_union=True,
+                   obj_diff=False, obj_intersect=False, fixed=False, dynamic=False, make_region=False, topo_f=None):
+    act, tot = C.c_uint(0), C.c_uint(0)
+    _ok(lib().ref_isosurface_csg(int(fix_grid), _p(pos), _p(norm), F(iso), C.c_uint(dims[0]), C.c_uint(dims[1]), C.c_uint(dims[2]), F(voxel[0]), F(voxel[1]),
+                                 F(voxel[2]), F(center[0]), F(center[1]), F(center[2]), *_scr(s), C.c_uint(max_verts), _p(fixed_f), _p(dynamic_f),
+                                 _p(topo_f), _p(lattice_f), F(iso1), F(iso2), int(obj_union), int(obj_diff), int(obj_intersect), int(fixed), int(dynamic),
+                                 int(make_region), C.byref(act), C.byref(tot)))
+    return act.value, tot.value
+
+
+def isosurface_topo(with_disp_variant, pos, norm, iso, dims, voxel, center, s, max_verts, vol_topo, vol_two, isovalue1, d_result, disp=False, disp_two=None,
+                    vol_one=None, d_solid=None):
+    act, tot = C.c_uint(0), C.c_uint(0)
+    _ok(lib().ref_isosurface_topo(int(with_disp_variant), _p(pos), _p(norm), F(iso), C.c_uint(dims[0]), C.c_uint(dims[1]), C.c_uint(dims[2]), F(voxel[0]),
+                                  F(voxel[1]), F(voxel[2]), F(center[0]), F(center[1]), F(center[2]), *_scr(s), C.c_uint(max_verts), _p(vol_topo),
+                                  _p(vol_one), _p(vol_two), _p(d_solid), F(isovalue1), _p(d_result), int(disp), _p(disp_two), C.byref(act), C.byref(tot)))
+    return act.value, tot.value
+
+
+def write_obj(pos, total_verts, filename):
+    _ok(lib().ref_write_obj(_p(pos), C.c_uint(total_verts), filename.encode()))

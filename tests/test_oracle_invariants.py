@@ -1,0 +1,108 @@
+"""Known-answer style checks of the CPU oracle: the reference ships no tests, so
+these are closed-form invariants; the golden-vector tests (test_oracle_golden.py) pin it to the
+reference's own CUDA output."""
+import numpy as np
+
+import cases
+import oracle_py as orc
+
+
+def _band_case(n=24, typ=0):
+    f = orc.normalise_buffer(orc.create_lattice(n, n, n, typ))
+    mask, k = orc.normalise_four(f, cases.BAND_LO, cases.BAND_HI)
+    return mask, k
+
+
+def test_scans_and_counts_are_consistent():
+    mask, k = _band_case()
+    n = mask.shape[0]
+    r = orc.extract(orc.MODE_LATTICE_ONE, (n, n, n), (1, 1, 1), (0, 0, 0), cases.ISO_MASK, f0=mask, f1=k, iso1=cases.BAND_LO, iso2=cases.BAND_HI)
+    assert r["total"] == int(r["voxelVerts"].sum()) and r["total"] % 3 == 0 and r["total"] > 0
+    assert r["active"] == int(r["voxelOccupied"].sum()) == len(r["compVoxelArray"])
+    assert np.all(np.diff(r["compVoxelArray"].astype(np.int64)) > 0)
+    assert np.array_equal(r["voxelVertsScan"], np.concatenate([[0], np.cumsum(r["voxelVerts"])[:-1]]).astype(np.uint32))
+    assert np.array_equal(r["voxelOccupiedScan"], np.concatenate([[0], np.cumsum(r["voxelOccupied"])[:-1]]).astype(np.uint32))
+    a, t = orc.count(orc.MODE_LATTICE_ONE, (n, n, n), cases.ISO_MASK, f0=mask, f1=k)
+    assert (a, t) == (r["active"], r["total"])
+    # w components: pos.w = 1, norm.w = 0 for the lattice variants
+    assert np.all(r["pos"][:r["total"], 3] == 1.0) and np.all(r["norm"][:r["total"], 3] == 0.0)
+    # all vertices inside the domain; forced-closed faces (A-13): nothing outside [0, n-1]
+    p = r["pos"][:r["total"], :3]
+    assert p.min() >= 0.0 and p.max() <= n - 1
+
+
+def test_band_vertices_lie_on_band_edges():
+    """Each vertex sits on a grid edge; interpolating k there gives iso1 or iso2 unless it was snapped."""
+    mask, k = _band_case(20)
+    n = 20
+    r = orc.extract(orc.MODE_LATTICE_ONE, (n, n, n), (1, 1, 1), (0, 0, 0), cases.ISO_MASK, f0=mask, f1=k, iso1=cases.BAND_LO, iso2=cases.BAND_HI)
+    p = r["pos"][:r["total"], :3].astype(np.float64)
+    frac = np.abs(p - np.round(p))
+    assert np.all((frac > 1e-6).sum(axis=1) <= 1)  # at most one non-integer coordinate
+
+
+def test_sphere_mesh_is_closed_and_near_the_sphere():
+    """B-3: plain CSG (union of nothing and a sphere), vertices within voxel*sqrt(3) of the sphere, Euler characteristic 2."""
+    n, d, rad = 36, 0.5, 6.0
+    dyn = orc.sphere((n, n, n), (d, d, d), (0, 0, 0), rad, 2.0, False)
+    gp = np.zeros(n * n * n, orc.GP_DTYPE)
+    c = (n - 1) / 2.0
+    r = orc.extract(orc.MODE_CSG, (n, n, n), (d, d, d), (c, c, c), 0.0, f0=dyn, gp=gp, flags=orc.F_UNION, iso1=0.2, iso2=0.3)
+    assert r["total"] > 0
+    p = r["pos"][:r["total"], :3].astype(np.float64)
+    dist = np.linalg.norm(p, axis=1)
+    assert np.all(np.abs(dist - rad) <= d * np.sqrt(3))
+    assert np.all(r["norm"][:r["total"], 3] == 0.5)
+    # weld and compute V - E + F
+    key = np.round(p * 4096).astype(np.int64)
+    _, inv = np.unique(key, axis=0, return_inverse=True)
+    tris = inv.reshape(-1, 3)
+    tris = tris[(tris[:, 0] != tris[:, 1]) & (tris[:, 1] != tris[:, 2]) & (tris[:, 0] != tris[:, 2])]
+    edges = np.sort(np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]]), axis=1)
+    ue, cnt = np.unique(edges, axis=0, return_counts=True)
+    assert np.all(cnt == 2)  # closed 2-manifold
+    V, E, Fc = len(np.unique(tris)), len(ue), len(tris)
+    assert V - E + Fc == 2
+
+
+def test_csg_truth_table():
+    """B-2: union s|d, diff (!d)&s, intersect s&d on a 2x2x2 grid with one corner toggled."""
+    for s in (0, 1):
+        for dbit in (0, 1):
+            gp = np.zeros(8, orc.GP_DTYPE)
+            gp["val"] = 1
+            gp["val"][0] = -1 if s else 1
+            dyn = np.ones((2, 2, 2), np.float32)
+            dyn[0, 0, 0] = -1.0 if dbit else 1.0
+            for flag, expect in ((orc.F_UNION, s | dbit), (orc.F_DIFF, (1 - dbit) & s), (orc.F_INTERSECT, s & dbit)):
+                a, t = orc.count(orc.MODE_CSG, (2, 2, 2), 0.0, f0=dyn, gp=gp, flags=flag)
+                assert (t == 3) == bool(expect), (s, dbit, flag)
+
+
+def test_minmax_is_clamped_through_zero():
+    """Min_reduction_lattice seeds its lanes with {0,0} (Gratings.cu:1443-1468)."""
+    assert orc.minmax(np.array([2.0, 3.0, 5.0], np.float32)) == (0.0, 5.0)
+    assert orc.minmax(np.array([-2.0, -3.0], np.float32)) == (-3.0, 0.0)
+
+
+def test_refine_even_points_copy_and_odd_points_average():
+    rng = np.random.RandomState(0)
+    c = rng.rand(5, 6, 7).astype(np.float32)
+    f = orc.refine(c, (14, 12, 10), (0.5, 0.5, 0.5))
+    assert np.array_equal(f[::2, ::2, ::2], c)
+    assert np.allclose(f[0, 0, 1:-1:2], 0.5 * (c[0, 0, :-1].astype(np.float64) + c[0, 0, 1:]), rtol=0, atol=1e-7)
+    assert np.array_equal(f[-1], f[-2])  # last fine plane clamps to the last control plane (A-12)
+
+
+def test_obj_writer_welds_and_flips(tmp_path):
+    pos = np.array([[0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1],
+                    [1, 0, 0, 1], [1, 1, 0, 1], [0, 1, 0, 1],
+                    [0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1],            # duplicate face -> dropped
+                    [2, 2, 2, 1], [2, 2, 2.0004, 1], [3, 3, 3, 1]], np.float32)  # degenerate after quantisation
+    path = str(tmp_path / "t.obj")
+    assert orc.write_obj(pos, 12, path) == 0
+    text = open(path).read()
+    assert text.startswith("##Sample latttice new Obj \no Solid \n")
+    assert text.count("\nv ") + text.startswith("v ") == 6
+    faces = [l for l in text.splitlines() if l.startswith(" f ")]
+    assert faces == [" f  1 3 2", " f  2 3 4"]
