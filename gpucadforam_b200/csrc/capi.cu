@@ -99,8 +99,20 @@ int gcb_set_options(gcb_ctx* ctx, unsigned int flags) { CTX(ctx); C->options = f
 unsigned long long gcb_launch_count(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); return C ? C->launches : 0; }
 void gcb_reset_launch_count(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); if (C) C->launches = 0; }
 int gcb_enable_kernel_timing(gcb_ctx* ctx, int on) { CTX(ctx); C->timing = on != 0; return 0; }
-float gcb_last_extract_kernel_ms(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); return C ? C->last_extract_ms : -1.f; }
-float gcb_last_field_kernel_ms(gcb_ctx* ctx) { Ctx* C = reinterpret_cast<Ctx*>(ctx); return C ? C->last_field_ms : -1.f; }
+float gcb_last_extract_kernel_ms(gcb_ctx* ctx) {
+    Ctx* C = reinterpret_cast<Ctx*>(ctx);
+    if (!C || !C->extract_timed) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(C->ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, C->ev[0], C->ev[1]) != cudaSuccess) return -1.f;
+    return ms;
+}
+float gcb_last_field_kernel_ms(gcb_ctx* ctx) {
+    Ctx* C = reinterpret_cast<Ctx*>(ctx);
+    if (!C || !C->field_timed) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(C->ev[3]) != cudaSuccess || cudaEventElapsedTime(&ms, C->ev[2], C->ev[3]) != cudaSuccess) return -1.f;
+    return ms;
+}
 
 void gcb_tables(unsigned int* tri, unsigned int* nverts) { host_tables(tri, nverts); }
 
@@ -387,9 +399,8 @@ int gcb_svl_field(gcb_ctx* ctx, float* d_svl, const float* d_phi, int nh, const 
     if (int r = k_svl_field(C, d_svl, d_phi, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, NZ2_local, slab.z0, dx, dy, dz, accumulate,
                             d_minmax ? C->d_minmax : nullptr))
         return r;
-    if (C->timing) cudaEventRecord(C->ev[3], C->stream);
+    if (C->timing) { cudaEventRecord(C->ev[3], C->stream); C->field_timed = true; }
     if (d_minmax) if (int r = k_minmax_decode(C, C->d_minmax, d_minmax)) return r;
-    if (C->timing) { GCB_CHECK(C, cudaStreamSynchronize(C->stream)); cudaEventElapsedTime(&C->last_field_ms, C->ev[2], C->ev[3]); }
     return 0;
 }
 

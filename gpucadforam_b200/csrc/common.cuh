@@ -84,7 +84,7 @@ struct Ctx {
     // timing
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float last_extract_ms = -1.f, last_field_ms = -1.f;
+    bool extract_timed = false, field_timed = false;
 };
 
 int fail(Ctx* c, const char* what, cudaError_t e);

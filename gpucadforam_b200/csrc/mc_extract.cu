@@ -614,10 +614,9 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     }
     if (e != cudaSuccess) return fail(c, "mc_fused_kernel launch", e);
     c->launches++;
-    if (c->timing) cudaEventRecord(c->ev[1], c->stream);
+    if (c->timing) { cudaEventRecord(c->ev[1], c->stream); c->extract_timed = true; }
     GCB_CHECK(c, cudaMemcpyAsync(c->h_totals, c->d_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     GCB_CHECK(c, cudaStreamSynchronize(c->stream));
-    if (c->timing) cudaEventElapsedTime(&c->last_extract_ms, c->ev[0], c->ev[1]);
     *active = c->h_totals[0];
     *verts = c->h_totals[0] ? c->h_totals[1] : 0;  // early-out of Isosurface.cu:83-87
     return 0;

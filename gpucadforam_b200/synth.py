@@ -38,7 +38,7 @@ def phase_grids(cx, cy, cz, device="cpu", z0=0, cz_total=None, harmonics=None, p
     exactly the planes a single rank would."""
     harmonics = HARMONICS if harmonics is None else harmonics
     cz_total = cz if cz_total is None else cz_total
-    n = float(max(cx, cy, cz_total))
+    n = float(max(cx, cy))  # independent of the z extent so z-slab / weak-scaling runs see the same lattice period
     x = torch.arange(cx, device=device, dtype=torch.float64) - (cx - 1) / 2.0
     y = torch.arange(cy, device=device, dtype=torch.float64) - (cy - 1) / 2.0
     z = torch.arange(z0, z0 + cz, device=device, dtype=torch.float64) - (cz_total - 1) / 2.0

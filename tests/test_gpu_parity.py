@@ -1,0 +1,595 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box).  Every call goes through the C ABI
+(libgpucad_b200.so).  Three-way comparison on identical inputs:
+    product library  vs  the reference's own CUDA kernels (oracle/_ref, when the prebuilt .so travelled)
+                     vs  the CPU oracle (oracle/liboracle.so)
+Bar: stage arrays, counts, cube topology bit-exact; vertex positions / normals bit-exact against the
+reference kernels (same compiler, same expression order) and within 1e-5 relative against the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on the CPU box too; everything here is skipped there
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import gpucadforam_b200 as g
+from gpucadforam_b200 import _capi
+
+import cases
+import oracle_py as orc
+import ref_py as ref
+from gpu_util import *  # noqa: F401,F403
+
+HAVE_REF = ref.available()
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libgpucad_ref.so not present")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(0, options=_capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET)
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------ fields
+@needs_ref
+@pytest.mark.parametrize("typ", cases.TPMS_TYPES)
+def test_create_lattice_matches_reference(ctx, typ):
+    n = 33  # odd, not a multiple of anything
+    mine = torch.zeros(n * n * n, device="cuda")
+    theirs = torch.zeros_like(mine)
+    g.Fft_lattice(ctx).create_lattice(mine, n, n, n, n * n * n, typ)
+    ref.create_lattice(theirs, n, n, n, typ)
+    assert_bits_equal(mine, theirs, "create_lattice type %d" % typ)
+    o = orc.create_lattice(n, n, n, typ).reshape(-1)
+    assert np.allclose(mine.cpu().numpy(), o, rtol=0, atol=4e-6), "oracle TPMS type %d" % typ
+
+
+def _prim_calls(ctx):
+    P = cases.PRIMS
+    dims, d, c, a = P["dims"], P["d"], P["center"], P["angles"]
+    m = g.Modelling(ctx)
+    nx, ny, nz = dims
+    return dims, d, [
+        ("sphere", lambda o: m.sphere_with_center(o, c, 6.5, 2.0, nx, ny, nz, *d, False), lambda o: ref.sphere(o, c, 6.5, 2.0, dims, d, False),
+         lambda: orc.sphere(dims, d, c, 6.5, 2.0, False)),
+        ("sphere_shell", lambda o: m.sphere_with_center(o, c, 6.5, 2.0, nx, ny, nz, *d, True), lambda o: ref.sphere(o, c, 6.5, 2.0, dims, d, True),
+         lambda: orc.sphere(dims, d, c, 6.5, 2.0, True)),
+        ("cylinder", lambda o: m.distance_from_line(o, c, (0.2, 0.1, 1.0), 4.0, 2.0, 9.0, nx, ny, nz, *d, False),
+         lambda o: ref.distance_from_line(o, c, (0.2, 0.1, 1.0), 4.0, 2.0, 9.0, dims, d, False),
+         lambda: orc.distance_from_line(dims, d, c, (0.2, 0.1, 1.0), 4.0, 2.0, 9.0, False)),
+        ("cylinder_disc", lambda o: m.distance_from_line(o, c, (0.2, 0.1, 1.0), 4.0, 2.0, 9.0, nx, ny, nz, *d, True),
+         lambda o: ref.distance_from_line(o, c, (0.2, 0.1, 1.0), 4.0, 2.0, 9.0, dims, d, True),
+         lambda: orc.distance_from_line(dims, d, c, (0.2, 0.1, 1.0), 4.0, 2.0, 9.0, True)),
+        ("cuboid", lambda o: m.cuboid(o, c, a, 9.0, 5.0, 7.0, nx, ny, nz, *d), lambda o: ref.cuboid(o, c, a, 9.0, 5.0, 7.0, dims, d),
+         lambda: orc.cuboid(dims, d, c, a, 9.0, 5.0, 7.0)),
+        ("cuboid_shell", lambda o: m.cuboid_shell(o, c, a, 9.0, 5.0, 7.0, 1.0, nx, ny, nz, *d), lambda o: ref.cuboid_shell(o, c, a, 9.0, 5.0, 7.0, 1.0, dims, d),
+         lambda: orc.cuboid_shell(dims, d, c, a, 9.0, 5.0, 7.0, 1.0)),
+        ("torus", lambda o: m.torus_with_center(o, c, a, 5.0, 2.0, nx, ny, nz, *d), lambda o: ref.torus(o, c, a, 5.0, 2.0, dims, d),
+         lambda: orc.torus(dims, d, c, a, 5.0, 2.0)),
+        ("cone", lambda o: m.cone_with_base_radius_height(o, c, a, 4.0, 8.0, nx, ny, nz, *d), lambda o: ref.cone(o, c, a, 4.0, 8.0, dims, d),
+         lambda: orc.cone(dims, d, c, a, 4.0, 8.0)),
+        ("cone_frustum", lambda o: m.cone_frustum(o, c, a, 2.0, 5.0, 8.0, nx, ny, nz, *d), lambda o: ref.cone_frustum(o, c, a, 2.0, 5.0, 8.0, dims, d),
+         lambda: orc.cone_frustum(dims, d, c, a, 2.0, 5.0, 8.0)),
+        ("pyramid_frustum", lambda o: m.pyramid_frustum(o, c, a, 8.0, 4.0, 7.0, 6.0, 3.0, nx, ny, nz, *d),
+         lambda o: ref.pyramid_frustum(o, c, a, 8.0, 4.0, 7.0, 6.0, 3.0, dims, d), lambda: orc.pyramid_frustum(dims, d, c, a, 8.0, 4.0, 7.0, 6.0, 3.0)),
+    ]
+
+
+@pytest.mark.parametrize("idx", range(10))
+def test_primitives(ctx, idx):
+    dims, d, calls = _prim_calls(ctx)
+    name, mine_fn, ref_fn, orc_fn = calls[idx]
+    n = dims[0] * dims[1] * dims[2]
+    mine = torch.zeros(n, device="cuda")
+    mine_fn(mine)
+    o = orc_fn().reshape(-1)
+    scale = max(1.0, float(np.abs(o).max()))
+    assert np.allclose(mine.cpu().numpy(), o, rtol=0, atol=2e-5 * scale), "oracle primitive %s: %g" % (name, np.abs(mine.cpu().numpy() - o).max())
+    if HAVE_REF:
+        theirs = torch.zeros_like(mine)
+        ref_fn(theirs)
+        assert_bits_equal(mine, theirs, "primitive " + name)
+
+
+@needs_ref
+def test_normalise_matches_reference(ctx):
+    n = 32
+    f = torch.zeros(n * n * n, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(f, n, n, n, n * n * n, 0)
+    lat = g.Gratings(ctx)
+    a, b = torch.zeros_like(f), torch.zeros_like(f)
+    lat.GPU_buffer_normalise_buffer(f, a, f.numel())
+    ref.normalise_buffer(f, b, f.numel())
+    assert_bits_equal(a, b, "GPU_buffer_normalise_buffer")
+    m1, k1, m2, k2 = [torch.zeros_like(f) for _ in range(4)]
+    lat.GPU_buffer_normalise_four(a, m1, k1, f.numel(), n, n, n, cases.BAND_LO, cases.BAND_HI)
+    ref.normalise_four(b, m2, k2, (n, n, n), cases.BAND_LO, cases.BAND_HI)
+    assert_bits_equal(m1, m2, "normalise_four mask")
+    assert_bits_equal(k1, k2, "normalise_four k")
+    om, ok = orc.normalise_four(a.cpu().numpy().reshape(n, n, n), cases.BAND_LO, cases.BAND_HI)
+    assert np.array_equal(om.reshape(-1), m1.cpu().numpy()) and np.array_equal(ok.reshape(-1), k1.cpu().numpy())
+    # all-positive input exercises the clamp-through-zero of the reference reduction
+    pos_f = (f.abs() + 0.5).contiguous()
+    lat.GPU_buffer_normalise_buffer(pos_f, a, f.numel())
+    ref.normalise_buffer(pos_f, b, f.numel())
+    assert_bits_equal(a, b, "normalise_buffer (positive input)")
+
+
+def _upsample(ctx, cfg, coarse):
+    cx, cy, cz = cfg["cdims"]
+    fx, fy, fz = cfg["fdims"]
+    lat = g.Gratings(ctx)
+    lat.setupTexture(cx, cy, cz)
+    c = dev(coarse)
+    pitched_buf = torch.zeros(cx * cy * cz, device="cuda")
+    pp = lat.pitched(pitched_buf, cx, cy)
+    lat.copytotexture(c, pp, cx, cy, cz)
+    lat.updateTexture(pp)
+    out = torch.zeros(fx * fy * fz, device="cuda")
+    lat.refine(out, fx, fy, fz, *cfg["d"])
+    return out
+
+
+@pytest.mark.parametrize("cfg", [cases.SVL, cases.SVL4, cases.TOPO], ids=["ratio2", "ratio4", "ratio2_aniso"])
+def test_refine_matches_texture_unit(ctx, cfg):
+    rng = np.random.RandomState(7)
+    cx, cy, cz = cfg["cdims"]
+    coarse = (rng.rand(cz, cy, cx).astype(np.float32) * 40 - 20)
+    mine = _upsample(ctx, cfg, coarse)
+    o = orc.refine(coarse, cfg["fdims"], cfg["d"]).reshape(-1)
+    assert np.allclose(mine.cpu().numpy(), o, rtol=0, atol=4e-6 * 20)
+    if HAVE_REF:
+        ref.setup_texture(cx, cy, cz)
+        ref.upload_texture(dev(coarse), cx, cy, cz)
+        theirs = torch.zeros_like(mine)
+        ref.refine(theirs, cfg["fdims"], cfg["d"])
+        ref.delete_texture()
+        # the texture unit's internal accumulation order is undocumented: require <= 1 ulp, report exactness
+        u = ulp_diff(mine, theirs)
+        print("refine vs tex3D: max ulp diff", u)
+        assert u <= 1
+
+
+@pytest.mark.parametrize("cfg", [cases.SVL, cases.SVL4], ids=["ratio2", "ratio4"])
+def test_svl_field(ctx, cfg):
+    phi, coef = cases.svl_inputs(cfg)
+    fx, fy, fz = cfg["fdims"]
+    dphi = dev(phi)
+    mine = torch.zeros(fx * fy * fz, device="cuda")
+    mm = torch.zeros(2, device="cuda")
+    g.svl_field(ctx, mine, dphi, coef, cfg["cdims"], cfg["fdims"], cfg["d"], d_minmax=mm)
+    o = orc.svl_field(phi, coef, cfg["fdims"], cfg["d"]).reshape(-1)
+    assert np.allclose(mine.cpu().numpy(), o, rtol=0, atol=2e-5), "fused SVL vs oracle: %g" % np.abs(mine.cpu().numpy() - o).max()
+    lo, hi = orc.minmax(mine.cpu().numpy())
+    assert (float(mm[0]), float(mm[1])) == (lo, hi)
+    # legacy per-harmonic path of the product library == fused kernel, bit for bit
+    lat = g.Gratings(ctx)
+    cx, cy, cz = cfg["cdims"]
+    lat.setupTexture(cx, cy, cz)
+    legacy = torch.zeros_like(mine)
+    ga = torch.zeros((fx * fy * fz, 2), device="cuda")
+    dcoef = dev(np.array(coef, np.float32))
+    pbuf = torch.zeros(cx * cy * cz, device="cuda")
+    for h in range(len(coef)):
+        pp = lat.pitched(pbuf, cx, cy)
+        lat.copytotexture(dphi[h].contiguous(), pp, cx, cy, cz)
+        lat.updateTexture(pp)
+        lat.grating(ga, fx, fy, fz, *cfg["d"])
+        lat.svl(legacy, ga, fx, fy, fz, h, dcoef)
+    assert_bits_equal(mine, legacy, "fused SVL vs legacy grating+svl")
+    if HAVE_REF:
+        ref.setup_texture(cx, cy, cz)
+        theirs = torch.zeros_like(mine)
+        ref.svl_field(theirs, ga, dphi, len(coef), dcoef, cfg["cdims"], cfg["fdims"], cfg["d"])
+        ref.delete_texture()
+        err = float((mine - theirs).abs().max())
+        print("SVL vs reference: max abs diff %g, max ulp %d" % (err, ulp_diff(mine, theirs)))
+        assert err <= 2e-5
+
+
+# ------------------------------------------------------------------ extraction
+def _lattice_inputs(ctx, n, typ=0):
+    f = torch.zeros(n * n * n, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(f, n, n, n, n * n * n, typ)
+    lat = g.Gratings(ctx)
+    lat.GPU_buffer_normalise_buffer(f, f, f.numel())
+    mask, k = torch.zeros_like(f), torch.zeros_like(f)
+    lat.GPU_buffer_normalise_four(f, mask, k, f.numel(), n, n, n, cases.BAND_LO, cases.BAND_HI)
+    return f, mask, k
+
+
+@pytest.mark.parametrize("n,typ", [(32, 0), (33, 1), (47, 3), (61, 0)])
+def test_latticeone_three_way(ctx, n, typ):
+    _, mask, k = _lattice_inputs(ctx, n, typ)
+    dims = (n, n, n)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    iso = g.Isosurface(ctx)
+    act, tot = iso.computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), mv, k, cases.BAND_LO, cases.BAND_HI)
+    assert tot > 0
+    mine = mine_result(scr, mesh, dims, act, tot)
+    o = orc.extract(orc.MODE_LATTICE_ONE, dims, (1, 1, 1), (0, 0, 0), cases.ISO_MASK, f0=mask.cpu().numpy(), f1=k.cpu().numpy(), iso1=cases.BAND_LO,
+                    iso2=cases.BAND_HI, max_verts=mv)
+    compare_extractions(mine, o, "latticeone vs oracle n=%d" % n, exact_mesh=False)
+    if HAVE_REF:
+        scr2, mesh2 = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+        a2, t2 = ref.isosurface_lattice(True, False, mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, (1, 1, 1), (0, 0, 0), scr2, mv, k, None,
+                                        cases.BAND_LO, cases.BAND_HI)
+        compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "latticeone vs reference n=%d" % n, exact_mesh=True)
+
+
+def test_lattice_variant_with_zero_vol_two(ctx):
+    n = 40
+    _, mask, k = _lattice_inputs(ctx, n, 0)
+    dims = (n, n, n)
+    mv = max_verts_for(dims)
+    zeros = torch.zeros_like(k)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    act, tot = g.Isosurface(ctx).computeIsosurface_lattice(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (0.5, 0.5, 0.5), (0, 0, 0), mv, k, zeros,
+                                                           cases.BAND_LO, cases.BAND_HI, 0.0, 0.0)
+    mine = mine_result(scr, mesh, dims, act, tot)
+    o = orc.extract(orc.MODE_LATTICE, dims, (0.5, 0.5, 0.5), (0, 0, 0), cases.ISO_MASK, f0=mask.cpu().numpy(), f1=k.cpu().numpy(), f2=zeros.cpu().numpy(),
+                    iso1=cases.BAND_LO, iso2=cases.BAND_HI, max_verts=mv)
+    compare_extractions(mine, o, "lattice vs oracle", exact_mesh=False)
+    if HAVE_REF:
+        scr2, mesh2 = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+        a2, t2 = ref.isosurface_lattice(False, False, mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, (0.5, 0.5, 0.5), (0, 0, 0), scr2, mv, k, zeros,
+                                        cases.BAND_LO, cases.BAND_HI, 0.0, 0.0)
+        compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "lattice vs reference", exact_mesh=True)
+
+
+def _csg_pipeline(ctx, use_ref):
+    """sphere -> retain(union); cuboid -> retain(union); cylinder with obj_diff -> mesh (config 2)."""
+    C = cases.CSG
+    dims, d = C["dims"], C["d"]
+    nx, ny, nz = dims
+    npts = nx * ny * nz
+    vol_one = gp_zeros(npts)
+    boundary = torch.zeros(npts, device="cuda")
+    m, iso = g.Modelling(ctx), g.Isosurface(ctx)
+    s, c, y = C["sphere"], C["cuboid"], C["cylinder"]
+
+    def retain(**kw):
+        if use_ref:
+            ref.copy_parameter(vol_one, boundary, None, dims, d, 0.0, **kw)
+        else:
+            iso.copy_parameter(0.0, dims, d, vol_one, boundary, None, **kw)
+
+    if use_ref:
+        ref.sphere(boundary, s["center"], s["radius"], s["thickness"], dims, d, False)
+    else:
+        m.sphere_with_center(boundary, s["center"], s["radius"], s["thickness"], nx, ny, nz, *d, False)
+    retain(obj_union=True)
+    if use_ref:
+        ref.cuboid(boundary, c["center"], c["angles"], c["xw"], c["yw"], c["zw"], dims, d)
+    else:
+        m.cuboid(boundary, c["center"], c["angles"], c["xw"], c["yw"], c["zw"], nx, ny, nz, *d)
+    retain(obj_union=True)
+    if use_ref:
+        ref.distance_from_line(boundary, y["center"], y["axis"], y["radius"], y["tr"], y["ta"], dims, d, False)
+    else:
+        m.distance_from_line(boundary, y["center"], y["axis"], y["radius"], y["tr"], y["ta"], nx, ny, nz, *d, False)
+    return vol_one, boundary
+
+
+def test_csg_pipeline_three_way(ctx, tmp_path):
+    C = cases.CSG
+    dims, d = C["dims"], C["d"]
+    mv = max_verts_for(dims)
+    ncell = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)
+    vol_one, boundary = _csg_pipeline(ctx, False)
+    scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+    act, tot, nf = g.Isosurface(ctx).computeIsosurface(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv, vol_one, boundary, None, obj_union=False,
+                                                       obj_diff=True)
+    assert tot > 0 and nf == tot // 3
+    mine = mine_result(scr, mesh, dims, act, tot)
+    # oracle on the product library's own inputs
+    o = orc.extract(orc.MODE_CSG, dims, d, (0, 0, 0), 0.0, f0=boundary.cpu().numpy(), gp=gp_to_numpy(vol_one), flags=orc.F_DIFF, iso1=0.2, iso2=0.3,
+                    max_verts=mv)
+    compare_extractions(mine, o, "CSG vs oracle", exact_mesh=False)
+    # oracle retain on the same primitive fields reproduces vol_one bit for bit
+    g.File_output(ctx).file_write_obj(mesh.pos, tot, str(tmp_path / "mine.obj"))
+    orc.write_obj(o["pos"], tot, str(tmp_path / "oracle.obj"))
+    if HAVE_REF:
+        vol_one_r, boundary_r = _csg_pipeline(ctx, True)
+        assert_bits_equal(boundary, boundary_r, "cylinder field")
+        assert_bits_equal(vol_one, vol_one_r, "grid_points after two retains")
+        scr2, mesh2 = g.Scratch(ncell), g.MeshBuffers(mv)
+        a2, t2 = ref.isosurface_csg(False, mesh2.pos, mesh2.norm, 0.0, dims, d, (0, 0, 0), scr2, mv, vol_one_r, boundary_r, None, obj_union=False,
+                                    obj_diff=True)
+        compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "CSG vs reference", exact_mesh=True)
+        # whole output buffers (including the byte-granular memset region) are identical
+        assert_bits_equal(mesh.pos, mesh2.pos, "CSG pos buffer incl. tail")
+        ref.write_obj(mesh2.pos, t2, str(tmp_path / "ref.obj"))
+        assert open(tmp_path / "mine.obj", "rb").read() == open(tmp_path / "ref.obj", "rb").read(), ".obj bytes differ from the reference writer"
+    # the oracle mesh may differ in the last ulp, which can flip a 1e-3 quantisation: compare structure, not bytes
+    mo, oo = open(tmp_path / "mine.obj").read().splitlines(), open(tmp_path / "oracle.obj").read().splitlines()
+    assert abs(len(mo) - len(oo)) <= max(4, len(mo) // 500)
+
+
+def test_csg_retain_matches_oracle(ctx):
+    C = cases.CSG
+    dims, d = C["dims"], C["d"]
+    nx, ny, nz = dims
+    npts = nx * ny * nz
+    s = C["sphere"]
+    boundary = torch.zeros(npts, device="cuda")
+    g.Modelling(ctx).sphere_with_center(boundary, s["center"], s["radius"], s["thickness"], nx, ny, nz, *d, False)
+    for kw in (dict(obj_union=True), dict(obj_union=False, obj_diff=True), dict(obj_union=False, obj_intersect=True)):
+        vol_one = gp_zeros(npts)
+        vol_one[:, 0] = torch.where(torch.arange(npts, device="cuda") % 3 == 0, -1, 1).to(torch.int32)
+        host = gp_to_numpy(vol_one).copy()
+        g.Isosurface(ctx).copy_parameter(0.0, dims, d, vol_one, boundary, None, **kw)
+        g.Isosurface(ctx).copy_parameter(0.0, dims, d, vol_one, boundary, None, **kw)  # second pass exercises the t averaging
+        b = boundary.cpu().numpy()
+        orc.copy_parameter(host, b, None, dims, 0.0, **kw)
+        orc.copy_parameter(host, b, None, dims, 0.0, **kw)
+        got = gp_to_numpy(vol_one)
+        assert np.array_equal(got.view(np.uint32), host.view(np.uint32)), "copy_parameter %s" % kw
+
+
+@pytest.mark.parametrize("mode", ["fixed_union", "dynamic_union", "dynamic_diff", "fixed_intersect", "make_region"])
+def test_csg_lattice_modes(ctx, mode):
+    """lattice_fixed / lattice_dynamic / make_region branches of classifyVoxel + generateTriangles_lattice_kernel."""
+    n = 36
+    dims, d = (n, n, n), (0.5, 0.5, 0.5)
+    npts = n ** 3
+    _, _, k = _lattice_inputs(ctx, n, 0)                      # lattice_field in [0,1]
+    dyn = torch.zeros(npts, device="cuda")
+    g.Modelling(ctx).sphere_with_center(dyn, (0, 0, 0), 6.0, 2.0, n, n, n, *d, False)
+    vol_one = gp_zeros(npts)
+    box = torch.zeros(npts, device="cuda")
+    g.Modelling(ctx).cuboid(box, (0.5, 0, 0), (0.1, 0.2, 0.3), 11.0, 9.0, 7.0, n, n, n, *d)
+    g.Isosurface(ctx).copy_parameter(0.0, dims, d, vol_one, box, None, obj_union=True)
+    if mode.startswith("dynamic"):  # retain the lattice band into the grid (dynamic retain captures band crossings)
+        g.Isosurface(ctx).copy_parameter(0.0, dims, d, vol_one, box, k, dynamic=True, iso1=cases.BAND_LO, iso2=cases.BAND_HI, obj_union=False,
+                                         obj_intersect=True)
+    kw = dict(fixed=mode.startswith("fixed"), dynamic=mode.startswith("dynamic"), make_region=mode == "make_region",
+              obj_union=mode.endswith("union") or mode == "make_region", obj_diff=mode.endswith("diff"), obj_intersect=mode.endswith("intersect"))
+    flags = (orc.F_FIXED if kw["fixed"] else 0) | (orc.F_DYNAMIC if kw["dynamic"] else 0) | (orc.F_MAKE_REGION if kw["make_region"] else 0) | \
+            (orc.F_UNION if kw["obj_union"] else 0) | (orc.F_DIFF if kw["obj_diff"] else 0) | (orc.F_INTERSECT if kw["obj_intersect"] else 0)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    act, tot, _ = g.Isosurface(ctx).computeIsosurface(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv, vol_one, dyn, k, iso1=cases.BAND_LO,
+                                                      iso2=cases.BAND_HI, **kw)
+    assert tot > 0
+    mine = mine_result(scr, mesh, dims, act, tot)
+    o = orc.extract(orc.MODE_CSG, dims, d, (0, 0, 0), 0.0, f0=dyn.cpu().numpy(), f1=k.cpu().numpy(), gp=gp_to_numpy(vol_one), flags=flags,
+                    iso1=cases.BAND_LO, iso2=cases.BAND_HI, max_verts=mv)
+    compare_extractions(mine, o, "CSG %s vs oracle" % mode, exact_mesh=False)
+    if HAVE_REF:
+        scr2, mesh2 = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+        a2, t2 = ref.isosurface_csg(False, mesh2.pos, mesh2.norm, 0.0, dims, d, (0, 0, 0), scr2, mv, vol_one, dyn, k, iso1=cases.BAND_LO, iso2=cases.BAND_HI,
+                                    **kw)
+        compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "CSG %s vs reference" % mode, exact_mesh=True)
+
+
+@pytest.mark.parametrize("variant", ["_2", "_topo", "_topo_disp"])
+def test_topo_three_way(ctx, variant):
+    T = cases.TOPO
+    fx, fy, fz = T["fdims"]
+    dims = (fx, fy, fz)
+    npts = fx * fy * fz
+    dens = _upsample(ctx, T, cases.topo_coarse(T))            # refine(d_volume_twice) main.cu:3060-3064
+    rng = np.random.RandomState(3)
+    vol_topo = gp_zeros(npts)
+    # a few stored crossing parameters and a solid (val = -1) patch, as a retained primitive would leave them
+    host = gp_to_numpy(vol_topo).copy()
+    host["t_x"] = np.where(rng.rand(npts) < 0.2, rng.rand(npts), 0).astype(np.float32)
+    host["t_z"] = np.where(rng.rand(npts) < 0.2, rng.rand(npts), 0).astype(np.float32)
+    host["val"][:200] = -1
+    vol_topo = gp_from_numpy(host)
+    result = dev(rng.rand(npts).astype(np.float32))
+    disp = dev(rng.rand(npts, 4).astype(np.float32) * 30)
+    mv = max_verts_for(dims)
+    ncell = (fx - 1) * (fy - 1) * (fz - 1)
+    scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+    iso = g.Isosurface(ctx)
+    use_disp = variant == "_topo_disp"
+    if variant == "_2":
+        act, tot = iso.computeIsosurface_2(mesh.pos, mesh.norm, T["iso"], scr, dims, T["d"], (0, 0, 0), mv, vol_topo, dens, 0.0, result)
+    else:
+        act, tot = iso.computeIsosurface_topo(mesh.pos, mesh.norm, T["iso"], scr, dims, T["d"], (0, 0, 0), mv, vol_topo, dens, 0.0, result, disp=use_disp,
+                                              disp_two=disp)
+    assert tot > 0
+    mine = mine_result(scr, mesh, dims, act, tot)
+    o = orc.extract(orc.MODE_TOPO, dims, T["d"], (0, 0, 0), T["iso"], f0=dens.cpu().numpy(), f1=result.cpu().numpy(), gp=host, disp=disp.cpu().numpy(),
+                    iso1=0.0, flags=orc.F_DISP if use_disp else 0, max_verts=mv)
+    compare_extractions(mine, o, "topo%s vs oracle" % variant, exact_mesh=False)
+    if HAVE_REF:
+        scr2, mesh2 = g.Scratch(ncell), g.MeshBuffers(mv)
+        a2, t2 = ref.isosurface_topo(variant != "_2", mesh2.pos, mesh2.norm, T["iso"], dims, T["d"], (0, 0, 0), scr2, mv, vol_topo, dens, 0.0, result,
+                                     disp=use_disp, disp_two=disp, vol_one=vol_topo, d_solid=dens)
+        compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "topo%s vs reference" % variant, exact_mesh=True)
+
+
+# ------------------------------------------------------------------ fused entry points == composition of legacy calls
+@pytest.mark.parametrize("n", [32, 45, 64])
+def test_band_raw_equals_normalise_four_plus_latticeone(ctx, n):
+    f = torch.zeros(n * n * n, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(f, n, n, n, n * n * n, 0)
+    dims = (n, n, n)
+    lat = g.Gratings(ctx)
+    mask, k = torch.zeros_like(f), torch.zeros_like(f)
+    lat.GPU_buffer_normalise_four(f, mask, k, f.numel(), n, n, n, cases.BAND_LO, cases.BAND_HI)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    a1, t1 = g.Isosurface(ctx).computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (0.5, 0.5, 0.5), (0, 0, 0), mv, k,
+                                                            cases.BAND_LO, cases.BAND_HI)
+    lo, hi = orc.minmax(f.cpu().numpy())
+    mesh2 = g.MeshBuffers(mv)
+    comp = torch.zeros((n - 1) ** 3, dtype=torch.int32, device="cuda")
+    a2, t2 = g.extract_band_raw(ctx, f, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, (0.5, 0.5, 0.5), (0, 0, 0), mesh2.pos, mesh2.norm, mv,
+                                comp=comp)
+    assert (a1, t1) == (a2, t2) and t1 > 0
+    assert_bits_equal(mesh.pos[:t1], mesh2.pos[:t1], "band_raw pos")
+    assert_bits_equal(mesh.norm[:t1], mesh2.norm[:t1], "band_raw norm")
+    assert torch.equal(comp[:a1], scr.compVoxelArray[:a1])
+    a3, t3 = g.extract_band_raw(ctx, f, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, (0.5, 0.5, 0.5), (0, 0, 0), None, None, 0,
+                                count_only=True)
+    assert (a3, t3) == (a1, t1)
+
+
+def test_svl_lattice_pipeline_and_host_entry(ctx):
+    cfg = cases.SVL
+    phi, coef = cases.svl_inputs(cfg)
+    fx, fy, fz = cfg["fdims"]
+    dims = cfg["fdims"]
+    mv = max_verts_for(dims)
+    dphi = dev(phi)
+    svl = torch.zeros(fx * fy * fz, device="cuda")
+    mesh = g.MeshBuffers(mv)
+    a1, t1, mm = g.svl_lattice(ctx, svl, dphi, coef, cfg["cdims"], dims, cfg["d"], cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, cfg["d"], (0, 0, 0),
+                               mesh.pos, mesh.norm, mv)
+    assert t1 > 0
+    # composition: svl_field -> normalise_four -> latticeone
+    field = torch.zeros_like(svl)
+    g.svl_field(ctx, field, dphi, coef, cfg["cdims"], dims, cfg["d"])
+    mask, k = torch.zeros_like(field), torch.zeros_like(field)
+    g.Gratings(ctx).GPU_buffer_normalise_four(field, mask, k, field.numel(), fx, fy, fz, cases.BAND_LO, cases.BAND_HI)
+    scr, mesh2 = g.Scratch((fx - 1) * (fy - 1) * (fz - 1)), g.MeshBuffers(mv)
+    a2, t2 = g.Isosurface(ctx).computeIsosurface_lattice(mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, scr, dims, cfg["d"], (0, 0, 0), mv, k,
+                                                         torch.zeros_like(k), cases.BAND_LO, cases.BAND_HI, 0.0, 0.0)
+    assert (a1, t1) == (a2, t2)
+    assert_bits_equal(mesh.pos[:t1], mesh2.pos[:t1], "svl_lattice pos")
+    assert_bits_equal(mesh.norm[:t1], mesh2.norm[:t1], "svl_lattice norm")
+    # host-input entry point (what bench.py times as e2e)
+    hphi = torch.from_numpy(phi).pin_memory()
+    scratch_phi = torch.zeros_like(dphi)
+    mesh3 = g.MeshBuffers(mv)
+    a3, t3, mm3 = g.svl_lattice_host(ctx, hphi, scratch_phi, svl, coef, cfg["cdims"], dims, cfg["d"], cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, cfg["d"],
+                                     (0, 0, 0), mesh3.pos, mesh3.norm, mv)
+    assert (a3, t3, mm3) == (a1, t1, mm)
+    assert_bits_equal(mesh.pos[:t1], mesh3.pos[:t1], "svl_lattice_host pos")
+
+
+@pytest.mark.parametrize("nslabs", [2, 3, 5])
+def test_z_slab_concatenation_equals_single_pass(ctx, nslabs):
+    """fake multi-rank mode -- slabs extracted one after another on one GPU, concatenated in
+    rank order, must equal the single-GPU mesh byte for byte (global min/max, global boundary faces, global z)."""
+    n = 48
+    f = torch.zeros(n * n * n, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(f, n, n, n, n * n * n, 0)
+    f3 = f.view(n, n, n)
+    lo, hi = orc.minmax(f.cpu().numpy())
+    dims = (n, n, n)
+    mv = max_verts_for(dims)
+    mesh = g.MeshBuffers(mv)
+    comp = torch.zeros((n - 1) ** 3, dtype=torch.int32, device="cuda")
+    a, t = g.extract_band_raw(ctx, f, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, (0.5, 0.5, 0.5), (0, 0, 0), mesh.pos, mesh.norm, mv, comp=comp)
+    bounds = [round(i * (n - 1) / nslabs) for i in range(nslabs + 1)]  # cell layers
+    pos_parts, norm_parts, comp_parts, tot_a, tot_t = [], [], [], 0, 0
+    for r in range(nslabs):
+        z0, z1 = bounds[r], bounds[r + 1]
+        slab = f3[z0:z1 + 1].contiguous()                      # point layers z0..z1 (one halo plane on +z)
+        ldims = (n, n, z1 - z0 + 1)
+        ac, tc = g.extract_band_raw(ctx, slab, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, ldims, (0.5, 0.5, 0.5), (0, 0, 0), None, None, 0,
+                                    slab=(z0, n), count_only=True)
+        m = g.MeshBuffers(max(tc, 3))
+        cp = torch.zeros(max(ac, 1), dtype=torch.int32, device="cuda")
+        a_r, t_r = g.extract_band_raw(ctx, slab, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, ldims, (0.5, 0.5, 0.5), (0, 0, 0), m.pos, m.norm,
+                                      1 << 33, slab=(z0, n), comp=cp)
+        assert (a_r, t_r) == (ac, tc)
+        pos_parts.append(m.pos[:t_r]); norm_parts.append(m.norm[:t_r]); comp_parts.append(cp[:a_r])
+        tot_a += a_r; tot_t += t_r
+    assert (tot_a, tot_t) == (a, t)
+    assert_bits_equal(torch.cat(pos_parts), mesh.pos[:t], "slab concat pos")
+    assert_bits_equal(torch.cat(norm_parts), mesh.norm[:t], "slab concat norm")
+    assert torch.equal(torch.cat(comp_parts), comp[:a])
+
+
+def test_svl_field_slabs_equal_single_pass(ctx):
+    cfg = cases.SVL
+    phi, coef = cases.svl_inputs(cfg)
+    fx, fy, fz = cfg["fdims"]
+    dphi = dev(phi)
+    whole = torch.zeros(fx * fy * fz, device="cuda")
+    g.svl_field(ctx, whole, dphi, coef, cfg["cdims"], cfg["fdims"], cfg["d"])
+    whole = whole.view(fz, fy, fx)
+    for (z0, z1) in ((0, 8), (8, 17), (17, 23)):                 # cell layers; second slab starts on an even, third on an odd global layer
+        nzl = z1 - z0 + 1
+        c0 = z0 // 2
+        c1 = min((z1 // 2) + 1, cfg["cdims"][2] - 1)
+        sub = dphi[:, c0:c1 + 1].contiguous()
+        out = torch.zeros(fx * fy * nzl, device="cuda")
+        g.svl_field(ctx, out, sub, coef, (cfg["cdims"][0], cfg["cdims"][1], c1 - c0 + 1), (fx, fy, nzl), cfg["d"], slab=(z0, fz), cz0=c0)
+        assert_bits_equal(out, whole[z0:z1 + 1].contiguous(), "svl slab z0=%d" % z0)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_and_full_fields(ctx):
+    n = 24
+    dims = (n, n, n)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    zeros = torch.zeros(n ** 3, device="cuda")
+    ones = torch.ones(n ** 3, device="cuda")
+    for mask in (zeros, ones):  # all inside / all outside -> no triangles, early-out totalVerts = 0
+        act, tot = g.Isosurface(ctx).computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), mv, zeros,
+                                                                  cases.BAND_LO, cases.BAND_HI)
+        assert (act, tot) == (0, 0)
+
+
+@pytest.mark.parametrize("dims", [(5, 4, 3), (2, 2, 2), (130, 7, 9), (37, 65, 11), (8, 300, 4)])
+def test_ragged_and_tiny_grids(ctx, dims):
+    nx, ny, nz = dims
+    rng = np.random.RandomState(11)
+    k = rng.rand(nz, ny, nx).astype(np.float32)
+    mask, kk = orc.normalise_four(k, cases.BAND_LO, 0.6, ab=(0.0, 1.0))
+    mv = max_verts_for(dims)
+    ncell = (nx - 1) * (ny - 1) * (nz - 1)
+    o = orc.extract(orc.MODE_LATTICE_ONE, dims, (1, 1, 1), (0, 0, 0), cases.ISO_MASK, f0=mask, f1=kk, iso1=cases.BAND_LO, iso2=0.6, max_verts=mv)
+    for opts in (_capi.GCB_OPT_FILL_STAGE_ARRAYS, _capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_NO_TMA):
+        ctx.set_options(opts)
+        scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+        act, tot = g.Isosurface(ctx).computeIsosurface_latticeone(dev(mask), mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), mv, dev(kk),
+                                                                  cases.BAND_LO, 0.6)
+        compare_extractions(mine_result(scr, mesh, dims, act, tot), o, "ragged %s opts=%d" % (dims, opts), exact_mesh=False)
+    ctx.set_options(_capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET)
+
+
+def test_max_verts_truncation(ctx):
+    """Writes at index >= maxVerts-3 are dropped (MarchingCubes_kernel.cu:2181); totals still report the full count."""
+    n = 32
+    _, mask, k = _lattice_inputs(ctx, n, 0)
+    dims = (n, n, n)
+    full = g.MeshBuffers(max_verts_for(dims))
+    scr = g.Scratch((n - 1) ** 3)
+    iso = g.Isosurface(ctx)
+    a, t = iso.computeIsosurface_latticeone(mask, full.pos, full.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), full.max_verts, k, cases.BAND_LO,
+                                            cases.BAND_HI)
+    cap = (t // 2) // 3 * 3 + 1
+    small = g.MeshBuffers(cap + 16)
+    small.pos.fill_(-7.0)
+    a2, t2 = iso.computeIsosurface_latticeone(mask, small.pos, small.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), cap, k, cases.BAND_LO,
+                                              cases.BAND_HI)
+    assert (a2, t2) == (a, t)
+    last = ((cap - 3 - 1) // 3) * 3 + 3  # first vertex index NOT written: smallest multiple of 3 >= cap-3
+    assert_bits_equal(small.pos[:last], full.pos[:last], "truncated prefix")
+    assert bool((small.pos[last:] == -7.0).all())
+
+
+@needs_ref
+def test_large_grid_counts_and_mesh_match_reference(ctx):
+    """256^3 gyroid band (config-1 field at config-2 size): full bit parity against the reference kernels."""
+    n = 256
+    _, mask, k = _lattice_inputs(ctx, n, 0)
+    dims = (n, n, n)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    ctx.set_options(_capi.GCB_OPT_LEGACY_MEMSET)
+    a, t = g.Isosurface(ctx).computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (0.5, 0.5, 0.5), (0, 0, 0), mv, k,
+                                                          cases.BAND_LO, cases.BAND_HI)
+    ctx.set_options(_capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET)
+    scr2, mesh2 = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    a2, t2 = ref.isosurface_lattice(True, False, mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, (0.5, 0.5, 0.5), (0, 0, 0), scr2, mv, k, None,
+                                    cases.BAND_LO, cases.BAND_HI)
+    assert (a, t) == (a2, t2) and t > 1000000
+    assert torch.equal(scr.compVoxelArray[:a], scr2.compVoxelArray[:a])
+    assert_bits_equal(mesh.pos[:t], mesh2.pos[:t], "256^3 pos")
+    assert_bits_equal(mesh.norm[:t], mesh2.norm[:t], "256^3 norm")
