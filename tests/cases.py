@@ -17,8 +17,9 @@ CSG = dict(dims=(48, 48, 48), d=(0.5, 0.5, 0.5),
 
 PRIMS = dict(dims=(40, 36, 44), d=(0.5, 0.5, 0.5), center=(0.7, -0.4, 0.3), angles=(0.3, 0.2, 0.1))
 
-# configs 3/4 in miniature: control 12^3 -> fine 24^3 (ratio 2, the app's own), and control 8^3 -> fine 32^3 (ratio 4)
-SVL = dict(cdims=(12, 12, 12), fdims=(24, 24, 24), d=(0.5, 0.5, 0.5), nh=10)
+# configs 3/4 in miniature: control 16x16x8 -> fine 32x32x16 (ratio 2, the app's own), and control 8^3 -> fine 32^3 (ratio 4)
+# (point counts are multiples of 1024: the reference's min/max reduction reads uninitialised shared memory otherwise)
+SVL = dict(cdims=(16, 16, 8), fdims=(32, 32, 16), d=(0.5, 0.5, 0.5), nh=10)
 SVL4 = dict(cdims=(8, 8, 8), fdims=(32, 32, 32), d=(0.25, 0.25, 0.25), nh=6)
 
 # config 5 in miniature: coarse 24x12x12 -> fine 48x24x24, iso = VolumeFraction 0.4

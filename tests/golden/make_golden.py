@@ -61,13 +61,14 @@ def main(out):
     npts = dims[0] * dims[1] * dims[2]
     vol_one = gp_zeros(npts)
     boundary = torch.zeros(npts, device="cuda")
+    lattice = torch.zeros(npts, device="cuda")  # d_volumethree, read unconditionally by classify_copy_Voxel
     s, c, y = C["sphere"], C["cuboid"], C["cylinder"]
     ref.sphere(boundary, s["center"], s["radius"], s["thickness"], dims, d, False)
     sphere_f = boundary.cpu().numpy().copy()
-    ref.copy_parameter(vol_one, boundary, None, dims, d, 0.0, obj_union=True)
+    ref.copy_parameter(vol_one, boundary, lattice, dims, d, 0.0, obj_union=True)
     ref.cuboid(boundary, c["center"], c["angles"], c["xw"], c["yw"], c["zw"], dims, d)
     cuboid_f = boundary.cpu().numpy().copy()
-    ref.copy_parameter(vol_one, boundary, None, dims, d, 0.0, obj_union=True)
+    ref.copy_parameter(vol_one, boundary, lattice, dims, d, 0.0, obj_union=True)
     ref.distance_from_line(boundary, y["center"], y["axis"], y["radius"], y["tr"], y["ta"], dims, d, False)
     mv = max_verts_for(dims)
     ncell = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)

@@ -107,8 +107,17 @@ def svl_field(svl, ga, phi, nh, coef_dev, cdims, fdims, d):
                             F(d[2])))
 
 
+def _zeros_like_grid(dims, like):
+    return torch.zeros(dims[0] * dims[1] * dims[2], device=like.device, dtype=torch.float32)
+
+
 def copy_parameter(vol_one, vol_two, vol_lattice, dims, voxel, iso, fixed=False, dynamic=False, iso1=0.2, iso2=0.3, obj_union=True, obj_diff=False,
                    obj_intersect=False):
+    # classify_copy_Voxel reads BOTH float fields unconditionally (MarchingCubes_kernel.cu:177-178): the app always passes valid buffers
+    if vol_lattice is None:
+        vol_lattice = _zeros_like_grid(dims, vol_one)
+    if vol_two is None:
+        vol_two = _zeros_like_grid(dims, vol_one)
     _ok(lib().ref_copy_parameter(None, F(iso), C.c_uint(dims[0]), C.c_uint(dims[1]), C.c_uint(dims[2]), F(voxel[0]), F(voxel[1]), F(voxel[2]),
                                  _p(vol_one), _p(vol_two), _p(vol_lattice), int(fixed), int(dynamic), F(iso1), F(iso2), int(obj_union), int(obj_diff),
                                  int(obj_intersect)))
@@ -140,6 +149,11 @@ def isosurface_lattice(one, fix_grid, vol, pos, norm, iso, dims, voxel, center, 
 
 def isosurface_csg(fix_grid, pos, norm, iso, dims, voxel, center, s, max_verts, fixed_f, dynamic_f, lattice_f, iso1=0.2, iso2=0.3, obj_union=True,
                    obj_diff=False, obj_intersect=False, fixed=False, dynamic=False, make_region=False, topo_f=None):
+    # classifyVoxel gathers all three fields unconditionally (MarchingCubes_kernel.cu:889-914)
+    if lattice_f is None:
+        lattice_f = _zeros_like_grid(dims, fixed_f)
+    if dynamic_f is None:
+        dynamic_f = _zeros_like_grid(dims, fixed_f)
     act, tot = C.c_uint(0), C.c_uint(0)
     _ok(lib().ref_isosurface_csg(int(fix_grid), _p(pos), _p(norm), F(iso), C.c_uint(dims[0]), C.c_uint(dims[1]), C.c_uint(dims[2]), F(voxel[0]), F(voxel[1]),
                                  F(voxel[2]), F(center[0]), F(center[1]), F(center[2]), *_scr(s), C.c_uint(max_verts), _p(fixed_f), _p(dynamic_f),

@@ -70,7 +70,23 @@ __global__ void probe(cudaTextureObject_t tex, const float* g, int cx, int cy, i
     }
 }
 
-int main() {
+// dump raw samples {8 taps, ax, ay, az, hw} for offline analysis of the filter arithmetic
+__global__ void dump(cudaTextureObject_t tex, const float* g, int cx, int cy, int cz, int nx, int ny, int nz, float d, float* out, int nsamp) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsamp) return;
+    unsigned long long h = (unsigned long long)(s + 1) * 0x9E3779B97F4A7C15ull;
+    int tx = (h >> 8) % nx, ty = (h >> 24) % ny, tz = (h >> 40) % nz;
+    float x = tx * d, y = ty * d, z = tz * d;
+    float X = (float)(x + 0.5), Y = (float)(y + 0.5), Z = (float)(z + 0.5);
+    Axis ax = tex_axis(X, cx), ay = tex_axis(Y, cy), az = tex_axis(Z, cz);
+    int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1}, xi[2] = {ax.i0, ax.i1};
+    float* o = out + (size_t)s * 12;
+    int q = 0;
+    for (int k = 0; k < 2; ++k) for (int j = 0; j < 2; ++j) for (int i = 0; i < 2; ++i) o[q++] = g[((size_t)zi[k] * cy + yi[j]) * cx + xi[i]];
+    o[8] = ax.a; o[9] = ay.a; o[10] = az.a; o[11] = tex3D<float>(tex, X, Y, Z);
+}
+
+int main(int argc, char** argv) {
     const int cx = 40, cy = 36, cz = 32;
     std::vector<float> h((size_t)cx * cy * cz);
     srand(1);
@@ -96,6 +112,17 @@ int main() {
         cudaMemcpy(hb, bad, NC * 8, cudaMemcpyDeviceToHost); cudaMemcpy(hm, mu, NC * 4, cudaMemcpyDeviceToHost);
         printf("ratio %d (%d x %d x %d points): %s\n", ratio, nx, ny, nz, cudaGetErrorString(cudaGetLastError()));
         for (int q = 0; q < NC; ++q) printf("   cand %d %-28s mismatches %12llu  max ulp %d\n", q, names[q], hb[q], hm[q]);
+    }
+    if (argc > 1) {
+        const int nsamp = 200000;
+        float* dout; cudaMalloc(&dout, (size_t)nsamp * 12 * 4);
+        std::vector<float> ho((size_t)nsamp * 12);
+        for (int ratio : {2, 4, 8}) {
+            dump<<<(nsamp + 255) / 256, 256>>>(tex, dg, cx, cy, cz, cx * ratio, cy * ratio, cz * ratio, 1.0f / ratio, dout, nsamp);
+            cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost);
+            char name[512]; snprintf(name, sizeof name, "%s/tex_samples_r%d.bin", argv[1], ratio);
+            FILE* f = fopen(name, "wb"); fwrite(ho.data(), 4, ho.size(), f); fclose(f);
+        }
     }
     return 0;
 }
