@@ -106,6 +106,7 @@ def main():
     ap.add_argument("--ratio", type=int, default=4, help="fine/control upsampling ratio (2 = the app's own, 4 default, 8)")
     ap.add_argument("--harmonics", type=int, default=62)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="timed steps only (no e2e leg, no CPU baseline): for runs under ncu")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -199,6 +200,11 @@ def main():
     ms = ev0.elapsed_time(ev1) / args.steps
     ctx.enable_kernel_timing(False)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms, "extract_kernel_ms": sum(ext_ms) / len(ext_ms),
+                              "field_kernel_ms": sum(fld_ms) / len(fld_ms), "verts": tot, "launches": launches}))
+        return
     # ---- e2e: host control grids -> C-ABI host entry point (single GPU) / per-rank H2D + same step (multi GPU)
     hphi = torch.empty(phi.shape, dtype=torch.float32, pin_memory=True)
     hphi.copy_(phi)

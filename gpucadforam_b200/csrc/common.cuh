@@ -55,7 +55,8 @@ struct McArgs {
     uint32_t prow_stride;          // floats between the two staged slices in smem ( (R+1)*nx rounded )
     int use_tma;
     int count_only;
-    uint32_t magic_cx_mul, magic_cx_shift;  // unused (kept for layout stability)
+    uint32_t magic_cx_mul, magic_cx_shift;  // c / cx == (c * mul) >> shift for c < 2^28
+    float snap_thr;                         // smallest float >= 0.0005 (endpoint snapping threshold)
 };
 
 struct Ctx {

@@ -23,6 +23,8 @@
 // 36-56 B/cell through them).
 #include "common.cuh"
 
+#include <cmath>
+
 namespace gcb {
 
 // ---------------------------------------------------------------- tables
@@ -132,39 +134,48 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {  // helper_math.h
 }
 
 // vertexInterp2_new (MarchingCubes_kernel.cu:3593-3674); t = 0 where the reference leaves it unset
-__device__ __forceinline__ float3 interp_band(float l1, float l2, float3 p0, float3 p1, float f0, float f1, uint32_t id0, uint32_t id1) {
-    float t = 0.f;
-    if ((id0 == 1u && id1 == 0u) || (id0 == 0u && id1 == 1u)) {
-        if (f1 < f0) { float3 tp = p1; p1 = p0; p0 = tp; float tf = f1; f1 = f0; f0 = tf; }
-        if ((f1 >= l1) && (f0 <= l1)) {
-            if (fabs(l1 - f0) < 0.0005) return p0;
-            if (fabs(l1 - f1) < 0.0005) return p1;
-            if (fabs(f1 - f0) < 0.0005) return p0;
-            t = __fdiv_rn(__fsub_rn(l1, f0), __fsub_rn(f1, f0));
-        } else if ((f1 >= l2) && (f0 <= l2)) {
-            if (fabs(l2 - f0) < 0.0005) return p0;
-            if (fabs(l2 - f1) < 0.0005) return p1;
-            if (fabs(f1 - f0) < 0.0005) return p0;
-            t = __fdiv_rn(__fsub_rn(l2, f0), __fsub_rn(f1, f0));
-        } else if ((f1 == f0) && (p0.z == 0.0)) t = 1;
-        else if (f1 == f0) t = 0;
+// `fabs(d) < 0.0005` in the reference compares a float against a double literal; kSnap is the smallest float whose value is
+// >= 0.0005, so `fabsf(d) < kSnap` decides identically for every float d without leaving the FP32 pipe.
+__device__ __forceinline__ bool snap(float d, float thr) { return fabsf(d) < thr; }
+__device__ __forceinline__ float3 interp_band(float thr, float l1, float l2, float3 p0, float3 p1, float f0, float f1, uint32_t id0, uint32_t id1) {
+    // Branch-free restatement (lanes of a warp hold unrelated edges, so every if/else of the reference would serialise):
+    // all candidates are computed, the reference's decision tree only selects.
+    const bool crossing = (id0 == 1u && id1 == 0u) || (id0 == 0u && id1 == 1u);
+    const bool sw = f1 < f0;
+    const float lo = sw ? f1 : f0, hi = sw ? f0 : f1;
+    const float3 plo = sw ? p1 : p0, phi = sw ? p0 : p1;
+    const bool c1 = (hi >= l1) && (lo <= l1);
+    const bool c2 = !c1 && (hi >= l2) && (lo <= l2);
+    const float lv = c1 ? l1 : l2;
+    const float dn = __fsub_rn(lv, lo), dd = __fsub_rn(hi, lo);
+    const bool s_lo = snap(dn, thr) || (!snap(__fsub_rn(lv, hi), thr) && snap(dd, thr));  // -> p0 (1st or 3rd test)
+    const bool s_hi = !snap(dn, thr) && snap(__fsub_rn(lv, hi), thr);                        // -> p1 (2nd test)
+    float t = __fdiv_rn(dn, dd);
+    if (!(c1 || c2)) t = (hi == lo && plo.z == 0.0f) ? 1.f : 0.f;  // reference: t = 1 / t = 0 / (unset -> 0 here)
+    if (!crossing) t = 0.f;
+    // without a crossing the reference lerps the UNSWAPPED endpoints with t = 0, i.e. returns p0 + 0*(p1-p0)
+    const float3 a = crossing ? plo : p0, bb = crossing ? phi : p1;
+    float3 r = lerp3(a, bb, t);
+    if (crossing && (c1 || c2)) {
+        if (s_lo) r = plo;
+        else if (s_hi) r = phi;
     }
-    return lerp3(p0, p1, t);
+    return r;
 }
 // second half of vertexInterp3_new (:3347-3413): band on the vol_two pair when ids are {2,0}
-__device__ __forceinline__ bool interp_band_two(float m1, float m2, float3& p0, float3& p1, float f2, float f3, float& t, float3& out) {
+__device__ __forceinline__ bool interp_band_two(float thr, float m1, float m2, float3& p0, float3& p1, float f2, float f3, float& t, float3& out) {
     if (f3 < f2) { float3 tp = p1; p1 = p0; p0 = tp; float tf = f3; f3 = f2; f2 = tf; }
     if ((f3 >= m1) && (f2 <= m1)) {
-        if (fabs(m1 - f2) < 0.0005) { out = p0; return true; }
-        if (fabs(m1 - f3) < 0.0005) { out = p1; return true; }
-        if (fabs(f3 - f2) < 0.0005) { out = p0; return true; }
+        if (snap(__fsub_rn(m1, f2), thr)) { out = p0; return true; }
+        if (snap(__fsub_rn(m1, f3), thr)) { out = p1; return true; }
+        if (snap(__fsub_rn(f3, f2), thr)) { out = p0; return true; }
         t = __fdiv_rn(__fsub_rn(m1, f2), __fsub_rn(f3, f2));
     } else if ((f3 >= m2) && (f2 <= m2)) {
-        if (fabs(m2 - f2) < 0.0005) { out = p0; return true; }
-        if (fabs(m2 - f3) < 0.0005) { out = p1; return true; }
-        if (fabs(f3 - f2) < 0.0005) { out = p0; return true; }
+        if (snap(__fsub_rn(m2, f2), thr)) { out = p0; return true; }
+        if (snap(__fsub_rn(m2, f3), thr)) { out = p1; return true; }
+        if (snap(__fsub_rn(f3, f2), thr)) { out = p0; return true; }
         t = __fdiv_rn(__fsub_rn(m2, f2), __fsub_rn(f3, f2));
-    } else if ((f3 == f2) && (p0.z == 0.0)) t = 1;
+    } else if ((f3 == f2) && (p0.z == 0.0f)) t = 1;
     else if (f3 == f2) t = 0;
     return false;
 }
@@ -250,7 +261,7 @@ __device__ __forceinline__ void stage_point(const McArgs& A, size_t gi, uint32_t
 template <int MODE>
 __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, uint32_t z, uint32_t y0, uint32_t c, uint32_t j,
                                               unsigned long long vidx) {
-    const uint32_t r = c / A.cx, x = c - r * A.cx;
+    const uint32_t r = (uint32_t)(((unsigned long long)c * A.magic_cx_mul) >> A.magic_cx_shift), x = c - r * A.cx;  // c / cx, exact for c < 2^28
     const uint32_t cube = S.cube[c];
     const unsigned long long tri = S.tri[cube];
     const uint32_t y = y0 + r;
@@ -275,7 +286,7 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
         const float fa = (za ? S.val[1] : S.val[0])[sa], fb = (zb ? S.val[1] : S.val[0])[sb];
         w[k] = 0.f;
         if (MODE == M_LATTICE_ONE || MODE == M_BAND_RAW) {
-            v[k] = interp_band(A.iso1, A.iso2, pa, pb, fa, fb, ((za ? S.bit[1] : S.bit[0])[sa] & 3u), ((zb ? S.bit[1] : S.bit[0])[sb] & 3u));
+            v[k] = interp_band(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb, ((za ? S.bit[1] : S.bit[0])[sa] & 3u), ((zb ? S.bit[1] : S.bit[0])[sb] & 3u));
         } else if (MODE == M_LATTICE) {
             const uint32_t ida = ((za ? S.bit[1] : S.bit[0])[sa] & 3u), idb = ((zb ? S.bit[1] : S.bit[0])[sb] & 3u);
             if ((ida == 2u && idb == 0u) || (idb == 2u && ida == 0u)) {
@@ -285,9 +296,9 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
                 float t = 0.f;
                 float3 out;
                 float3 q0 = pa, q1 = pb;
-                if (interp_band_two(A.iso1b, A.iso2b, q0, q1, __ldg(A.f2 + ga), __ldg(A.f2 + gb), t, out)) v[k] = out;
+                if (interp_band_two(A.snap_thr, A.iso1b, A.iso2b, q0, q1, __ldg(A.f2 + ga), __ldg(A.f2 + gb), t, out)) v[k] = out;
                 else v[k] = lerp3(q0, q1, t);
-            } else v[k] = interp_band(A.iso1, A.iso2, pa, pb, fa, fb, ida, idb);
+            } else v[k] = interp_band(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb, ida, idb);
         } else {
             const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
             const size_t gb = ((size_t)(z + zb) * A.ny + y + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
@@ -395,16 +406,18 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
             float* sv = s ? S.val[1] : S.val[0];
             unsigned char* sb = s ? S.bit[1] : S.bit[0];
             const size_t gs = g0 + (size_t)s * slice_pts;
-            for (uint32_t pnt = tid; pnt < npts; pnt += kThreads) {
-                const uint32_t rr = pnt / A.nx, x = pnt - rr * A.nx;
-                float raw;
-                if (A.use_tma && A.f0) raw = sv[pnt];
-                else raw = A.f0 ? __ldg(A.f0 + gs + pnt) : 0.f;
-                float val;
-                uint32_t bits;
-                stage_point<MODE>(A, gs + pnt, x, y0 + rr, z + s, raw, val, bits);
-                sv[pnt] = val;
-                sb[pnt] = (unsigned char)bits;
+            for (uint32_t rr = warp; rr <= rows; rr += kWarps) {
+                for (uint32_t x = lane; x < A.nx; x += 32) {
+                    const uint32_t pnt = rr * A.nx + x;
+                    float raw;
+                    if (A.use_tma && A.f0) raw = sv[pnt];
+                    else raw = A.f0 ? __ldg(A.f0 + gs + pnt) : 0.f;
+                    float val;
+                    uint32_t bits;
+                    stage_point<MODE>(A, gs + pnt, x, y0 + rr, z + s, raw, val, bits);
+                    sv[pnt] = val;
+                    sb[pnt] = (unsigned char)bits;
+                }
             }
         }
         __syncthreads();
@@ -570,6 +583,15 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     if (nt >= 0xffffffffull) return fail_msg(c, "too many tiles");
     a.num_tiles = (uint32_t)nt;
     a.prow_stride = (uint32_t)((((size_t)(R + 1) * a.nx) + 15) & ~(size_t)15);
+    {   // c / cx for c < 2^28 as (c * mul) >> shift  (round-up method: mul = ceil(2^shift / cx), shift = 28 + ceil(log2 cx))
+        uint32_t l = 0;
+        while ((1u << l) < a.cx) ++l;
+        a.magic_cx_shift = 28 + l;
+        a.magic_cx_mul = (uint32_t)(((1ull << a.magic_cx_shift) + a.cx - 1) / a.cx);
+        float thr = (float)0.0005;
+        if ((double)thr < 0.0005) thr = nextafterf(thr, 1.0f);
+        a.snap_thr = thr;
+    }
     // TMA bulk copies need 16-byte aligned global addresses and sizes
     a.use_tma = !(c->options & GCB_OPT_NO_TMA) && a.f0 && (a.nx % 4 == 0) && (((uintptr_t)a.f0 & 15) == 0);
 

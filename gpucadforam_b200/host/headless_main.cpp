@@ -1,0 +1,173 @@
+// headless_main.cpp -- runs the hot path without GLFW / ImGui / Vulkan.
+//
+// The reference has no headless mode: class Multitopo (src/main.cu) owns every buffer and drives the path from
+// its frame loop.  This harness replays the same call sequences through the C++ host mirror (gpucad_host.hpp):
+//   config 1  check_unit_lattice / display_unit_lattice   main.cu:4080-4137   gyroid unit cell, band extraction
+//   config 2  show_model + retain                         main.cu:3304-3465   sphere U box - cylinder, .obj export :4695-4778
+//   config 5  toprun_struct (extraction part)             main.cu:3060-3109   refine + computeIsosurface_2
+// and the fused entry point for config 3 (spatial_lattice_run, main.cu:3904-4037).  Buffers are plain cudaMalloc
+// allocations with the layouts of vulkan_create_lattice_buffers / initMC_two (main.cu:2125-2161, :2714-2814).
+//
+//   gpucad_headless <config 1|2|3|5> [N] [out.obj]
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "gpucad_host.hpp"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+struct Mc {  // initMC_two
+    uint3 gridSize, gridSizeShift, gridSizeMask;
+    uint numVoxels, maxVerts;
+    float3 voxelSize, gridcenter;
+    uint *d_voxelVerts, *d_voxelVertsScan, *d_voxelOccupied, *d_voxelOccupiedScan, *d_compVoxelArray;
+    float4 *d_pos, *d_normal;
+    Mc(uint nx, uint ny, uint nz, float dx) {
+        gridSize = make_uint3(nx, ny, nz);
+        gridSizeMask = make_uint3(nx - 1, ny - 1, nz - 1);
+        gridSizeShift = make_uint3(1, nx - 1, (nx - 1) * (ny - 1));
+        numVoxels = gridSizeMask.x * gridSizeMask.y * gridSizeMask.z;
+        voxelSize = make_float3(dx, dx, dx);
+        gridcenter = make_float3(0, 0, 0);
+        maxVerts = (uint)std::max<size_t>((size_t)nx * ny * nz * 4, 300000);  // main.cu:2850
+        size_t m = sizeof(uint) * (size_t)numVoxels;
+        CK(cudaMalloc(&d_voxelVerts, m)); CK(cudaMalloc(&d_voxelVertsScan, m)); CK(cudaMalloc(&d_voxelOccupied, m));
+        CK(cudaMalloc(&d_voxelOccupiedScan, m)); CK(cudaMalloc(&d_compVoxelArray, m));
+        CK(cudaMalloc(&d_pos, sizeof(float4) * (size_t)maxVerts)); CK(cudaMalloc(&d_normal, sizeof(float4) * (size_t)maxVerts));
+    }
+};
+
+static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b); return ms; }
+
+int main(int argc, char** argv) {
+    const int config = argc > 1 ? atoi(argv[1]) : 1;
+    const int N = argc > 2 ? atoi(argv[2]) : (config == 1 ? 128 : 256);
+    const char* obj = argc > 3 ? argv[3] : nullptr;
+    Isosurface isosurf;
+    Gratings lattice;
+    Fft_lattice fftlattice;
+    File_output output_file;
+    uint *d_tri, *d_nv;
+    isosurf.allocateTextures_s(&d_tri, &d_nv);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    uint active = 0, total = 0;
+    float ms = 0;
+    float4* d_pos = nullptr;
+
+    if (config == 1) {  // gyroid unit cell, band [0.20, 0.30], mask iso 0.25
+        Mc mc(N, N, N, 1.0f);
+        size_t n = (size_t)N * N * N;
+        float *d_vol, *d_mask;
+        CK(cudaMalloc(&d_vol, n * 4)); CK(cudaMalloc(&d_mask, n * 4));
+        float iso = 0.25f;
+        cudaEventRecord(e0);
+        fftlattice.create_lattice(d_vol, N, N, N, (uint)n, 0);                                         // unit_latticeone :3717
+        lattice.GPU_buffer_normalise_buffer(d_vol, d_vol, (int)n);                                     // :3719
+        lattice.GPU_buffer_normalise_four(d_vol, d_mask, d_vol, n, N, N, N, 0.20f, 0.30f);            // display_unit_lattice :4113
+        isosurf.computeIsosurface_latticeone(d_mask, mc.d_pos, mc.d_normal, iso, mc.numVoxels, mc.d_voxelVerts, mc.d_voxelVertsScan, mc.d_voxelOccupied,
+                                             mc.d_voxelOccupiedScan, mc.gridSize, mc.gridSizeShift, mc.gridSizeMask, mc.voxelSize, mc.gridcenter, &active,
+                                             &total, mc.d_compVoxelArray, mc.maxVerts, d_vol, 0.20f, 0.30f);     // :4115-4119
+        cudaEventRecord(e1);
+        ms = elapsed(e0, e1);
+        d_pos = mc.d_pos;
+    } else if (config == 2) {  // sphere U box - cylinder on the 2x refined grid (dx2 = 0.5)
+        Mc mc(N, N, N, 0.5f);
+        size_t n = (size_t)N * N * N;
+        const float s = N / 256.0f;
+        Modelling model(N, N, N);
+        float *d_boundary, *d_lat;
+        grid_points* vol_one;
+        CK(cudaMalloc(&d_boundary, n * 4)); CK(cudaMalloc(&d_lat, n * 4)); CK(cudaMalloc(&vol_one, n * sizeof(grid_points)));
+        CK(cudaMemset(d_boundary, 0, n * 4)); CK(cudaMemset(d_lat, 0, n * 4)); CK(cudaMemset(vol_one, 0, n * sizeof(grid_points)));  // init_Boundary :3282
+        size_t nfacets = 0;
+        cudaEventRecord(e0);
+        model.sphere_with_center(d_boundary, make_float3(0, 0, 0), 40 * s, 2, N, N, N, 0.5f, 0.5f, 0.5f, false);
+        isosurf.copy_parameter(mc.d_voxelVerts, 0.0f, mc.gridSize, mc.gridSizeShift, mc.gridSizeMask, mc.voxelSize, mc.numVoxels, vol_one, d_boundary, d_lat,
+                               false, false, 0.20f, 0.30f, true, false, false);                                    // retain :3309
+        model.cuboid(d_boundary, make_float3(0, 0, 0), make_float3(0.3f, 0.2f, 0.1f), 90 * s, 50 * s, 60 * s, N, N, N, 0.5f, 0.5f, 0.5f);
+        isosurf.copy_parameter(mc.d_voxelVerts, 0.0f, mc.gridSize, mc.gridSizeShift, mc.gridSizeMask, mc.voxelSize, mc.numVoxels, vol_one, d_boundary, d_lat,
+                               false, false, 0.20f, 0.30f, true, false, false);
+        model.distance_from_line(d_boundary, make_float3(0, 0, 0), make_float3(0, 0, 1), 18 * s, 2, 200 * s, N, N, N, 0.5f, 0.5f, 0.5f, false);
+        isosurf.computeIsosurface(nullptr, mc.gridSize, mc.d_pos, mc.d_normal, 0.0f, mc.numVoxels, mc.d_voxelVerts, mc.d_voxelVertsScan, mc.d_voxelOccupied,
+                                  mc.d_voxelOccupiedScan, mc.gridSize, mc.gridSizeShift, mc.gridSizeMask, mc.voxelSize, mc.gridcenter, &active, &total,
+                                  mc.d_compVoxelArray, mc.maxVerts, vol_one, d_boundary, nullptr, d_lat, 0.20f, 0.30f, false, true, false, true, false, false,
+                                  false, false, false, &nfacets);                                                  // show_model :3410-3413, obj_diff
+        cudaEventRecord(e1);
+        ms = elapsed(e0, e1);
+        d_pos = mc.d_pos;
+    } else if (config == 3) {  // fused SVL lattice: control grid N/4, 62 harmonics, synthetic linear phases
+        const int C = N / 4, NH = 62;
+        std::vector<float> phi((size_t)NH * C * C * C), coef(2 * NH);
+        int h = 0;
+        for (int k = -2; k <= 2 && h < NH; ++k) for (int j = -2; j <= 2 && h < NH; ++j) for (int i = -2; i <= 2 && h < NH; ++i, ++h) {
+            coef[2 * h] = 0.05f * (1 + (h % 5)); coef[2 * h + 1] = 0.03f * ((h % 3) - 1);
+            for (int z = 0; z < C; ++z) for (int y = 0; y < C; ++y) for (int x = 0; x < C; ++x)
+                phi[(((size_t)h * C + z) * C + y) * C + x] = 6.2831853f / 10.0f * (i * (x - C / 2.0f) + j * (y - C / 2.0f) + k * (z - C / 2.0f));
+        }
+        float *d_phi, *d_svl, *h_phi;
+        size_t n = (size_t)N * N * N;
+        CK(cudaMalloc(&d_phi, phi.size() * 4)); CK(cudaMalloc(&d_svl, n * 4)); CK(cudaMallocHost(&h_phi, phi.size() * 4));
+        memcpy(h_phi, phi.data(), phi.size() * 4);
+        unsigned long long a64 = 0, t64 = 0;
+        float mm[2];
+        gcb_float3 vs{0.25f, 0.25f, 0.25f}, gc{0, 0, 0};
+        // count first (mesh stays unallocated), then allocate exactly: SURVEY.md 7 "Capacity"
+        gpucad::check(gcb_svl_field(gpucad::ctx(), d_svl, d_phi, 0, coef.data(), C, C, C, 0, N, N, N, gcb_slab{0, (unsigned)N}, 0.25f, 0.25f, 0.25f, 0, nullptr), "warm");
+        CK(cudaMemcpy(d_phi, h_phi, phi.size() * 4, cudaMemcpyHostToDevice));
+        float4 *pos = nullptr, *norm = nullptr;
+        gpucad::check(gcb_svl_lattice(gpucad::ctx(), d_svl, d_phi, NH, coef.data(), C, C, C, N, N, N, 0.25f, 0.25f, 0.25f, 0.25f, 0.20f, 0.30f, vs, gc, nullptr,
+                                      nullptr, 3, &a64, &t64, mm), "svl_lattice(count)");
+        CK(cudaMalloc(&pos, (t64 + 3) * 16)); CK(cudaMalloc(&norm, (t64 + 3) * 16));
+        cudaEventRecord(e0);
+        gpucad::check(gcb_svl_lattice_host(gpucad::ctx(), h_phi, d_phi, d_svl, NH, coef.data(), C, C, C, N, N, N, 0.25f, 0.25f, 0.25f, 0.25f, 0.20f, 0.30f, vs, gc,
+                                           pos, norm, t64 + 3, &a64, &t64, mm), "svl_lattice_host");
+        cudaEventRecord(e1);
+        ms = elapsed(e0, e1);
+        active = (uint)a64; total = (uint)t64; d_pos = pos;
+        printf("field min/max %g %g\n", mm[0], mm[1]);
+    } else if (config == 5) {  // density (coarse N/2 x N/4 x N/4 blobs) -> refine -> computeIsosurface_2, iso 0.4
+        const int nx = N, ny = N / 2, nz = N / 2, cx = nx / 2, cy = ny / 2, cz = nz / 2;
+        Mc mc(nx, ny, nz, 0.5f);
+        std::vector<float> coarse((size_t)cx * cy * cz);
+        for (int z = 0; z < cz; ++z) for (int y = 0; y < cy; ++y) for (int x = 0; x < cx; ++x) {
+            float v = 0.5f + 0.5f * sinf(0.21f * x) * sinf(0.17f * y + 0.4f) * cosf(0.19f * z);
+            coarse[((size_t)z * cy + y) * cx + x] = 0.07f + 0.93f * v * v;
+        }
+        float *d_coarse, *d_pitched, *d_dens, *d_result;
+        grid_points* vol_topo;
+        size_t n = (size_t)nx * ny * nz;
+        CK(cudaMalloc(&d_coarse, coarse.size() * 4)); CK(cudaMalloc(&d_pitched, coarse.size() * 4)); CK(cudaMalloc(&d_dens, n * 4));
+        CK(cudaMalloc(&d_result, n * 4)); CK(cudaMalloc(&vol_topo, n * sizeof(grid_points)));
+        CK(cudaMemcpy(d_coarse, coarse.data(), coarse.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(d_result, 0, n * 4)); CK(cudaMemset(vol_topo, 0, n * sizeof(grid_points)));
+        lattice.setupTexture(cx, cy, cz);
+        cudaPitchedPtr pp = make_cudaPitchedPtr(d_pitched, cx * 4, cx * 4, cy);
+        cudaEventRecord(e0);
+        lattice.copytotexture(d_coarse, pp, cx, cy, cz);                                               // toprun_struct :3060
+        lattice.updateTexture(pp);
+        lattice.refine(d_dens, nx, ny, nz, 0.5f, 0.5f, 0.5f);                                          // :3064
+        isosurf.patch_topo_field(d_dens, nx, ny, nz, vol_topo);                                        // :3066
+        isosurf.computeIsosurface_2(mc.d_pos, mc.d_normal, 0.4f, mc.numVoxels, mc.d_voxelVerts, mc.d_voxelVertsScan, mc.d_voxelOccupied, mc.d_voxelOccupiedScan,
+                                    mc.gridSize, mc.gridSizeShift, mc.gridSizeMask, mc.voxelSize, mc.gridcenter, &active, &total, mc.d_compVoxelArray, mc.maxVerts,
+                                    vol_topo, vol_topo, d_dens, d_dens, 0.0f, d_result, nullptr);      // :3107-3109
+        cudaEventRecord(e1);
+        ms = elapsed(e0, e1);
+        d_pos = mc.d_pos;
+    } else {
+        fprintf(stderr, "usage: gpucad_headless <1|2|3|5> [N] [out.obj]\n");
+        return 2;
+    }
+    printf("config %d N=%d: activeVoxels=%u totalVerts=%u triangles=%u  %.3f ms  (%.1f Mvoxel/s)\n", config, N, active, total, total / 3, ms,
+           (double)N * N * N / ms / 1e3);
+    if (obj && total) {
+        output_file.file_write_obj(d_pos, total, obj);
+        printf("wrote %s\n", obj);
+    }
+    return 0;
+}
