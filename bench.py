@@ -89,13 +89,6 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def slab_bounds(gnz, world, rank):
-    cells = gnz - 1
-    z0 = round(rank * cells / world)
-    z1 = round((rank + 1) * cells / world)
-    return z0, z1  # cell layers [z0, z1); point layers z0..z1
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -127,17 +120,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import gpucadforam_b200 as g
-    from gpucadforam_b200 import synth
+    from gpucadforam_b200 import sharding, synth
 
     F, R, NH = args.fine, args.ratio, args.harmonics
     gnz = F * world                      # global point layers
-    z0, z1 = slab_bounds(gnz, world, rank)
+    z0, z1 = sharding.slab_bounds(gnz, world, rank)
     nzl = z1 - z0 + 1
     d = (1.0 / R,) * 3
     cxy = F // R
     czg = gnz // R
-    c0 = z0 // R
-    c1 = min(z1 // R + 1, czg - 1)
+    c0, c1 = sharding.control_slab(z0, z1, R, czg)
     czl = c1 - c0 + 1
     coef = synth.gyroid_coefficients()[:NH]
     harm = synth.HARMONICS[:NH]
@@ -152,14 +144,7 @@ def main():
 
     def field_and_minmax():
         g.svl_field(ctx, svl, phi, coef, (cxy, cxy, czl), ldims, d, slab=(z0, gnz), cz0=c0, d_minmax=mm)
-        if world > 1:
-            t = torch.stack([-mm[0], mm[1]])
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            a, b = -float(t[0]), float(t[1])
-        else:
-            h = mm.cpu()
-            a, b = float(h[0]), float(h[1])
-        return a, b
+        return sharding.allreduce_minmax(dist, mm)   # one 2-float all-reduce (N > 1), then the values on the host
 
     # set-up (untimed): count, then allocate the mesh exactly (count-then-allocate, SURVEY.md 7 "Capacity")
     a, b = field_and_minmax()
@@ -217,9 +202,8 @@ def main():
             return a_, t_
         phi_scratch.copy_(hphi, non_blocking=True)
         g.svl_field(ctx, svl, phi_scratch, coef, (cxy, cxy, czl), ldims, d, slab=(z0, gnz), cz0=c0, d_minmax=mm)
-        t = torch.stack([-mm[0], mm[1]])
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return g.extract_band_raw(ctx, svl, -float(t[0]), float(t[1]), ISO_MASK, BAND_LO, BAND_HI, ldims, voxel, center, mesh.pos, mesh.norm, cap,
+        a_, b_ = sharding.allreduce_minmax(dist, mm)
+        return g.extract_band_raw(ctx, svl, a_, b_, ISO_MASK, BAND_LO, BAND_HI, ldims, voxel, center, mesh.pos, mesh.norm, cap,
                                   slab=(z0, gnz))
 
     for _ in range(2):
@@ -236,16 +220,13 @@ def main():
 
     # max over ranks, global counts and offsets
     stats = torch.tensor([ms, e2e_ms, sum(ext_ms) / len(ext_ms), sum(fld_ms) / len(fld_ms)], device=dev, dtype=torch.float64)
-    counts = torch.tensor([act, tot, launches], device=dev, dtype=torch.int64)
+    per_rank, voff, aoff, (g_act, g_tot) = sharding.gather_counts(dist, act, tot, device=dev)   # global vertex offsets = exclusive scan
+    g_launch = launches
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        allc = [torch.zeros_like(counts) for _ in range(world)]
-        dist.all_gather(allc, counts)                 # per-rank {active, verts} -> global vertex offsets = exclusive scan
-        g_act = sum(int(c[0]) for c in allc)
-        g_tot = sum(int(c[1]) for c in allc)
-        g_launch = sum(int(c[2]) for c in allc)
-    else:
-        g_act, g_tot, g_launch = act, tot, launches
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        g_launch = int(lt[0])
     ms, e2e_ms, ext_k_ms, fld_k_ms = [float(x) for x in stats.cpu()]
 
     if rank == 0:

@@ -89,6 +89,7 @@ int gcb_destroy(gcb_ctx* ctx) {
     cudaFree(C->d_status); cudaFree(C->d_tile_counter); cudaFree(C->d_totals); cudaFreeHost(C->h_totals);
     cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef);
     cudaFree(C->d_tri); cudaFree(C->d_nverts);
+    if (C->copy_stream) { cudaStreamDestroy(C->copy_stream); for (int i = 0; i < Ctx::kBatches; ++i) cudaEventDestroy(C->copy_ev[i]); }
     for (int i = 0; i < 4; ++i) if (C->ev[i]) cudaEventDestroy(C->ev[i]);
     delete C;
     return 0;
@@ -447,9 +448,46 @@ int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch,
                          gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned long long* activeVoxels,
                          unsigned long long* totalVerts, float* minmax_out) {
     CTX(ctx);
-    GCB_CHECK(C, cudaMemcpyAsync(d_phi_scratch, h_phi, (size_t)nh * cx * cy * cz * sizeof(float), cudaMemcpyHostToDevice, C->stream));
-    return gcb_svl_lattice(ctx, d_svl_scratch, d_phi_scratch, nh, coef_host, cx, cy, cz, NX2, NY2, NZ2, dx, dy, dz, isoValue, isovalue1, isovalue2, voxelSize,
-                           gridcenter, pos, norm, maxVerts, activeVoxels, totalVerts, minmax_out);
+    // The harmonics are independent terms of one running sum, so the control grids are uploaded in batches on a copy
+    // stream while the field kernel consumes the previous batch (accumulate = 1 keeps the reference's summation order:
+    // the partial sum round-trips through the fp32 field buffer unchanged).
+    if (!C->copy_stream) {
+        GCB_CHECK(C, cudaStreamCreateWithFlags(&C->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < Ctx::kBatches; ++i) GCB_CHECK(C, cudaEventCreateWithFlags(&C->copy_ev[i], cudaEventDisableTiming));
+    }
+    const size_t per = (size_t)cx * cy * cz;
+    const int nb = nh < Ctx::kBatches ? (nh > 0 ? nh : 1) : Ctx::kBatches;
+    // order the copy stream after everything already queued on the compute stream (the scratch may still be in use)
+    GCB_CHECK(C, cudaEventRecord(C->copy_ev[0], C->stream));
+    GCB_CHECK(C, cudaStreamWaitEvent(C->copy_stream, C->copy_ev[0], 0));
+    int h0 = 0;
+    int start[Ctx::kBatches + 1];
+    for (int b = 0; b < nb; ++b) { start[b] = h0; h0 += (nh - h0) / (nb - b); }
+    start[nb] = nh;
+    for (int b = 0; b < nb; ++b) {
+        const size_t off = (size_t)start[b] * per, cnt = (size_t)(start[b + 1] - start[b]) * per;
+        if (cnt) GCB_CHECK(C, cudaMemcpyAsync(d_phi_scratch + off, h_phi + off, cnt * sizeof(float), cudaMemcpyHostToDevice, C->copy_stream));
+        GCB_CHECK(C, cudaEventRecord(C->copy_ev[b], C->copy_stream));
+    }
+    gcb_slab slab{0u, (unsigned)NZ2};
+    if (int r = k_minmax_init(C, C->d_minmax)) return r;
+    if (C->timing) cudaEventRecord(C->ev[2], C->stream);
+    for (int b = 0; b < nb; ++b) {
+        GCB_CHECK(C, cudaStreamWaitEvent(C->stream, C->copy_ev[b], 0));
+        const bool last = b == nb - 1;
+        if (int r = k_svl_field(C, d_svl_scratch, d_phi_scratch + (size_t)start[b] * per, start[b + 1] - start[b], coef_host + 2 * start[b], cx, cy, cz, 0, NX2,
+                                NY2, NZ2, slab.z0, dx, dy, dz, b > 0, last ? C->d_minmax : nullptr))
+            return r;
+    }
+    if (C->timing) { cudaEventRecord(C->ev[3], C->stream); C->field_timed = true; }
+    if (int r = k_minmax_decode(C, C->d_minmax, C->d_minmax)) return r;
+    GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
+    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
+    const float a = C->h_minmax[0], bmax = C->h_minmax[1];
+    if (minmax_out) { minmax_out[0] = a; minmax_out[1] = bmax; }
+    gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
+    return gcb_extract_band_raw(ctx, d_svl_scratch, a, bmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts, nullptr, 0,
+                                activeVoxels, totalVerts);
 }
 
 } // extern "C"

@@ -86,6 +86,10 @@ struct Ctx {
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool extract_timed = false, field_timed = false;
+    // host-input pipeline: control grids uploaded in batches on a copy stream, overlapped with the field kernel
+    static constexpr int kBatches = 8;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[kBatches] = {};
 };
 
 int fail(Ctx* c, const char* what, cudaError_t e);

@@ -1,0 +1,102 @@
+"""N > 1 host logic on the CPU: world_size-2 gloo processes, the CPU oracle standing in for the per-rank GPU work.
+Checks that z-slab sharding + one min/max all-reduce + one count all-gather reproduce the single-rank mesh byte for byte."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import cases  # noqa: E402
+import oracle_py as orc  # noqa: E402
+from gpucadforam_b200 import sharding  # noqa: E402
+
+N = 40
+VOX = (0.5, 0.5, 0.5)
+
+
+def _field():
+    return orc.create_lattice(N, N, N, 0)
+
+
+def _band_raw_slab(slab, z0, gnz, lo, hi):
+    """oracle version of gcb_extract_band_raw on a slab: normalise with the GLOBAL min/max, global boundary faces, global z."""
+    nzl = slab.shape[0]
+    k = ((slab - np.float32(lo)) / (np.float32(hi) - np.float32(lo))).astype(np.float32)
+    mask = ((k >= np.float32(cases.BAND_LO)) & (k <= np.float32(cases.BAND_HI))).astype(np.float32)
+    gz = np.arange(z0, z0 + nzl)
+    face = np.zeros(slab.shape, bool)
+    face[:, 0, :] = face[:, -1, :] = face[:, :, 0] = face[:, :, -1] = True
+    face[gz == 0] = True
+    face[gz == gnz - 1] = True
+    k[face] = 0.0
+    mask[face] = 0.0
+    r = orc.extract(orc.MODE_LATTICE_ONE, (N, N, nzl), VOX, (0, 0, -float(z0)), cases.ISO_MASK, f0=mask, f1=k, iso1=cases.BAND_LO, iso2=cases.BAND_HI)
+    return r
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f = _field()
+    z0, z1 = sharding.slab_bounds(N, world, rank)
+    slab = np.ascontiguousarray(f[z0:z1 + 1])
+    lo_l, hi_l = orc.minmax(slab)
+    lo, hi = sharding.allreduce_minmax(dist, torch.tensor([lo_l, hi_l], dtype=torch.float32))
+    r = _band_raw_slab(slab, z0, N, lo, hi)
+    per_rank, voff, aoff, totals = sharding.gather_counts(dist, r["active"], r["total"])
+    np.savez(os.path.join(out, "rank%d.npz" % rank), pos=r["pos"][:r["total"]], norm=r["norm"][:r["total"]],
+             comp=r["compVoxelArray"].astype(np.int64) + z0 * (N - 1) * (N - 1), voff=voff[rank], aoff=aoff[rank], totals=np.array(totals), lohi=np.array([lo, hi]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_slabs_reproduce_single_rank(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 2
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    f = _field()
+    lo, hi = orc.minmax(f)
+    single = _band_raw_slab(f, 0, N, lo, hi)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    assert tuple(parts[0]["lohi"]) == (np.float32(lo), np.float32(hi)) or np.allclose(parts[0]["lohi"], [lo, hi], rtol=0, atol=0)
+    assert tuple(parts[0]["totals"]) == (single["active"], single["total"])
+    assert int(parts[0]["voff"]) == 0 and int(parts[1]["voff"]) == len(parts[0]["pos"])
+    pos = np.concatenate([p["pos"] for p in parts])
+    norm = np.concatenate([p["norm"] for p in parts])
+    comp = np.concatenate([p["comp"] for p in parts])
+    t = single["total"]
+    assert np.array_equal(pos.view(np.uint32), single["pos"][:t].view(np.uint32))
+    assert np.array_equal(norm.view(np.uint32), single["norm"][:t].view(np.uint32))
+    assert np.array_equal(comp, single["compVoxelArray"].astype(np.int64))
+
+
+def test_slab_bounds_cover_every_cell_layer_once():
+    for gnz in (2, 17, 512, 2048):
+        for world in (1, 2, 3, 4, 8):
+            b = [sharding.slab_bounds(gnz, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == gnz - 1
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+
+
+def test_control_slab_covers_sampled_planes():
+    for ratio in (2, 4, 8):
+        czg = 64
+        gnz = czg * ratio
+        for world in (2, 4, 8):
+            for r in range(world):
+                z0, z1 = sharding.slab_bounds(gnz, world, r)
+                c0, c1 = sharding.control_slab(z0, z1, ratio, czg)
+                for z in (z0, z1):
+                    i = z // ratio
+                    assert c0 <= i <= c1 and min(i + 1, czg - 1) <= c1
