@@ -218,8 +218,7 @@ __device__ __forceinline__ float t_analysis(float iso, float f0, float f1, float
 // ---------------------------------------------------------------- stage-in: one grid point -> {value, bits}
 // bits: [1:0] id class of the mask value (0:==0, 1:==1, 2:==2, 3:other), [2] inside flag.
 template <int MODE>
-__device__ __forceinline__ void stage_point(const McArgs& A, size_t gi, uint32_t x, uint32_t y, uint32_t zl, float raw, float& val,
-                                            uint32_t& bits) {
+__device__ __forceinline__ void stage_point(const McArgs& A, size_t gi, uint32_t x, bool row_face, float raw, float& val, uint32_t& bits) {
     if (MODE == M_LATTICE_ONE || MODE == M_LATTICE) {
         const float m = __ldg(A.f1 + gi);  // mask `vol`; classifyVoxel_new :3232-3239
         uint32_t id = (m == 1.f) ? 1u : (m == 0.f) ? 0u : (m == 2.f) ? 2u : 3u;
@@ -229,8 +228,7 @@ __device__ __forceinline__ void stage_point(const McArgs& A, size_t gi, uint32_t
         // device_bufferfour (Gratings.cu:1089-1134) fused; domain faces use GLOBAL coordinates
         float k = __fdiv_rn(__fsub_rn(raw, A.na), __fsub_rn(A.nb, A.na));
         float m;
-        const uint32_t gz = zl + A.gz0;
-        if (x == 0 || x == A.nx - 1 || y == 0 || y == A.ny - 1 || gz == 0 || gz == A.gnz - 1) { m = 0.0f; k = 0.0f; }
+        if (row_face || x == 0 || x == A.nx - 1) { m = 0.0f; k = 0.0f; }
         else m = ((k >= A.iso1) && (k <= A.iso2)) ? 1.0f : 0.0f;
         bits = (m == 1.f ? 1u : 0u) | ((m < A.iso) ? 4u : 0u);
         val = k;
@@ -269,6 +267,8 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
     const float3 p = make_float3(__fmul_rn(__fsub_rn((float)x, A.center.x), A.voxel.x), __fmul_rn(__fsub_rn((float)y, A.center.y), A.voxel.y),
                                  __fmul_rn(__fsub_rn((float)(z + A.gz0), A.center.z), A.voxel.z));  // global z under slab sharding
 
+    const float3 pmax = make_float3(__fadd_rn(p.x, A.voxel.x), __fadd_rn(p.y, A.voxel.y), __fadd_rn(p.z, A.voxel.z));
+    const uint32_t sbase = r * A.nx + x;
     float3 v[3];
     float w[3];
 #pragma unroll
@@ -277,11 +277,11 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
         const bool own = (MODE == M_TOPO) || (MODE == M_CSG && !(A.flags & F_FIXED));
         const uint32_t ab = own ? edge_own(e) : edge_lat(e);
         const uint32_t ca = corner_bits(ab & 15u), cb = corner_bits(ab >> 4);
-        // corner positions: v[0] = p, v[i] = p + (voxel or 0) per component (:1892-1900)
-        float3 pa = p, pb = p;
-        if (ca) pa = make_float3(__fadd_rn(p.x, (ca & 1u) ? A.voxel.x : 0.f), __fadd_rn(p.y, (ca & 2u) ? A.voxel.y : 0.f), __fadd_rn(p.z, (ca & 4u) ? A.voxel.z : 0.f));
-        if (cb) pb = make_float3(__fadd_rn(p.x, (cb & 1u) ? A.voxel.x : 0.f), __fadd_rn(p.y, (cb & 2u) ? A.voxel.y : 0.f), __fadd_rn(p.z, (cb & 4u) ? A.voxel.z : 0.f));
-        const uint32_t sa = (r + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u), sb = (r + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
+        // corner positions: v[0] = p, v[i] = p + (voxel or 0) per component (:1892-1900).  p + 0.0f == p bit for bit for every
+        // p this kernel can produce (x - center is never -0, voxel sizes are positive), so each component is a select.
+        const float3 pa = make_float3((ca & 1u) ? pmax.x : p.x, (ca & 2u) ? pmax.y : p.y, (ca & 4u) ? pmax.z : p.z);
+        const float3 pb = make_float3((cb & 1u) ? pmax.x : p.x, (cb & 2u) ? pmax.y : p.y, (cb & 4u) ? pmax.z : p.z);
+        const uint32_t sa = sbase + ((ca & 2u) ? A.nx : 0u) + (ca & 1u), sb = sbase + ((cb & 2u) ? A.nx : 0u) + (cb & 1u);
         const uint32_t za = (ca >> 2) & 1u, zb = (cb >> 2) & 1u;
         const float fa = (za ? S.val[1] : S.val[0])[sa], fb = (zb ? S.val[1] : S.val[0])[sb];
         w[k] = 0.f;
@@ -309,19 +309,20 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
                 et = ax == 0 ? g.t_x : ax == 1 ? g.t_y : g.t_z;
             }
             float t;
+            float3 qa = pa, qb = pb;
             if (MODE == M_TOPO) {
                 t = t_analysis(A.iso, fa, fb, et);
                 w[k] = A.f1 ? __ldg(A.f1 + ga) : 0.f;  // *field_val = r0 (:1797)
                 if (A.flags & F_DISP) {
                     const float4 d0 = A.disp[ga], d1 = A.disp[gb];
-                    pa = make_float3(d0.x, d0.y, d0.z);
-                    pb = make_float3(d1.x, d1.y, d1.z);
+                    qa = make_float3(d0.x, d0.y, d0.z);
+                    qb = make_float3(d1.x, d1.y, d1.z);
                 }
             } else if (A.flags & F_MAKE_REGION) t = et;
             else if (A.flags & F_FIXED) t = t_fixed(A.iso, A.iso1, A.iso2, fa, fb, __ldg(A.f1 + ga), __ldg(A.f1 + gb));
             else if (A.flags & F_DYNAMIC) t = t_primitive_one(A.iso1, A.iso2, __ldg(A.f1 + ga), __ldg(A.f1 + gb), et);
             else t = t_primitive(A.iso, fa, fb, et);
-            v[k] = lerp3(pa, pb, t);
+            v[k] = lerp3(qa, qb, t);
         }
     }
     float3 n;
@@ -407,6 +408,8 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
             unsigned char* sb = s ? S.bit[1] : S.bit[0];
             const size_t gs = g0 + (size_t)s * slice_pts;
             for (uint32_t rr = warp; rr <= rows; rr += kWarps) {
+                const uint32_t yy = y0 + rr, gz = z + s + A.gz0;
+                const bool row_face = yy == 0 || yy == A.ny - 1 || gz == 0 || gz == A.gnz - 1;  // domain faces in GLOBAL coordinates
                 for (uint32_t x = lane; x < A.nx; x += 32) {
                     const uint32_t pnt = rr * A.nx + x;
                     float raw;
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                     else raw = A.f0 ? __ldg(A.f0 + gs + pnt) : 0.f;
                     float val;
                     uint32_t bits;
-                    stage_point<MODE>(A, gs + pnt, x, y0 + rr, z + s, raw, val, bits);
+                    stage_point<MODE>(A, gs + pnt, x, row_face, raw, val, bits);
                     sv[pnt] = val;
                     sb[pnt] = (unsigned char)bits;
                 }
@@ -525,7 +528,9 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                     A.st_verts_scan[gc] = (uint32_t)(vert_base + 3ull * (tail + excl));
                     A.st_occ_scan[gc] = (uint32_t)(act_base + act_run + rank);
                 }
-                for (uint32_t jj = 0; jj < nt; ++jj) q[(tail + excl + jj) & (kQueue - 1)] = (jj << 28) | c;
+#pragma unroll
+                for (uint32_t jj = 0; jj < 5; ++jj)  // a cell has at most 5 triangles; predicated stores instead of a divergent loop
+                    if (jj < nt) q[(tail + excl + jj) & (kQueue - 1)] = (jj << 28) | c;
                 tail += step_tris;
                 act_run += __popc(amask);
                 __syncwarp();
