@@ -200,8 +200,7 @@ def main():
             a_, t_, _ = g.svl_lattice_host(ctx, hphi, phi_scratch, svl, coef, (cxy, cxy, czl), ldims, d, ISO_MASK, BAND_LO, BAND_HI, voxel, center, mesh.pos,
                                            mesh.norm, cap)
             return a_, t_
-        phi_scratch.copy_(hphi, non_blocking=True)
-        g.svl_field(ctx, svl, phi_scratch, coef, (cxy, cxy, czl), ldims, d, slab=(z0, gnz), cz0=c0, d_minmax=mm)
+        g.svl_field_host(ctx, svl, hphi, phi_scratch, coef, (cxy, cxy, czl), ldims, d, slab=(z0, gnz), cz0=c0, d_minmax=mm)
         a_, b_ = sharding.allreduce_minmax(dist, mm)
         return g.extract_band_raw(ctx, svl, a_, b_, ISO_MASK, BAND_LO, BAND_HI, ldims, voxel, center, mesh.pos, mesh.norm, cap,
                                   slab=(z0, gnz))

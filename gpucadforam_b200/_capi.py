@@ -86,6 +86,7 @@ SIGNATURES = {
     "gcb_deleteTexture": (I, [P]),
     "gcb_file_write_obj": (I, [P, P, U, C.c_char_p]),
     "gcb_svl_field": (I, [P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, I, P]),
+    "gcb_svl_field_host": (I, [P, P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, P]),
     "gcb_minmax": (I, [P, P, C.c_size_t, PF, PF]),
     "gcb_extract_band_raw": (I, [P, P, F, F, F, F, F, Uint3, Slab, Float3, Float3, P, P, ULL, P, I, PULL, PULL]),
     "gcb_svl_lattice": (I, [P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),

@@ -299,6 +299,15 @@ def svl_field(ctx, d_svl, d_phi, coef, cdims, fdims, d, slab=(0, 0), cz0=0, accu
                                   Slab(slab[0], slab[1] or nz2l), d[0], d[1], d[2], int(accumulate), _ptr(d_minmax)))
 
 
+def svl_field_host(ctx, d_svl, h_phi, d_phi_scratch, coef, cdims, fdims, d, slab=(0, 0), cz0=0, d_minmax=None):
+    """h_phi: pinned (or pageable) HOST tensor [nh, czl, cy, cx]; batched upload overlapped with the field kernel."""
+    assert not h_phi.is_cuda and h_phi.is_contiguous()
+    cx, cy, czl = cdims
+    nx2, ny2, nz2l = fdims
+    ctx.check(lib().gcb_svl_field_host(ctx._h, _ptr(d_svl), C.c_void_p(h_phi.data_ptr()), _ptr(d_phi_scratch), len(coef), _coef_array(coef), cx, cy, czl, cz0,
+                                       nx2, ny2, nz2l, Slab(slab[0], slab[1] or nz2l), d[0], d[1], d[2], _ptr(d_minmax)))
+
+
 def extract_band_raw(ctx, d_field, a, b, isoValue, isovalue1, isovalue2, gridSizeLocal, voxelSize, gridcenter, pos, norm, maxVerts, slab=(0, 0),
                      comp=None, count_only=False):
     act, tot = C.c_ulonglong(0), C.c_ulonglong(0)

@@ -443,10 +443,8 @@ int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int 
                                 activeVoxels, totalVerts);
 }
 
-int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host, int cx, int cy, int cz,
-                         int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2, gcb_float3 voxelSize,
-                         gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned long long* activeVoxels,
-                         unsigned long long* totalVerts, float* minmax_out) {
+int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_phi_scratch, int nh, const float* coef_host, int cx, int cy, int cz_local,
+                       int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_minmax) {
     CTX(ctx);
     // The harmonics are independent terms of one running sum, so the control grids are uploaded in batches on a copy
     // stream while the field kernel consumes the previous batch (accumulate = 1 keeps the reference's summation order:
@@ -455,7 +453,7 @@ int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch,
         GCB_CHECK(C, cudaStreamCreateWithFlags(&C->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < Ctx::kBatches; ++i) GCB_CHECK(C, cudaEventCreateWithFlags(&C->copy_ev[i], cudaEventDisableTiming));
     }
-    const size_t per = (size_t)cx * cy * cz;
+    const size_t per = (size_t)cx * cy * cz_local;
     const int nb = nh < Ctx::kBatches ? (nh > 0 ? nh : 1) : Ctx::kBatches;
     // order the copy stream after everything already queued on the compute stream (the scratch may still be in use)
     GCB_CHECK(C, cudaEventRecord(C->copy_ev[0], C->stream));
@@ -469,18 +467,27 @@ int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch,
         if (cnt) GCB_CHECK(C, cudaMemcpyAsync(d_phi_scratch + off, h_phi + off, cnt * sizeof(float), cudaMemcpyHostToDevice, C->copy_stream));
         GCB_CHECK(C, cudaEventRecord(C->copy_ev[b], C->copy_stream));
     }
-    gcb_slab slab{0u, (unsigned)NZ2};
-    if (int r = k_minmax_init(C, C->d_minmax)) return r;
+    if (d_minmax) if (int r = k_minmax_init(C, C->d_minmax)) return r;
     if (C->timing) cudaEventRecord(C->ev[2], C->stream);
     for (int b = 0; b < nb; ++b) {
         GCB_CHECK(C, cudaStreamWaitEvent(C->stream, C->copy_ev[b], 0));
         const bool last = b == nb - 1;
-        if (int r = k_svl_field(C, d_svl_scratch, d_phi_scratch + (size_t)start[b] * per, start[b + 1] - start[b], coef_host + 2 * start[b], cx, cy, cz, 0, NX2,
-                                NY2, NZ2, slab.z0, dx, dy, dz, b > 0, last ? C->d_minmax : nullptr))
+        if (int r = k_svl_field(C, d_svl, d_phi_scratch + (size_t)start[b] * per, start[b + 1] - start[b], coef_host + 2 * start[b], cx, cy, cz_local, cz0, NX2,
+                                NY2, NZ2_local, slab.z0, dx, dy, dz, b > 0, (last && d_minmax) ? C->d_minmax : nullptr))
             return r;
     }
     if (C->timing) { cudaEventRecord(C->ev[3], C->stream); C->field_timed = true; }
-    if (int r = k_minmax_decode(C, C->d_minmax, C->d_minmax)) return r;
+    if (d_minmax) if (int r = k_minmax_decode(C, C->d_minmax, d_minmax)) return r;
+    return 0;
+}
+
+int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host, int cx, int cy, int cz,
+                         int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2, gcb_float3 voxelSize,
+                         gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned long long* activeVoxels,
+                         unsigned long long* totalVerts, float* minmax_out) {
+    CTX(ctx);
+    gcb_slab slab{0u, (unsigned)NZ2};
+    if (int r = gcb_svl_field_host(ctx, d_svl_scratch, h_phi, d_phi_scratch, nh, coef_host, cx, cy, cz, 0, NX2, NY2, NZ2, slab, dx, dy, dz, C->d_minmax)) return r;
     GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
     GCB_CHECK(C, cudaStreamSynchronize(C->stream));
     const float a = C->h_minmax[0], bmax = C->h_minmax[1];

@@ -176,6 +176,11 @@ typedef struct gcb_slab { unsigned int z0, gnz; } gcb_slab;
 int gcb_svl_field(gcb_ctx* ctx, float* d_svl, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz_local,
     int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, int accumulate, float* d_minmax);
 
+/* Same field from HOST control grids (pinned or pageable): the grids are uploaded in harmonic batches on a copy stream
+ * while the kernel consumes the previous batch; bit-identical to gcb_svl_field.  d_phi_scratch: device float[nh*cx*cy*cz_local]. */
+int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_phi_scratch, int nh, const float* coef_host, int cx, int cy,
+    int cz_local, int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_minmax);
+
 /* min/max of a device array with the reference's semantics (result on host). */
 int gcb_minmax(gcb_ctx* ctx, const float* d_in, size_t n, float* lo, float* hi);
 

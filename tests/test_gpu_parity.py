@@ -472,6 +472,11 @@ def test_svl_lattice_pipeline_and_host_entry(ctx):
                                      (0, 0, 0), mesh3.pos, mesh3.norm, mv)
     assert (a3, t3, mm3) == (a1, t1, mm)
     assert_bits_equal(mesh.pos[:t1], mesh3.pos[:t1], "svl_lattice_host pos")
+    # batched host upload of the field alone (multi-rank e2e path)
+    f2, mmd = torch.zeros_like(field), torch.zeros(2, device="cuda")
+    g.svl_field_host(ctx, f2, hphi, scratch_phi, coef, cfg["cdims"], dims, cfg["d"], d_minmax=mmd)
+    assert_bits_equal(f2, field, "svl_field_host")
+    assert (float(mmd[0]), float(mmd[1])) == mm
 
 
 @pytest.mark.parametrize("nslabs", [2, 3, 5])
