@@ -120,6 +120,7 @@ struct Smem {
     unsigned long long* prefix;  // [0]=active prefix, [1]=vertex prefix (exclusive, for this tile)
     uint32_t* tile_id;
     uint64_t* mbar;
+    unsigned char* edge;  // [0..11] lattice edge order, [16..27] owner edge order: corner bits ca | cb << 3
 };
 
 __device__ __forceinline__ float3 lerp3(float3 a, float3 b, float t) {
@@ -275,8 +276,8 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
     for (int k = 0; k < 3; ++k) {
         const uint32_t e = (uint32_t)(tri >> (4 * (3 * j + k))) & 15u;
         const bool own = (MODE == M_TOPO) || (MODE == M_CSG && !(A.flags & F_FIXED));
-        const uint32_t ab = own ? edge_own(e) : edge_lat(e);
-        const uint32_t ca = corner_bits(ab & 15u), cb = corner_bits(ab >> 4);
+        const uint32_t ab = S.edge[(own ? 16u : 0u) + e];
+        const uint32_t ca = ab & 7u, cb = ab >> 3;
         // corner positions: v[0] = p, v[i] = p + (voxel or 0) per component (:1892-1900).  p + 0.0f == p bit for bit for every
         // p this kernel can produce (x - center is never -0, voxel sizes are positive), so each component is a select.
         const float3 pa = make_float3((ca & 1u) ? pmax.x : p.x, (ca & 2u) ? pmax.y : p.y, (ca & 4u) ? pmax.z : p.z);
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
         S.prefix = (unsigned long long*)p; p += 16;
         S.mbar = (uint64_t*)p; p += 8;
         S.tile_id = (uint32_t*)p; p += 8;
+        S.edge = p; p += 32;
         S.queue = (uint32_t*)p; p += kWarps * kQueue * 4;
         S.warp_tot = (uint32_t*)p; p += kWarps * 2 * 4;
         S.nv = p; p += 256;
@@ -372,6 +374,11 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
         unsigned long long u = ~t;                      // used nibble != 0xF  <=> ~nibble != 0
         u = (u | (u >> 1) | (u >> 2) | (u >> 3)) & 0x1111111111111111ull;
         S.nv[i] = (unsigned char)__popcll(u);
+    }
+    if (tid < 12) {
+        const uint32_t l = edge_lat(tid), o = edge_own(tid);
+        S.edge[tid] = (unsigned char)(corner_bits(l & 15u) | (corner_bits(l >> 4) << 3));
+        S.edge[16 + tid] = (unsigned char)(corner_bits(o & 15u) | (corner_bits(o >> 4) << 3));
     }
     if (tid == 0) { mbar_init(S.mbar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -410,6 +417,26 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
             for (uint32_t rr = warp; rr <= rows; rr += kWarps) {
                 const uint32_t yy = y0 + rr, gz = z + s + A.gz0;
                 const bool row_face = yy == 0 || yy == A.ny - 1 || gz == 0 || gz == A.gnz - 1;  // domain faces in GLOBAL coordinates
+                if (A.use_tma && A.f0) {
+                    // TMA path: nx % 4 == 0 and rows are 16-byte aligned in shared memory -> four points per lane and iteration
+                    for (uint32_t x = lane * 4; x < A.nx; x += 128) {
+                        const uint32_t pnt = rr * A.nx + x;
+                        float4 v4 = *reinterpret_cast<const float4*>(sv + pnt);
+                        float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+                        uint32_t packed = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float val;
+                            uint32_t bits;
+                            stage_point<MODE>(A, gs + pnt + u, x + u, row_face, vv[u], val, bits);
+                            vv[u] = val;
+                            packed |= bits << (8 * u);
+                        }
+                        *reinterpret_cast<float4*>(sv + pnt) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                        *reinterpret_cast<uint32_t*>(sb + pnt) = packed;
+                    }
+                    continue;
+                }
                 for (uint32_t x = lane; x < A.nx; x += 32) {
                     const uint32_t pnt = rr * A.nx + x;
                     float raw;
@@ -510,6 +537,8 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                 const bool valid = c < cend;
                 const uint32_t nv = valid ? S.nv[S.cube[c]] : 0u;
                 const uint32_t nt = (nv * 11u) >> 5;  // nv / 3 for nv in {0,3,..,15}
+                const uint32_t amask = __ballot_sync(0xffffffffu, nv > 0);
+                if (amask == 0u && !A.st_verts) continue;  // nothing to scan, enqueue or drain in this 32-cell step
                 uint32_t incl = nt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -518,7 +547,6 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                 }
                 const uint32_t excl = incl - nt;
                 const uint32_t step_tris = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t amask = __ballot_sync(0xffffffffu, nv > 0);
                 const uint32_t rank = __popc(amask & ((1u << lane) - 1u));
                 if (nv > 0 && A.comp) A.comp[act_base + act_run + rank] = (uint32_t)(cell0 + c) + A.gz0 * A.cx * A.cy;
                 if (A.st_verts && valid) {
@@ -528,8 +556,7 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                     A.st_verts_scan[gc] = (uint32_t)(vert_base + 3ull * (tail + excl));
                     A.st_occ_scan[gc] = (uint32_t)(act_base + act_run + rank);
                 }
-#pragma unroll
-                for (uint32_t jj = 0; jj < 5; ++jj)  // a cell has at most 5 triangles; predicated stores instead of a divergent loop
+                for (uint32_t jj = 0; __any_sync(0xffffffffu, jj < nt); ++jj)  // at most 5 rounds, warp-uniform trip count
                     if (jj < nt) q[(tail + excl + jj) & (kQueue - 1)] = (jj << 28) | c;
                 tail += step_tris;
                 act_run += __popc(amask);
@@ -573,7 +600,7 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     uint32_t R = 4096u / a.cx;
     if (R < 1) R = 1;
     if (R > a.cy) R = a.cy;
-    const size_t fixed_bytes = 256 * 8 + 16 + 8 + 8 + kWarps * kQueue * 4 + kWarps * 8 + 256 + 256 /*slack*/;
+    const size_t fixed_bytes = 256 * 8 + 16 + 8 + 8 + 32 + kWarps * kQueue * 4 + kWarps * 8 + 256 + 256 /*slack*/;
     auto smem_for = [&](uint32_t r) {
         const size_t stride = (((size_t)(r + 1) * a.nx) + 15) & ~(size_t)15;
         return stride * 4 * 2 + stride * 2 + (size_t)r * a.cx + 16 + fixed_bytes;

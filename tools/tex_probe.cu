@@ -90,7 +90,8 @@ int main(int argc, char** argv) {
     const int cx = 40, cy = 36, cz = 32;
     std::vector<float> h((size_t)cx * cy * cz);
     srand(1);
-    for (auto& v : h) v = ((rand() % 200001) - 100000) * 0.00123f;
+    const bool wild = argc > 2;  // values spread over 2^24 in magnitude (exercise alignment / truncation of the filter)
+    for (auto& v : h) { v = ((rand() % 200001) - 100000) * 0.00123f; if (wild) v = ldexpf(v, -(rand() % 24)); }
     float* dg; cudaMalloc(&dg, h.size() * 4); cudaMemcpy(dg, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
     cudaArray_t arr; cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
     cudaExtent ext = make_cudaExtent(cx, cy, cz);
@@ -120,7 +121,7 @@ int main(int argc, char** argv) {
         for (int ratio : {2, 4, 8}) {
             dump<<<(nsamp + 255) / 256, 256>>>(tex, dg, cx, cy, cz, cx * ratio, cy * ratio, cz * ratio, 1.0f / ratio, dout, nsamp);
             cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost);
-            char name[512]; snprintf(name, sizeof name, "%s/tex_samples_r%d.bin", argv[1], ratio);
+            char name[512]; snprintf(name, sizeof name, "%s/tex_samples%s_r%d.bin", argv[1], wild ? "_wild" : "", ratio);
             FILE* f = fopen(name, "wb"); fwrite(ho.data(), 4, ho.size(), f); fclose(f);
         }
     }
