@@ -100,6 +100,7 @@ def main():
     ap.add_argument("--harmonics", type=int, default=62)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed steps only (no e2e leg, no CPU baseline): for runs under ncu")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the global grid is fine^3 for every N (e.g. --fine 2048 --gpus 8 = BASELINE config 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -123,7 +124,7 @@ def main():
     from gpucadforam_b200 import sharding, synth
 
     F, R, NH = args.fine, args.ratio, args.harmonics
-    gnz = F * world                      # global point layers
+    gnz = F if args.strong else F * world   # global point layers (weak scaling: one fine^3 block per rank)
     z0, z1 = sharding.slab_bounds(gnz, world, rank)
     nzl = z1 - z0 + 1
     d = (1.0 / R,) * 3
@@ -237,7 +238,7 @@ def main():
         sincos = float(F) * F * nzl * NH
         out = {
             "metric": "voxels/s (field + marching cubes, device-timed)", "value": points / (ms * 1e-3), "unit": "voxels/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config 3: spatially varying gyroid lattice, %d harmonics, control grid %dx%dx%d -> fine %dx%dx%d, band [0.20,0.30]"
                                    % (NH, cxy, cxy, czg, F, F, gnz),
@@ -296,7 +297,7 @@ def reference_arm(args, torch, rank, world, local_rank):
     import ref_py as ref
     F, R, NH = args.fine, args.ratio, args.harmonics
     base = {"impl": "reference", "metric": "voxels/s (field + marching cubes, device-timed)", "unit": "voxels/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
     if not (ref.available() and torch.cuda.is_available()):
         cb = cpu_baseline(NH)
         base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,

@@ -12,10 +12,18 @@ reference orders vertices by ascending linear cell id with z slowest (MarchingCu
 import torch
 
 
-def slab_bounds(gnz, world, rank):
-    """Cell layers [z0, z1) owned by `rank` of a grid with gnz point layers (gnz-1 cell layers)."""
+def slab_bounds(gnz, world, rank, align=2):
+    """Cell layers [z0, z1) owned by `rank` of a grid with gnz point layers (gnz-1 cell layers).  Interior boundaries are
+    multiples of `align` (2: the fused SVL kernel evaluates 2x2x2 point blocks and wants slabs to start on an even layer)."""
     cells = gnz - 1
-    return round(rank * cells / world), round((rank + 1) * cells / world)
+
+    def cut(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return cells
+        return min(cells, max(0, int(round(r * cells / world / align)) * align))
+    return cut(rank), cut(rank + 1)
 
 
 def control_slab(z0, z1, ratio, czg):
