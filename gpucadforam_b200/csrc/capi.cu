@@ -1,5 +1,7 @@
 // capi.cu -- extern "C" boundary of libgpucad_b200 (declared in include/gpucad_b200.h).
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 #include <cstdio>
 #include <cstring>
@@ -454,13 +456,28 @@ int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_
         for (int i = 0; i < Ctx::kBatches; ++i) GCB_CHECK(C, cudaEventCreateWithFlags(&C->copy_ev[i], cudaEventDisableTiming));
     }
     const size_t per = (size_t)cx * cy * cz_local;
-    const int nb = nh < Ctx::kBatches ? (nh > 0 ? nh : 1) : Ctx::kBatches;
+    int nb = nh < Ctx::kBatches ? (nh > 0 ? nh : 1) : Ctx::kBatches;
     // order the copy stream after everything already queued on the compute stream (the scratch may still be in use)
     GCB_CHECK(C, cudaEventRecord(C->copy_ev[0], C->stream));
     GCB_CHECK(C, cudaStreamWaitEvent(C->copy_stream, C->copy_ev[0], 0));
-    int h0 = 0;
     int start[Ctx::kBatches + 1];
-    for (int b = 0; b < nb; ++b) { start[b] = h0; h0 += (nh - h0) / (nb - b); }
+    if (const char* sched = getenv("GCB_SVL_BATCHES")) {  // experiment: explicit batch sizes "2,4,8,..." (remainder goes to the last batch)
+        int b = 0, h0 = 0;
+        for (const char* q = sched; *q && b < Ctx::kBatches - 1 && h0 < nh; ++b) {
+            start[b] = h0;
+            h0 = std::min(nh, h0 + std::max(1, atoi(q)));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (h0 < nh) { start[b++] = h0; }
+        nb = b;
+    } else {
+        // small batches first (the first kernel can start after a short copy), doubling up to ~nh/6, the rest split evenly:
+        // with the field kernel slower than the copy, the step then costs first copy + sum of kernels
+        int h0 = 0, b = 0;
+        for (int sz = 1; b < nb / 2 && sz * 6 <= nh; sz *= 2, ++b) { start[b] = h0; h0 += sz; }
+        for (; b < nb; ++b) { start[b] = h0; h0 += (nh - h0) / (nb - b); }
+    }
     start[nb] = nh;
     for (int b = 0; b < nb; ++b) {
         const size_t off = (size_t)start[b] * per, cnt = (size_t)(start[b + 1] - start[b]) * per;
@@ -469,12 +486,21 @@ int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_
     }
     if (d_minmax) if (int r = k_minmax_init(C, C->d_minmax)) return r;
     if (C->timing) cudaEventRecord(C->ev[2], C->stream);
+    static const bool trace = getenv("GCB_TRACE") != nullptr;  // debugging aid: per-batch timeline on stderr
+    cudaEvent_t tev[Ctx::kBatches + 1];
+    if (trace) { for (int b = 0; b <= nb; ++b) cudaEventCreate(&tev[b]); cudaEventRecord(tev[0], C->stream); }
     for (int b = 0; b < nb; ++b) {
         GCB_CHECK(C, cudaStreamWaitEvent(C->stream, C->copy_ev[b], 0));
         const bool last = b == nb - 1;
         if (int r = k_svl_field(C, d_svl, d_phi_scratch + (size_t)start[b] * per, start[b + 1] - start[b], coef_host + 2 * start[b], cx, cy, cz_local, cz0, NX2,
                                 NY2, NZ2_local, slab.z0, dx, dy, dz, b > 0, (last && d_minmax) ? C->d_minmax : nullptr))
             return r;
+        if (trace) cudaEventRecord(tev[b + 1], C->stream);
+    }
+    if (trace) {
+        cudaStreamSynchronize(C->stream);
+        for (int b = 0; b < nb; ++b) { float ms; cudaEventElapsedTime(&ms, tev[0], tev[b + 1]); fprintf(stderr, "[gcb trace] batch %d (%d harmonics) done at %.3f ms\n", b, start[b + 1] - start[b], ms); }
+        for (int b = 0; b <= nb; ++b) cudaEventDestroy(tev[b]);
     }
     if (C->timing) { cudaEventRecord(C->ev[3], C->stream); C->field_timed = true; }
     if (d_minmax) if (int r = k_minmax_decode(C, C->d_minmax, d_minmax)) return r;
