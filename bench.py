@@ -252,10 +252,14 @@ def main():
                             "as in the reference (Vulkan-exported vertex buffers)"},
             "gpu_launches": g_launch,
             "roofline": {"bound": "hbm", "kernel": "mc_fused_kernel<M_BAND_RAW>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel_ms": ext_k_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
-            "field_kernel": {"kernel": "svl_field_kernel<pair>", "bound": "fp32 pipe (libdevice sinf/cosf)", "kernel_ms": fld_k_ms,
+                         "traffic": NCU_TRAFFIC_BYTES if (F, R, NH, world) == (512, 4, 62, 1) else None,
+                         "traffic_source": "profiles/r01_ncu_mc_fused.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch, this workload)",
+                         "kernel_ms": ext_k_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+            # the field kernel moves 4 B/point and is bound by instruction issue (exact texture model in fp64 + libdevice-identical
+            # sincosf): reported as issue slots per (point, harmonic), not against the HBM roofline
+            "field_kernel": {"kernel": "svl_field_tile_kernel", "bound": "instruction issue (fp64 lerps + sincosf polynomial)", "kernel_ms": fld_k_ms,
                              "sincos_pairs_per_s": sincos / (fld_k_ms * 1e-3),
-                             "fp32_lane_cycles_per_sincos_pair": 148 * 128 * sm_mhz * 1e6 * (fld_k_ms * 1e-3) / sincos},
+                             "issue_slots_per_point_harmonic": 148 * 4 * 32 * sm_mhz * 1e6 * (fld_k_ms * 1e-3) / sincos},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
@@ -263,6 +267,10 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# measured once with `ncu --set full` on the default workload (profiles/r01_ncu_mc_fused.txt): 0.538 GB read + 5.464 GB written
+NCU_TRAFFIC_BYTES = 538399232 + 5464463000
 
 
 def cpu_baseline(nh, budget_s=12.0):
