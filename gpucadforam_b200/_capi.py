@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpucad_b200.so")
+LIB_PATH = os.environ.get("GCB_LIB_PATH") or os.path.join(_HERE, "libgpucad_b200.so")  # GCB_LIB_PATH: A/B builds of the library
 
 
 class Uint3(C.Structure):

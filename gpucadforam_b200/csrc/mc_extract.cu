@@ -163,6 +163,28 @@ __device__ __forceinline__ float3 interp_band(float thr, float l1, float l2, flo
     }
     return r;
 }
+// The same for M_BAND_RAW, where the mask is built in-kernel from the band test: an edge named by the triangle table joins
+// a point with mask 0 to a point with mask 1 (the cube bits ARE "mask < iso" and the mask only takes the values 0 and 1), so
+// the reference's id test is true for every edge that reaches this function and the ids need not be staged or looked at.
+__device__ __forceinline__ float3 interp_band_crossing(float thr, float l1, float l2, float3 p0, float3 p1, float f0, float f1) {
+    const bool sw = f1 < f0;
+    const float lo = sw ? f1 : f0, hi = sw ? f0 : f1;
+    const float3 plo = sw ? p1 : p0, phi = sw ? p0 : p1;
+    const bool c1 = (hi >= l1) && (lo <= l1);
+    const bool c2 = !c1 && (hi >= l2) && (lo <= l2);
+    const float lv = c1 ? l1 : l2;
+    const float dn = __fsub_rn(lv, lo), dd = __fsub_rn(hi, lo);
+    const bool s_lo = snap(dn, thr) || (!snap(__fsub_rn(lv, hi), thr) && snap(dd, thr));
+    const bool s_hi = !snap(dn, thr) && snap(__fsub_rn(lv, hi), thr);
+    float t = __fdiv_rn(dn, dd);
+    if (!(c1 || c2)) t = (hi == lo && plo.z == 0.0f) ? 1.f : 0.f;
+    float3 r = lerp3(plo, phi, t);
+    if (c1 || c2) {
+        if (s_lo) r = plo;
+        else if (s_hi) r = phi;
+    }
+    return r;
+}
 // second half of vertexInterp3_new (:3347-3413): band on the vol_two pair when ids are {2,0}
 __device__ __forceinline__ bool interp_band_two(float thr, float m1, float m2, float3& p0, float3& p1, float f2, float f3, float& t, float3& out) {
     if (f3 < f2) { float3 tp = p1; p1 = p0; p0 = tp; float tf = f3; f3 = f2; f2 = tf; }
@@ -218,8 +240,31 @@ __device__ __forceinline__ float t_analysis(float iso, float f0, float f1, float
 
 // ---------------------------------------------------------------- stage-in: one grid point -> {value, bits}
 // bits: [1:0] id class of the mask value (0:==0, 1:==1, 2:==2, 3:other), [2] inside flag.
+// n / d for a divisor that is the same for every point: y = RN(1/d) is computed once, the quotient is q = n*y followed by two
+// remainder corrections (r = n - q*d exactly by fma, q += r*y).  With |d| in [2^-40, 2^40] this equals __fdiv_rn(n, d) bit for
+// bit for every n whose remainder cannot underflow; tiny/zero numerators, tiny/huge quotients and inf/nan take the IEEE
+// division.  Checked exhaustively (all 2^32 numerators for 118 divisors incl. all-ones mantissas): tools/div_check.cu,
+// profiles/r01_div_check.txt.
+struct UniformDiv { float d, y; bool ok; };
+__device__ __forceinline__ UniformDiv make_uniform_div(float d) {
+    UniformDiv u;
+    u.d = d;
+    u.y = __frcp_rn(d);
+    u.ok = fabsf(d) >= 0x1p-40f && fabsf(d) <= 0x1p40f;
+    return u;
+}
+__device__ __forceinline__ float div_by_uniform(float n, const UniformDiv& u) {
+    const float q0 = __fmul_rn(n, u.y);
+    const float r0 = __fmaf_rn(-q0, u.d, n);
+    const float q1 = __fmaf_rn(r0, u.y, q0);
+    const float r1 = __fmaf_rn(-q1, u.d, n);
+    const float q2 = __fmaf_rn(r1, u.y, q1);
+    if (!(u.ok && fabsf(n) >= 1.0e-30f && fabsf(q2) >= 1.0e-30f && fabsf(q2) <= 1.0e30f)) return __fdiv_rn(n, u.d);
+    return q2;
+}
+
 template <int MODE>
-__device__ __forceinline__ void stage_point(const McArgs& A, size_t gi, uint32_t x, bool row_face, float raw, float& val, uint32_t& bits) {
+__device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& nd, size_t gi, uint32_t x, bool row_face, float raw, float& val, uint32_t& bits) {
     if (MODE == M_LATTICE_ONE || MODE == M_LATTICE) {
         const float m = __ldg(A.f1 + gi);  // mask `vol`; classifyVoxel_new :3232-3239
         uint32_t id = (m == 1.f) ? 1u : (m == 0.f) ? 0u : (m == 2.f) ? 2u : 3u;
@@ -227,7 +272,7 @@ __device__ __forceinline__ void stage_point(const McArgs& A, size_t gi, uint32_t
         val = raw;  // k `vol_one`
     } else if (MODE == M_BAND_RAW) {
         // device_bufferfour (Gratings.cu:1089-1134) fused; domain faces use GLOBAL coordinates
-        float k = __fdiv_rn(__fsub_rn(raw, A.na), __fsub_rn(A.nb, A.na));
+        float k = div_by_uniform(__fsub_rn(raw, A.na), nd);
         float m;
         if (row_face || x == 0 || x == A.nx - 1) { m = 0.0f; k = 0.0f; }
         else m = ((k >= A.iso1) && (k <= A.iso2)) ? 1.0f : 0.0f;
@@ -286,7 +331,9 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
         const uint32_t za = (ca >> 2) & 1u, zb = (cb >> 2) & 1u;
         const float fa = (za ? S.val[1] : S.val[0])[sa], fb = (zb ? S.val[1] : S.val[0])[sb];
         w[k] = 0.f;
-        if (MODE == M_LATTICE_ONE || MODE == M_BAND_RAW) {
+        if (MODE == M_BAND_RAW) {
+            v[k] = interp_band_crossing(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb);
+        } else if (MODE == M_LATTICE_ONE) {
             v[k] = interp_band(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb, ((za ? S.bit[1] : S.bit[0])[sa] & 3u), ((zb ? S.bit[1] : S.bit[0])[sb] & 3u));
         } else if (MODE == M_LATTICE) {
             const uint32_t ida = ((za ? S.bit[1] : S.bit[0])[sa] & 3u), idb = ((zb ? S.bit[1] : S.bit[0])[sb] & 3u);
@@ -385,6 +432,7 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
 
     uint32_t parity = 0;
     const uint32_t slice_pts = A.nx * A.ny;
+    const UniformDiv nd = make_uniform_div(__fsub_rn(A.nb, A.na));  // M_BAND_RAW normalisation range
 
     for (;;) {
         if (tid == 0) *S.tile_id = atomicAdd(A.tile_counter, 1u);
@@ -428,7 +476,7 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                         for (int u = 0; u < 4; ++u) {
                             float val;
                             uint32_t bits;
-                            stage_point<MODE>(A, gs + pnt + u, x + u, row_face, vv[u], val, bits);
+                            stage_point<MODE>(A, nd, gs + pnt + u, x + u, row_face, vv[u], val, bits);
                             vv[u] = val;
                             packed |= bits << (8 * u);
                         }
@@ -444,7 +492,7 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                     else raw = A.f0 ? __ldg(A.f0 + gs + pnt) : 0.f;
                     float val;
                     uint32_t bits;
-                    stage_point<MODE>(A, gs + pnt, x, row_face, raw, val, bits);
+                    stage_point<MODE>(A, nd, gs + pnt, x, row_face, raw, val, bits);
                     sv[pnt] = val;
                     sb[pnt] = (unsigned char)bits;
                 }
