@@ -380,6 +380,8 @@ int gcb_deleteTexture(gcb_ctx* ctx) {
 
 int gcb_file_write_obj(gcb_ctx* ctx, void* d_pos, unsigned int totalVerts, const char* filename) {
     CTX(ctx);
+    // default: weld, face filter and text formatting on the GPU (obj_gpu.cu); same bytes as the host restatement below
+    if (!(C->options & GCB_OPT_OBJ_HOST) && totalVerts < 0x7fffffffu) return write_obj_device(C, (const float4*)d_pos, totalVerts, filename);
     float* h = nullptr;
     if (totalVerts) {
         GCB_CHECK(C, cudaMallocHost(&h, (size_t)totalVerts * 16));

@@ -133,7 +133,8 @@ int k_topo_field(Ctx* c, const float* topo, float* isosurf, float volfrac, size_
 int k_patch_topo_field(Ctx* c, float* d, int nx, int ny, int nz, const GridPoint* vol_one);
 int k_copy_to_pitched(Ctx* c, const float* src, gcb_pitched_ptr dst, int nx, int ny, int nz);
 
-// obj_writer.cpp
+// obj_writer.cpp (host restatement, GCB_OPT_OBJ_HOST) and obj_gpu.cu (device weld + text, the default)
 int write_obj_host(const float* pos4, unsigned int total_verts, const char* filename);
+int write_obj_device(Ctx* c, const float4* pos, unsigned int total_verts, const char* filename);
 
 } // namespace gcb

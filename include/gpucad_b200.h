@@ -45,7 +45,8 @@ int gcb_set_stream(gcb_ctx* ctx, void* stream);
 enum {
     GCB_OPT_FILL_STAGE_ARRAYS = 1, /* also write d_voxelVerts/_Scan/d_voxelOccupied/_Scan (parity tests) */
     GCB_OPT_LEGACY_MEMSET = 2,     /* cudaMemset(pos/norm, 0, maxVerts BYTES) as Isosurface.cu:120-121 (default on) */
-    GCB_OPT_NO_TMA = 4             /* force the LDG stage-in path (debug / A-B measurement) */
+    GCB_OPT_NO_TMA = 4,            /* force the LDG stage-in path (debug / A-B measurement) */
+    GCB_OPT_OBJ_HOST = 8           /* gcb_file_write_obj: weld and format on one host thread (as the reference does) instead of on the GPU */
 };
 int gcb_set_options(gcb_ctx* ctx, unsigned int flags);
 /* number of kernels this library launched on the context since creation / last reset */
@@ -155,7 +156,9 @@ int gcb_copytotexture(gcb_ctx* ctx, float* d_phi, gcb_pitched_ptr data_ptr, int 
 int gcb_updateTexture(gcb_ctx* ctx, gcb_pitched_ptr data_ptr);
 int gcb_deleteTexture(gcb_ctx* ctx);
 
-/* File_output::file_write_obj (src/File_output.h:38, File_output.cu:5-81): d_pos device float4[totalVerts] */
+/* File_output::file_write_obj (src/File_output.h:38, File_output.cu:5-81): d_pos device float4[totalVerts].
+ * Same file bytes as the reference writer; the weld, the face filter and the text formatting run on the GPU
+ * (GCB_OPT_OBJ_HOST selects the single-thread host restatement). */
 int gcb_file_write_obj(gcb_ctx* ctx, void* d_pos, unsigned int totalVerts, const char* filename);
 
 /* ------------------------------------------------------------------ fused entry points (no reference twin) */

@@ -688,3 +688,61 @@ def test_large_grid_counts_and_mesh_match_reference(ctx):
     assert torch.equal(scr.compVoxelArray[:a], scr2.compVoxelArray[:a])
     assert_bits_equal(mesh.pos[:t], mesh2.pos[:t], "256^3 pos")
     assert_bits_equal(mesh.norm[:t], mesh2.norm[:t], "256^3 norm")
+
+
+# ------------------------------------------------------------------ .obj export on the GPU
+def _write_both(ctx, pos, tot, tmp_path, tag):
+    """default device writer vs the host restatement (GCB_OPT_OBJ_HOST) vs the reference writer: file bytes."""
+    dflt = _capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET
+    pd, ph = str(tmp_path / (tag + "_dev.obj")), str(tmp_path / (tag + "_host.obj"))
+    g.File_output(ctx).file_write_obj(pos, tot, pd)
+    ctx.set_options(dflt | _capi.GCB_OPT_OBJ_HOST)
+    try:
+        g.File_output(ctx).file_write_obj(pos, tot, ph)
+    finally:
+        ctx.set_options(dflt)
+    bd, bh = open(pd, "rb").read(), open(ph, "rb").read()
+    assert bd == bh, "%s: device .obj writer differs from the host writer (%d vs %d bytes)" % (tag, len(bd), len(bh))
+    if HAVE_REF:
+        pr = str(tmp_path / (tag + "_ref.obj"))
+        ref.write_obj(pos, tot, pr)
+        assert bd == open(pr, "rb").read(), "%s: device .obj writer differs from the reference writer" % tag
+    return bd
+
+
+def test_obj_device_writer_on_a_lattice_mesh(ctx, tmp_path):
+    n = 64
+    _, mask, k = _lattice_inputs(ctx, n, 0)
+    dims = (n, n, n)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    act, tot = g.Isosurface(ctx).computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), mv, k, cases.BAND_LO,
+                                                              cases.BAND_HI)
+    assert tot > 10000
+    data = _write_both(ctx, mesh.pos, tot, tmp_path, "lattice")
+    assert data.count(b"\nv ") < tot and data.count(b" f  ") <= tot // 3   # welded: far fewer vertex lines than soup vertices
+
+
+def test_obj_device_writer_adversarial_soup(ctx, tmp_path):
+    """duplicates, degenerate and repeated faces, negative/zero/-0/tiny coordinates, magnitudes across all '%g' branches
+    that int(p * 1000) can carry, values next to quantisation boundaries."""
+    rng = np.random.RandomState(11)
+    base = np.concatenate([
+        rng.uniform(-3, 3, (600, 3)),                       # ordinary
+        np.round(rng.uniform(-2, 2, (300, 3)), 3) + 1e-7,   # just above a quantisation boundary
+        np.round(rng.uniform(-2, 2, (300, 3)), 3) - 1e-7,   # just below
+        rng.uniform(-0.0009, 0.0009, (60, 3)),              # quantise to 0 (incl. negatives -> int 0 -> +0)
+        rng.uniform(900, 1100, (90, 3)), rng.uniform(-99999, 99999, (90, 3)), rng.uniform(-999999, 999999, (60, 3)),
+        rng.uniform(1.0e6, 2.0e6, (30, 3)),                 # '%g' switches to exponent form
+        np.array([[0.0, -0.0, 0.0], [0.001, 0.01, 0.1], [1, 10, 100], [1000, 10000, 100000], [0.5, 0.25, 0.125], [-0.001, -0.01, -0.1],
+                  [999.9995, 99.99995, 9.999995], [12345.678, 1234.5678, 123.45678]])]).astype(np.float32)
+    idx = rng.randint(0, len(base), 3 * 2500)
+    idx[30:33] = [5, 5, 9]            # degenerate
+    idx[60:63] = idx[0:3]             # repeated face
+    idx[90:93] = idx[[0, 2, 1]]       # same vertices, other order: a different ordered triple, kept
+    pos = np.ones((len(idx), 4), np.float32)
+    pos[:, :3] = base[idx]
+    data = _write_both(ctx, dev(pos), len(idx), tmp_path, "soup")
+    assert b"e+06" in data
+    # empty mesh
+    _write_both(ctx, dev(pos), 0, tmp_path, "empty")
