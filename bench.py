@@ -269,8 +269,8 @@ def main():
         dist.destroy_process_group()
 
 
-# measured once with `ncu --set full` on the default workload (profiles/r01_ncu_mc_fused.txt): 0.538 GB read + 5.464 GB written
-NCU_TRAFFIC_BYTES = 538399232 + 5464463000
+# measured once with `ncu --set full` on the default workload (profiles/r01_ncu_mc_fused.txt): 0.539 GB read + 5.466 GB written
+NCU_TRAFFIC_BYTES = 538731520 + 5465742000
 
 
 def cpu_baseline(nh, budget_s=12.0):
