@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" boundary of libgpucad_b200 (declared in include/gpucad_b200.h).
 #include "common.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include <cstdio>
@@ -92,6 +93,7 @@ int gcb_destroy(gcb_ctx* ctx) {
     cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef);
     cudaFree(C->d_tri); cudaFree(C->d_nverts);
     if (C->copy_stream) { cudaStreamDestroy(C->copy_stream); for (int i = 0; i < Ctx::kBatches; ++i) cudaEventDestroy(C->copy_ev[i]); }
+    if (C->aux_stream) { cudaStreamDestroy(C->aux_stream); cudaEventDestroy(C->aux_ev[0]); cudaEventDestroy(C->aux_ev[1]); }
     for (int i = 0; i < 4; ++i) if (C->ev[i]) cudaEventDestroy(C->ev[i]);
     delete C;
     return 0;
@@ -450,58 +452,83 @@ int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int 
 int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_phi_scratch, int nh, const float* coef_host, int cx, int cy, int cz_local,
                        int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_minmax) {
     CTX(ctx);
-    // The harmonics are independent terms of one running sum, so the control grids are uploaded in batches on a copy
-    // stream while the field kernel consumes the previous batch (accumulate = 1 keeps the reference's summation order:
-    // the partial sum round-trips through the fp32 field buffer unchanged).
+    // Upload / compute overlap by z-slabs of the FINE grid: a slab of fine layers needs only the control planes that bracket
+    // it, for all harmonics -- one strided copy (nh rows of `planes * cy * cx` floats) on a copy stream -- and is then evaluated
+    // for all harmonics in one launch, so every tile pays its staging prologue once and the running sum never round-trips
+    // through memory (an earlier version split the HARMONICS into batches instead: 8 launches over the whole volume, 8
+    // prologues per tile and an accumulate pass each).  Thin slabs first: the first kernel starts after a short copy.
     if (!C->copy_stream) {
         GCB_CHECK(C, cudaStreamCreateWithFlags(&C->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < Ctx::kBatches; ++i) GCB_CHECK(C, cudaEventCreateWithFlags(&C->copy_ev[i], cudaEventDisableTiming));
     }
-    const size_t per = (size_t)cx * cy * cz_local;
-    int nb = nh < Ctx::kBatches ? (nh > 0 ? nh : 1) : Ctx::kBatches;
+    if (!C->aux_stream) {
+        GCB_CHECK(C, cudaStreamCreateWithFlags(&C->aux_stream, cudaStreamNonBlocking));
+        GCB_CHECK(C, cudaEventCreateWithFlags(&C->aux_ev[0], cudaEventDisableTiming));
+        GCB_CHECK(C, cudaEventCreateWithFlags(&C->aux_ev[1], cudaEventDisableTiming));
+    }
+    if (nh <= 0 || NZ2_local <= 0) return gcb_svl_field(ctx, d_svl, d_phi_scratch, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, NZ2_local, slab, dx, dy, dz, 0, d_minmax);
+    const size_t plane = (size_t)cx * cy, per = plane * cz_local;
+    // slab thicknesses (fine layers, multiples of 8): 8, 8, 16, then ~1/14 of the grid each
+    int f_start[Ctx::kBatches + 1];
+    int nb = 0;
+    {
+        const int big = std::max(8, ((NZ2_local / 14) + 7) & ~7);
+        int f = 0;
+        const int lead[3] = {8, 8, 16};
+        while (f < NZ2_local && nb < Ctx::kBatches) {
+            f_start[nb] = f;
+            const int left = Ctx::kBatches - nb;
+            int t = nb < 3 ? std::min(lead[nb], big) : big;
+            if (left == 1) t = NZ2_local - f;
+            f = std::min(NZ2_local, f + t);
+            ++nb;
+        }
+        f_start[nb] = NZ2_local;
+    }
     // order the copy stream after everything already queued on the compute stream (the scratch may still be in use)
     GCB_CHECK(C, cudaEventRecord(C->copy_ev[0], C->stream));
     GCB_CHECK(C, cudaStreamWaitEvent(C->copy_stream, C->copy_ev[0], 0));
-    int start[Ctx::kBatches + 1];
-    if (const char* sched = getenv("GCB_SVL_BATCHES")) {  // experiment: explicit batch sizes "2,4,8,..." (remainder goes to the last batch)
-        int b = 0, h0 = 0;
-        for (const char* q = sched; *q && b < Ctx::kBatches - 1 && h0 < nh; ++b) {
-            start[b] = h0;
-            h0 = std::min(nh, h0 + std::max(1, atoi(q)));
-            while (*q && *q != ',') ++q;
-            if (*q == ',') ++q;
-        }
-        if (h0 < nh) { start[b++] = h0; }
-        nb = b;
-    } else {
-        // small batches first (the first kernel can start after a short copy), doubling up to ~nh/6, the rest split evenly:
-        // with the field kernel slower than the copy, the step then costs first copy + sum of kernels
-        int h0 = 0, b = 0;
-        for (int sz = 1; b < nb / 2 && sz * 6 <= nh; sz *= 2, ++b) { start[b] = h0; h0 += sz; }
-        for (; b < nb; ++b) { start[b] = h0; h0 += (nh - h0) / (nb - b); }
-    }
-    start[nb] = nh;
+    int copied = 0;  // local control planes [0, copied) are already queued
     for (int b = 0; b < nb; ++b) {
-        const size_t off = (size_t)start[b] * per, cnt = (size_t)(start[b + 1] - start[b]) * per;
-        if (cnt) GCB_CHECK(C, cudaMemcpyAsync(d_phi_scratch + off, h_phi + off, cnt * sizeof(float), cudaMemcpyHostToDevice, C->copy_stream));
+        // control planes bracketing fine layers [f_start[b], f_start[b+1]) (+1 plane of slack against rounding in generic ratios)
+        const double zhi = ((double)f_start[b + 1] - 1.0 + (double)slab.z0) * (double)dz;
+        int p_hi = (int)floor(zhi) + 2 - cz0;
+        p_hi = std::min(std::max(p_hi, 0), cz_local - 1);
+        if (b == nb - 1) p_hi = cz_local - 1;
+        if (p_hi + 1 > copied) {
+            const size_t off = (size_t)copied * plane, width = (size_t)(p_hi + 1 - copied) * plane * sizeof(float);
+            GCB_CHECK(C, cudaMemcpy2DAsync(d_phi_scratch + off, per * sizeof(float), h_phi + off, per * sizeof(float), width, (size_t)nh, cudaMemcpyHostToDevice,
+                                           C->copy_stream));
+            copied = p_hi + 1;
+        }
         GCB_CHECK(C, cudaEventRecord(C->copy_ev[b], C->copy_stream));
     }
     if (d_minmax) if (int r = k_minmax_init(C, C->d_minmax)) return r;
     if (C->timing) cudaEventRecord(C->ev[2], C->stream);
-    static const bool trace = getenv("GCB_TRACE") != nullptr;  // debugging aid: per-batch timeline on stderr
+    static const bool trace = getenv("GCB_TRACE") != nullptr;  // debugging aid: per-slab timeline on stderr
     cudaEvent_t tev[Ctx::kBatches + 1];
     if (trace) { for (int b = 0; b <= nb; ++b) cudaEventCreate(&tev[b]); cudaEventRecord(tev[0], C->stream); }
+    // slabs alternate between the context's stream and a second one: they write disjoint layers (min/max goes through atomics),
+    // so the last, partly filled wave of one launch overlaps the first waves of the next
+    GCB_CHECK(C, cudaEventRecord(C->aux_ev[0], C->stream));              // min/max init precedes the aux launches
+    GCB_CHECK(C, cudaStreamWaitEvent(C->aux_stream, C->aux_ev[0], 0));
+    cudaStream_t main_stream = C->stream;
     for (int b = 0; b < nb; ++b) {
-        GCB_CHECK(C, cudaStreamWaitEvent(C->stream, C->copy_ev[b], 0));
-        const bool last = b == nb - 1;
-        if (int r = k_svl_field(C, d_svl, d_phi_scratch + (size_t)start[b] * per, start[b + 1] - start[b], coef_host + 2 * start[b], cx, cy, cz_local, cz0, NX2,
-                                NY2, NZ2_local, slab.z0, dx, dy, dz, b > 0, (last && d_minmax) ? C->d_minmax : nullptr))
-            return r;
-        if (trace) cudaEventRecord(tev[b + 1], C->stream);
+        cudaStream_t st = (b & 1) ? C->aux_stream : main_stream;
+        GCB_CHECK(C, cudaStreamWaitEvent(st, C->copy_ev[b], 0));
+        const int f0 = f_start[b], f1 = f_start[b + 1];
+        C->stream = st;
+        const int r = k_svl_field(C, d_svl + (size_t)f0 * NX2 * NY2, d_phi_scratch, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, f1 - f0, slab.z0 + (unsigned)f0, dx,
+                                  dy, dz, 0, d_minmax ? C->d_minmax : nullptr);
+        C->stream = main_stream;
+        if (r) return r;
+        if (trace) cudaEventRecord(tev[b + 1], st);
     }
+    GCB_CHECK(C, cudaEventRecord(C->aux_ev[1], C->aux_stream));
+    GCB_CHECK(C, cudaStreamWaitEvent(C->stream, C->aux_ev[1], 0));
     if (trace) {
         cudaStreamSynchronize(C->stream);
-        for (int b = 0; b < nb; ++b) { float ms; cudaEventElapsedTime(&ms, tev[0], tev[b + 1]); fprintf(stderr, "[gcb trace] batch %d (%d harmonics) done at %.3f ms\n", b, start[b + 1] - start[b], ms); }
+        for (int b = 0; b < nb; ++b) { float ms; cudaEventElapsedTime(&ms, tev[0], tev[b + 1]); fprintf(stderr, "[gcb trace] slab %d (fine layers %d..%d) done at %.3f ms\n", b, f_start[b], f_start[b + 1], ms); }
         for (int b = 0; b <= nb; ++b) cudaEventDestroy(tev[b]);
     }
     if (C->timing) { cudaEventRecord(C->ev[3], C->stream); C->field_timed = true; }

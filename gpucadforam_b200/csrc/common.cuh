@@ -87,8 +87,10 @@ struct Ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool extract_timed = false, field_timed = false;
     // host-input pipeline: control grids uploaded in batches on a copy stream, overlapped with the field kernel
-    static constexpr int kBatches = 8;
+    static constexpr int kBatches = 20;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;   // second compute stream of the slab-overlapped host path (tail of slab k overlaps head of k+1)
+    cudaEvent_t aux_ev[2] = {};
     cudaEvent_t copy_ev[kBatches] = {};
 };
 
