@@ -85,6 +85,7 @@ SIGNATURES = {
     "gcb_updateTexture": (I, [P, PitchedPtr]),
     "gcb_deleteTexture": (I, [P]),
     "gcb_file_write_obj": (I, [P, P, U, C.c_char_p]),
+    "gcb_unit_lattice_spectrum": (I, [P, P, I, I, I, I, P]),
     "gcb_svl_field": (I, [P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, I, P]),
     "gcb_svl_field_host": (I, [P, P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, P]),
     "gcb_minmax": (I, [P, P, C.c_size_t, PF, PF]),

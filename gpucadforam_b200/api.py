@@ -278,6 +278,14 @@ class Gratings:
         return PitchedPtr(buf.data_ptr(), nx * 4, nx * 4, ny)
 
 
+def unit_lattice_spectrum(ctx, d_unit_cell, Nxu, Nyu, Nzu, range_st=2):
+    """lattice_data of Multitopo::unit_lattice (main.cu:3577-3706): complex64 tensor [(2*range_st+1)^3] on the device."""
+    side = 2 * range_st + 1
+    out = torch.zeros(side ** 3, 2, dtype=torch.float32, device=d_unit_cell.device)
+    ctx.check(lib().gcb_unit_lattice_spectrum(ctx._h, _ptr(d_unit_cell), Nxu, Nyu, Nzu, range_st, _ptr(out)))
+    return torch.view_as_complex(out)
+
+
 class File_output:
     def __init__(self, ctx):
         self.ctx = ctx

@@ -310,6 +310,10 @@ int gcb_create_lattice(gcb_ctx* ctx, float* d, unsigned int NX, unsigned int NY,
     (void)size;
     SYNC_RET(k_create_lattice(C, d, NX, NY, NZ, type));
 }
+int gcb_unit_lattice_spectrum(gcb_ctx* ctx, const float* d_unit_cell, int Nxu, int Nyu, int Nzu, int range_st, void* d_lattice_data) {
+    CTX(ctx);
+    SYNC_RET(k_unit_spectrum(C, d_unit_cell, Nxu, Nyu, Nzu, range_st, (float2*)d_lattice_data));
+}
 int gcb_GPU_buffer_normalise_buffer(gcb_ctx* ctx, float* d_vec1, float* d_vec2, int n) {
     CTX(ctx);
     float a, b;

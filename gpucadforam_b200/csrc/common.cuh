@@ -109,6 +109,7 @@ int upload_tables_legacy(Ctx* c);
 
 // fields.cu
 int k_create_lattice(Ctx* c, float* out, unsigned nx, unsigned ny, unsigned nz, unsigned type);
+int k_unit_spectrum(Ctx* c, const float* f, int nx, int ny, int nz, int range, float2* out);
 int k_sphere(Ctx* c, float* out, float3 center, float radius, float thickness, int nx, int ny, int nz, float dx, float dy, float dz, bool shell);
 int k_line(Ctx* c, float* out, float3 center, float3 axis, float radius, float tr, float ta, int nx, int ny, int nz, float dx, float dy, float dz, bool disc);
 int k_cuboid(Ctx* c, float* out, float3 center, float3 ang, float xw, float yw, float zw, int nx, int ny, int nz, float dx, float dy, float dz);

@@ -156,6 +156,13 @@ int gcb_copytotexture(gcb_ctx* ctx, float* d_phi, gcb_pitched_ptr data_ptr, int 
 int gcb_updateTexture(gcb_ctx* ctx, gcb_pitched_ptr data_ptr);
 int gcb_deleteTexture(gcb_ctx* ctx);
 
+/* Multitopo::unit_lattice, spectrum part (src/main.cu:3577-3706 with Fft_lattice::fft_func / fft_scalar / fft_fill,
+ * src/lattice_files/Fft_lattice.cu:107-236): the (2*range_st+1)^3 lowest Fourier coefficients of the unit cell, divided by
+ * the point count, in the order k, j, i = -range_st..range_st (i fastest) -- the reference's `lattice_data` (device
+ * float2[(2*range_st+1)^3]), i.e. the c_h of the spatially varying lattice.  Evaluated directly (no FFT); agrees with the
+ * reference's cuFFT route to ~1e-6 of the largest coefficient. */
+int gcb_unit_lattice_spectrum(gcb_ctx* ctx, const float* d_unit_cell, int Nxu, int Nyu, int Nzu, int range_st, void* d_lattice_data);
+
 /* File_output::file_write_obj (src/File_output.h:38, File_output.cu:5-81): d_pos device float4[totalVerts].
  * Same file bytes as the reference writer; the weld, the face filter and the text formatting run on the GPU
  * (GCB_OPT_OBJ_HOST selects the single-thread host restatement). */

@@ -485,6 +485,38 @@ int orc_extract(const orc_mc_params* pp, uint32_t* voxel_verts, uint32_t* voxel_
     return 0;
 }
 
+
+/* Unit-cell spectrum: Multitopo::unit_lattice, main.cu:3577-3706.  The reference runs cufftExecR2C (Fft_lattice.cu:107-112),
+ * divides by the point count (fft_scalar, :128-158), fills the Hermitian half (fft_fill, :163-236) and the host picks the
+ * (2*range+1)^3 lowest frequencies in the order k, j, i = -range..range with index i mod N (main.cu:3612-3690).  cuFFT is a
+ * third-party library (CUDA toolkit); what it computes is the DFT  F(k) = sum_r f(r) exp(-2 pi I k.r/N), restated here
+ * directly in double.  out: interleaved (re, im) floats, (2*range+1)^3 entries. */
+void orc_unit_spectrum(const float* f, int NX, int NY, int NZ, int range, float* out) {
+    const int side = 2 * range + 1;
+    const double two_pi = 6.283185307179586476925286766559;
+    const double total = (double)NX * NY * NZ;
+#pragma omp parallel for schedule(dynamic)
+    for (int e = 0; e < side * side * side; ++e) {
+        const int fi = e % side - range, fj = (e / side) % side - range, fk = e / (side * side) - range;
+        std::vector<double> cx(NX), sx(NX), cy(NY), sy(NY), cz(NZ), sz(NZ);
+        for (int x = 0; x < NX; ++x) { long long m = ((long long)fi * x) % NX; if (m < 0) m += NX; cx[x] = cos(two_pi * m / NX); sx[x] = -sin(two_pi * m / NX); }
+        for (int y = 0; y < NY; ++y) { long long m = ((long long)fj * y) % NY; if (m < 0) m += NY; cy[y] = cos(two_pi * m / NY); sy[y] = -sin(two_pi * m / NY); }
+        for (int z = 0; z < NZ; ++z) { long long m = ((long long)fk * z) % NZ; if (m < 0) m += NZ; cz[z] = cos(two_pi * m / NZ); sz[z] = -sin(two_pi * m / NZ); }
+        double re = 0.0, im = 0.0;
+        for (int z = 0; z < NZ; ++z)
+            for (int y = 0; y < NY; ++y) {
+                const double yzr = cy[y] * cz[z] - sy[y] * sz[z], yzi = cy[y] * sz[z] + sy[y] * cz[z];
+                double rr = 0.0, ri = 0.0;  /* row sum over x */
+                const float* row = f + ((size_t)z * NY + y) * NX;
+                for (int x = 0; x < NX; ++x) { rr += row[x] * cx[x]; ri += row[x] * sx[x]; }
+                re += rr * yzr - ri * yzi;
+                im += rr * yzi + ri * yzr;
+            }
+        out[2 * e] = (float)(re / total);
+        out[2 * e + 1] = (float)(im / total);
+    }
+}
+
 /* ---------------- field producers ---------------- */
 
 /* create_lattice_kernel: lattice_files/Fft_lattice.cu:12-66 (3.14 literal, coordinates in double) */

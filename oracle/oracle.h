@@ -74,6 +74,8 @@ int orc_count(const orc_mc_params* p, uint64_t* active_voxels, uint64_t* total_v
 
 /* ---- field producers ---- */
 void orc_create_lattice(float* out, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t type);
+/* unit-cell spectrum (main.cu:3577-3706): (2*range+1)^3 lowest DFT coefficients / point count, order k, j, i; out = (re, im) pairs */
+void orc_unit_spectrum(const float* f, int nx, int ny, int nz, int range, float* out);
 void orc_sphere(float* out, const float center[3], float radius, float thickness,
                 int nx, int ny, int nz, float dx, float dy, float dz, int shell);
 void orc_distance_from_line(float* out, const float center[3], const float axis[3], float radius,

@@ -91,6 +91,14 @@ def create_lattice(nx, ny, nz, typ):
     return out
 
 
+def unit_spectrum(f, rng=2):
+    """f: [nz, ny, nx] float32 -> complex64 [(2*rng+1)^3] in the reference's lattice_data order."""
+    nz, ny, nx = f.shape
+    out = np.zeros(((2 * rng + 1) ** 3, 2), np.float32)
+    lib().orc_unit_spectrum(_p(np.ascontiguousarray(f, np.float32)), nx, ny, nz, rng, _p(out))
+    return out[:, 0] + 1j * out[:, 1]
+
+
 def _prim(fn, dims, d, *args):
     nx, ny, nz = dims
     out = np.zeros((nz, ny, nx), np.float32)

@@ -746,3 +746,37 @@ def test_obj_device_writer_adversarial_soup(ctx, tmp_path):
     assert b"e+06" in data
     # empty mesh
     _write_both(ctx, dev(pos), 0, tmp_path, "empty")
+
+
+# ------------------------------------------------------------------ unit-cell spectrum
+def _reference_route_spectrum(f_dev, n, rng):
+    """Multitopo::unit_lattice as the reference runs it (main.cu:3577-3690): fp32 cuFFT R2C (here through torch.fft, the same
+    library), division by the point count, Hermitian fill with index N - x, host pick in k, j, i order."""
+    F = torch.fft.rfftn(f_dev.reshape(n, n, n), dim=(0, 1, 2)) / float(n ** 3)   # [z, y, x/2+1] complex64
+    F = F.cpu().numpy()
+    out = []
+    for k in range(-rng, rng + 1):
+        for j in range(-rng, rng + 1):
+            for i in range(-rng, rng + 1):
+                if i >= 0:
+                    out.append(F[k % n, j % n, i])
+                else:  # filled from the stored half: conj(F(-i, -j, -k))
+                    out.append(np.conj(F[(-k) % n, (-j) % n, -i]))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("typ", [0, 1, 3])
+def test_unit_lattice_spectrum(ctx, typ):
+    n, rng = 61, 2   # the reference's hard-coded unit cell (main.cu:582) and indi_range = 5
+    f = torch.zeros(n ** 3, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(f, n, n, n, n ** 3, typ)
+    got = g.unit_lattice_spectrum(ctx, f, n, n, n, rng).cpu().numpy()
+    want = orc.unit_spectrum(f.cpu().numpy().reshape(n, n, n), rng)
+    scale = np.abs(want).max()
+    assert scale > 1e-3
+    # floating point path: fp64 accumulation on both sides, fp32 result -> 1e-6 of the largest coefficient
+    assert np.abs(got - want).max() <= 1e-6 * scale
+    # against the reference's own route (fp32 cuFFT): its round-off is ~1e-6..1e-5 of the largest coefficient
+    ref_route = _reference_route_spectrum(f, n, rng)
+    assert np.abs(got - ref_route).max() <= 2e-5 * scale
+    assert np.abs(got[::-1] - np.conj(got)).max() <= 1e-6 * scale   # Hermitian: entry e <-> 124 - e

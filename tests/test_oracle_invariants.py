@@ -106,3 +106,24 @@ def test_obj_writer_welds_and_flips(tmp_path):
     assert text.count("\nv ") + text.startswith("v ") == 6
     faces = [l for l in text.splitlines() if l.startswith(" f ")]
     assert faces == [" f  1 3 2", " f  2 3 4"]
+
+
+def test_unit_spectrum_matches_fft_and_is_hermitian():
+    """Unit-cell spectrum: the direct DFT of the oracle against numpy's FFT with the reference's
+    pick rule (index i mod N, order k, j, i; main.cu:3612-3690); tolerance 1e-6 of the largest coefficient."""
+    n, rng = 61, 2
+    f = orc.create_lattice(n, n, n, 0)
+    got = orc.unit_spectrum(f, rng)
+    F = np.fft.fftn(f.astype(np.float64)) / f.size          # axes (z, y, x)
+    want = np.array([F[k % n, j % n, i % n] for k in range(-rng, rng + 1) for j in range(-rng, rng + 1) for i in range(-rng, rng + 1)])
+    scale = np.abs(want).max()
+    assert scale > 1e-3
+    assert np.abs(got - want).max() <= 1e-6 * scale
+    # real input: c(-k) = conj(c(k)); entry e <-> 124 - e
+    assert np.abs(got[::-1] - np.conj(got)).max() <= 1e-6 * scale
+    # anisotropic cell exercises the per-axis moduli
+    f2 = orc.create_lattice(20, 14, 9, 1)
+    g2 = orc.unit_spectrum(f2, 1)
+    F2 = np.fft.fftn(f2.astype(np.float64)) / f2.size
+    w2 = np.array([F2[k % 9, j % 14, i % 20] for k in (-1, 0, 1) for j in (-1, 0, 1) for i in (-1, 0, 1)])
+    assert np.abs(g2 - w2).max() <= 1e-6 * np.abs(w2).max()
