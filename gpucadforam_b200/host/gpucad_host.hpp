@@ -166,6 +166,11 @@ public:
     void create_lattice(float* d_latticevol, uint NX, uint NY, uint NZ, uint size, uint lattice_type_index) {
         gpucad::check(gcb_create_lattice(gpucad::ctx(), d_latticevol, NX, NY, NZ, size, lattice_type_index), "create_lattice");
     }
+    // the spectrum part of Multitopo::unit_lattice (main.cu:3577-3706: fft_func + fft_scalar + fft_fill + host pick) in one call:
+    // d_lattice_data = device float2[(2*range_st+1)^3], the reference's `lattice_data`
+    void unit_lattice_spectrum(const float* d_unit_cell, int Nxu, int Nyu, int Nzu, int range_st, float2* d_lattice_data) {
+        gpucad::check(gcb_unit_lattice_spectrum(gpucad::ctx(), d_unit_cell, Nxu, Nyu, Nzu, range_st, d_lattice_data), "unit_lattice_spectrum");
+    }
 };
 
 class Interpolations {
