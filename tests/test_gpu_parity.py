@@ -94,14 +94,39 @@ def test_primitives(ctx, idx):
         theirs = torch.zeros_like(mine)
         ref_fn(theirs)
         nbad = int((bits(mine) != bits(theirs)).sum())
-        if name == "cone_frustum":
-            # the one primitive whose last-bit behaviour we do not reproduce (double pow() next to float powf(); ~1% of points differ
-            # where x^2+z^2 - r^2 cancels): bounded absolute error instead of bit identity
-            err = float((mine - theirs).abs().max())
-            print("cone_frustum: %d of %d words differ, max abs err %g" % (nbad, n, err))
-            assert err <= 2e-5 * scale
-        else:
-            assert nbad == 0, "primitive %s: %d of %d words differ from the reference kernel, max %d ulp" % (name, nbad, n, ulp_diff(mine, theirs))
+        assert nbad == 0, "primitive %s: %d of %d words differ from the reference kernel, max %d ulp" % (name, nbad, n, ulp_diff(mine, theirs))
+
+
+@needs_ref
+def test_rotated_primitives_general_parameters_bit_exact(ctx):
+    """Random centres, Euler angles and sizes (non-dyadic ratios such as cone height / radius): every rotated primitive must
+    reproduce the reference kernel bit for bit -- this is what pins the FMA contraction of the rotation rows and of the
+    cone / frustum tails (a cone with height/radius = 2 hides a fused multiply-subtract, 8/5 does not)."""
+    rng = np.random.RandomState(17)
+    dims, d = (24, 20, 28), (0.5, 0.5, 0.5)
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    m = g.Modelling(ctx)
+    f32 = lambda v: float(np.float32(v))
+    for _ in range(12):
+        c = tuple(f32(v) for v in rng.uniform(-2, 2, 3))
+        a = tuple(f32(v) for v in rng.uniform(-3.2, 3.2, 3))
+        s1, s2, s3, s4, s5 = (f32(v) for v in rng.uniform(2.0, 9.0, 5))
+        pairs = [
+            ("cuboid", lambda o: m.cuboid(o, c, a, s1, s2, s3, nx, ny, nz, *d), lambda o: ref.cuboid(o, c, a, s1, s2, s3, dims, d)),
+            ("cuboid_shell", lambda o: m.cuboid_shell(o, c, a, s1, s2, s3, 0.7, nx, ny, nz, *d), lambda o: ref.cuboid_shell(o, c, a, s1, s2, s3, 0.7, dims, d)),
+            ("torus", lambda o: m.torus_with_center(o, c, a, s1, s4 / 3, nx, ny, nz, *d), lambda o: ref.torus(o, c, a, s1, s4 / 3, dims, d)),
+            ("cone", lambda o: m.cone_with_base_radius_height(o, c, a, s2, s5, nx, ny, nz, *d), lambda o: ref.cone(o, c, a, s2, s5, dims, d)),
+            ("cone_frustum", lambda o: m.cone_frustum(o, c, a, s4 / 2, s2, s5, nx, ny, nz, *d), lambda o: ref.cone_frustum(o, c, a, s4 / 2, s2, s5, dims, d)),
+            ("pyramid_frustum", lambda o: m.pyramid_frustum(o, c, a, s1, s1 / 2, s5, s3, s3 / 3, nx, ny, nz, *d),
+             lambda o: ref.pyramid_frustum(o, c, a, s1, s1 / 2, s5, s3, s3 / 3, dims, d)),
+        ]
+        for name, mine_fn, ref_fn in pairs:
+            mine, theirs = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+            mine_fn(mine)
+            ref_fn(theirs)
+            nbad = int((bits(mine) != bits(theirs)).sum())
+            assert nbad == 0, "%s centre %s angles %s: %d of %d words differ from the reference kernel" % (name, c, a, nbad, n)
 
 
 @needs_ref
