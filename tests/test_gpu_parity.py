@@ -805,3 +805,51 @@ def test_unit_lattice_spectrum(ctx, typ):
     ref_route = _reference_route_spectrum(f, n, rng)
     assert np.abs(got - ref_route).max() <= 2e-5 * scale
     assert np.abs(got[::-1] - np.conj(got)).max() <= 1e-6 * scale   # Hermitian: entry e <-> 124 - e
+
+
+@needs_ref
+@pytest.mark.parametrize("mode", ["latticeone", "lattice", "csg", "topo"])
+def test_extraction_general_voxel_size_and_centre_bit_exact(ctx, mode):
+    """Non-dyadic voxel sizes and a non-zero grid centre make every position product inexact, so any difference in FMA
+    contraction between this library and the reference build (corner offsets, lerps, normals) shows up in the mesh bits."""
+    n = 40
+    dims = (n, n - 4, n + 3)
+    voxel, center = (0.37, 0.41, 0.29), (3.3, -1.7, 0.9)
+    nx, ny, nz = dims
+    npts = nx * ny * nz
+    ncell = (nx - 1) * (ny - 1) * (nz - 1)
+    mv = max_verts_for(dims)
+    rng = np.random.RandomState(23)
+    iso = g.Isosurface(ctx)
+    scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+    scr2, mesh2 = g.Scratch(ncell), g.MeshBuffers(mv)
+    zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    smooth = (np.sin(0.31 * xx + 0.2) * np.cos(0.23 * yy) + np.sin(0.19 * zz + 0.4 * np.cos(0.11 * xx))).astype(np.float32)
+    k = dev((smooth - smooth.min()) / (smooth.max() - smooth.min()))
+    if mode in ("latticeone", "lattice"):
+        mask = ((k >= cases.BAND_LO) & (k <= cases.BAND_HI)).to(torch.float32)
+        two = dev(rng.rand(npts).astype(np.float32))
+        if mode == "latticeone":
+            act, tot = iso.computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, voxel, center, mv, k, cases.BAND_LO, cases.BAND_HI)
+            a2, t2 = ref.isosurface_lattice(True, False, mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, voxel, center, scr2, mv, k, None, cases.BAND_LO,
+                                            cases.BAND_HI)
+        else:
+            act, tot = iso.computeIsosurface_lattice(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, voxel, center, mv, k, two, cases.BAND_LO, cases.BAND_HI,
+                                                     0.4, 0.6)
+            a2, t2 = ref.isosurface_lattice(False, False, mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, voxel, center, scr2, mv, k, two, cases.BAND_LO,
+                                            cases.BAND_HI, 0.4, 0.6)
+    elif mode == "csg":
+        vol_one = gp_zeros(npts)
+        field = dev(smooth)
+        iso.copy_parameter(0.1, dims, voxel, vol_one, field, None, obj_union=True)
+        dyn = dev(np.cos(0.27 * xx - 0.13 * zz).astype(np.float32) + 0.3)
+        act, tot, _ = iso.computeIsosurface(mesh.pos, mesh.norm, 0.1, scr, dims, voxel, center, mv, vol_one, dyn, None, obj_union=False, obj_diff=True)
+        a2, t2 = ref.isosurface_csg(False, mesh2.pos, mesh2.norm, 0.1, dims, voxel, center, scr2, mv, vol_one, dyn, None, obj_union=False, obj_diff=True)
+    else:
+        vol_topo = gp_zeros(npts)
+        result = dev(rng.rand(npts).astype(np.float32))
+        act, tot = iso.computeIsosurface_2(mesh.pos, mesh.norm, 0.45, scr, dims, voxel, center, mv, vol_topo, k, 0.0, result)
+        a2, t2 = ref.isosurface_topo(False, mesh2.pos, mesh2.norm, 0.45, dims, voxel, center, scr2, mv, vol_topo, k, 0.0, result, vol_one=vol_topo, d_solid=k)
+    assert tot > 3000 and (act, tot) == (a2, t2)
+    assert_bits_equal(mesh.pos[:tot], mesh2.pos[:tot], "%s positions, general voxel size / centre" % mode)
+    assert_bits_equal(mesh.norm[:tot], mesh2.norm[:tot], "%s normals, general voxel size / centre" % mode)
