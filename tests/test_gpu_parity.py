@@ -808,12 +808,11 @@ def test_unit_lattice_spectrum(ctx, typ):
 
 
 @needs_ref
-@pytest.mark.parametrize("mode", ["latticeone", "lattice", "csg", "topo"])
+@pytest.mark.parametrize("mode", ["latticeone", "lattice", "csg", "topo", "band_raw"])
 def test_extraction_general_voxel_size_and_centre_bit_exact(ctx, mode):
     """Non-dyadic voxel sizes and a non-zero grid centre make every position product inexact, so any difference in FMA
     contraction between this library and the reference build (corner offsets, lerps, normals) shows up in the mesh bits."""
-    n = 40
-    dims = (n, n - 4, n + 3)
+    dims = (40, 32, 48)   # 60 * 1024 points: the reference's min/max reduction is only defined for multiples of 1024 (SURVEY.md A-11)
     voxel, center = (0.37, 0.41, 0.29), (3.3, -1.7, 0.9)
     nx, ny, nz = dims
     npts = nx * ny * nz
@@ -826,7 +825,16 @@ def test_extraction_general_voxel_size_and_centre_bit_exact(ctx, mode):
     zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     smooth = (np.sin(0.31 * xx + 0.2) * np.cos(0.23 * yy) + np.sin(0.19 * zz + 0.4 * np.cos(0.11 * xx))).astype(np.float32)
     k = dev((smooth - smooth.min()) / (smooth.max() - smooth.min()))
-    if mode in ("latticeone", "lattice"):
+    if mode == "band_raw":
+        # fused normalise + band mask + extraction on the RAW field against the reference's normalise_four -> latticeone
+        raw = dev(smooth)
+        a, b = float(min(0.0, smooth.min())), float(max(0.0, smooth.max()))
+        act, tot = g.extract_band_raw(ctx, raw, a, b, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, voxel, center, mesh.pos, mesh.norm, mv)
+        mask_r, k_r = torch.zeros(npts, device="cuda"), torch.zeros(npts, device="cuda")
+        ref.normalise_four(raw, mask_r, k_r, dims, cases.BAND_LO, cases.BAND_HI)
+        a2, t2 = ref.isosurface_lattice(True, False, mask_r, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, voxel, center, scr2, mv, k_r, None, cases.BAND_LO,
+                                        cases.BAND_HI)
+    elif mode in ("latticeone", "lattice"):
         mask = ((k >= cases.BAND_LO) & (k <= cases.BAND_HI)).to(torch.float32)
         two = dev(rng.rand(npts).astype(np.float32))
         if mode == "latticeone":
