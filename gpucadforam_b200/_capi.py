@@ -86,6 +86,9 @@ SIGNATURES = {
     "gcb_deleteTexture": (I, [P]),
     "gcb_file_write_obj": (I, [P, P, U, C.c_char_p]),
     "gcb_unit_lattice_spectrum": (I, [P, P, I, I, I, I, P]),
+    "gcb_finding_phi": (I, [P, P, P, I, I, I, I, I, I, F, F, F, C.c_char, I, F, F, F, F, F, F, I]),
+    "gcb_GPUCG_lattice": (I, [P, P, I, I, I, I, I, F, C.POINTER(I), PF]),
+    "gcb_svl_phase_solve": (I, [P, P, P, I, C.POINTER(I), I, I, I, F, F, F, C.c_char, I, F, F, F, F, F, F, I, I, F, C.POINTER(I), PF]),
     "gcb_svl_field": (I, [P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, I, P]),
     "gcb_svl_field_host": (I, [P, P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, P]),
     "gcb_minmax": (I, [P, P, C.c_size_t, PF, PF]),

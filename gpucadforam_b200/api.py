@@ -278,6 +278,31 @@ class Gratings:
         return PitchedPtr(buf.data_ptr(), nx * 4, nx * 4, ny)
 
 
+def finding_phi(ctx, d_phi, d_period, dims, ijk, d, latticetype="r", uniform_type=2, const_period=8.0, periods=(8.0, 8.0, 8.0), lcon=0.5, lcon_1=0.05,
+                sinewave_zaxis=False):
+    """Gratings::finding_phi for one harmonic (i, j, k) (Gratings.cu:1015-1025)."""
+    ctx.check(lib().gcb_finding_phi(ctx._h, _ptr(d_phi), _ptr(d_period), dims[0], dims[1], dims[2], ijk[0], ijk[1], ijk[2], d[0], d[1], d[2],
+                                    latticetype.encode(), uniform_type, const_period, periods[0], periods[1], periods[2], lcon, lcon_1, int(sinewave_zaxis)))
+
+
+def GPUCG_lattice(ctx, d_phi, dims, iters=500, end_res=0.01):
+    """Gratings::GPUCG_lattice (Gratings.cu:875-974): d_phi holds the right-hand side on entry, the solution on return."""
+    fi, fr = C.c_int(0), C.c_float(0)
+    ctx.check(lib().gcb_GPUCG_lattice(ctx._h, _ptr(d_phi), dims[0], dims[1], dims[2], iters, 1, end_res, C.byref(fi), C.byref(fr)))
+    return fi.value, fr.value
+
+
+def svl_phase_solve(ctx, d_phi_all, d_period, harmonics, dims, d, latticetype="r", uniform_type=2, const_period=8.0, periods=(8.0, 8.0, 8.0), lcon=0.5,
+                    lcon_1=0.05, sinewave_zaxis=False, iters=500, end_res=0.01):
+    """All harmonics at once: right-hand sides + batched CG.  Returns (FinalIter list, FinalRes list)."""
+    nh = len(harmonics)
+    flat = (C.c_int * (3 * nh))(*[int(v) for h in harmonics for v in h])
+    fi, fr = (C.c_int * nh)(), (C.c_float * nh)()
+    ctx.check(lib().gcb_svl_phase_solve(ctx._h, _ptr(d_phi_all), _ptr(d_period), nh, flat, dims[0], dims[1], dims[2], d[0], d[1], d[2], latticetype.encode(),
+                                        uniform_type, const_period, periods[0], periods[1], periods[2], lcon, lcon_1, int(sinewave_zaxis), iters, end_res, fi, fr))
+    return list(fi), list(fr)
+
+
 def unit_lattice_spectrum(ctx, d_unit_cell, Nxu, Nyu, Nzu, range_st=2):
     """lattice_data of Multitopo::unit_lattice (main.cu:3577-3706): complex64 tensor [(2*range_st+1)^3] on the device."""
     side = 2 * range_st + 1

@@ -401,6 +401,30 @@ int gcb_file_write_obj(gcb_ctx* ctx, void* d_pos, unsigned int totalVerts, const
     return 0;
 }
 
+// ------------------------------------------------------------------ SVL phase solve
+int gcb_finding_phi(gcb_ctx* ctx, float* d_phi, float* d_period, int x_dim, int y_dim, int z_dim, int i, int j, int k, float dx, float dy, float dz,
+                    char latticetype_one, int unform_type, float const_peirod, float x_period, float y_period, float z_period, float lcon, float lcon_1,
+                    int sinewave_zaxis) {
+    CTX(ctx);
+    const int ijk[3] = {i, j, k};
+    return k_finding_phi(C, d_phi, d_period, ijk, 1, x_dim, y_dim, z_dim, dx, dy, dz, latticetype_one, unform_type, const_peirod, x_period, y_period, z_period, lcon,
+                         lcon_1, sinewave_zaxis);
+}
+int gcb_GPUCG_lattice(gcb_ctx* ctx, float* d_phi, int NX, int NY, int NZ, int iter, int OptIter, float EndRes, int* FinalIter, float* FinalRes) {
+    CTX(ctx);
+    (void)OptIter;
+    return k_cg_batched(C, d_phi, 1, NX, NY, NZ, iter, EndRes, FinalIter, FinalRes);
+}
+int gcb_svl_phase_solve(gcb_ctx* ctx, float* d_phi_all, float* d_period, int nharm, const int* ijk, int x_dim, int y_dim, int z_dim, float dx, float dy, float dz,
+                        char latticetype_one, int unform_type, float const_peirod, float x_period, float y_period, float z_period, float lcon, float lcon_1,
+                        int sinewave_zaxis, int iter, float EndRes, int* FinalIter, float* FinalRes) {
+    CTX(ctx);
+    if (int r = k_finding_phi(C, d_phi_all, d_period, ijk, nharm, x_dim, y_dim, z_dim, dx, dy, dz, latticetype_one, unform_type, const_peirod, x_period, y_period,
+                              z_period, lcon, lcon_1, sinewave_zaxis))
+        return r;
+    return k_cg_batched(C, d_phi_all, nharm, x_dim, y_dim, z_dim, iter, EndRes, FinalIter, FinalRes);
+}
+
 // ------------------------------------------------------------------ fused entry points
 int gcb_svl_field(gcb_ctx* ctx, float* d_svl, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz_local, int cz0, int NX2, int NY2,
                   int NZ2_local, gcb_slab slab, float dx, float dy, float dz, int accumulate, float* d_minmax) {

@@ -136,6 +136,11 @@ int k_topo_field(Ctx* c, const float* topo, float* isosurf, float volfrac, size_
 int k_patch_topo_field(Ctx* c, float* d, int nx, int ny, int nz, const GridPoint* vol_one);
 int k_copy_to_pitched(Ctx* c, const float* src, gcb_pitched_ptr dst, int nx, int ny, int nz);
 
+// phase_solve.cu
+int k_finding_phi(Ctx* c, float* phi_all, const float* period, const int* ijk_host, int nharm, int nx, int ny, int nz, float dx, float dy, float dz, int latticetype,
+                  int uniform_type, float const_period, float x_period, float y_period, float z_period, float lcon, float lcon_1, int sinewave_zaxis);
+int k_cg_batched(Ctx* c, float* phi_all, int nharm, int nx, int ny, int nz, int iter, float end_res, int* final_iter, float* final_res);
+
 // obj_writer.cpp (host restatement, GCB_OPT_OBJ_HOST) and obj_gpu.cu (device weld + text, the default)
 int write_obj_host(const float* pos4, unsigned int total_verts, const char* filename);
 int write_obj_device(Ctx* c, const float4* pos, unsigned int total_verts, const char* filename);

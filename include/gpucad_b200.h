@@ -163,6 +163,22 @@ int gcb_deleteTexture(gcb_ctx* ctx);
  * reference's cuFFT route to ~1e-6 of the largest coefficient. */
 int gcb_unit_lattice_spectrum(gcb_ctx* ctx, const float* d_unit_cell, int Nxu, int Nyu, int Nzu, int range_st, void* d_lattice_data);
 
+/* ---- SVL phase solve.  Gratings::finding_phi (src/lattice_files/Gratings.h:40-41, Gratings.cu:100-417, :1015-1025)
+ * and Gratings::GPUCG_lattice (Gratings.h:43, Gratings.cu:875-974; NX/NY/NZ are members there, arguments here) as
+ * Multitopo::spatial_lattice_run calls them per harmonic (main.cu:3959-3962).  Same arithmetic, bit for bit (expression
+ * contraction and reduction trees of the reference build); the CG scalars stay on the device, the host polls a counter.
+ * FinalIter / FinalRes as the reference returns them. */
+int gcb_finding_phi(gcb_ctx* ctx, float* d_phi, float* d_period, int x_dim, int y_dim, int z_dim, int i, int j, int k, float dx, float dy, float dz,
+                    char latticetype_one, int unform_type, float const_peirod, float x_period, float y_period, float z_period, float lcon, float lcon_1,
+                    int sinewave_zaxis);
+int gcb_GPUCG_lattice(gcb_ctx* ctx, float* d_phi, int NX, int NY, int NZ, int iter, int OptIter, float EndRes, int* FinalIter, float* FinalRes);
+/* fused: right-hand sides and CG of ALL harmonics at once.  d_phi_all: device float[nharm][z][y][x] (output), ijk: host int[3*nharm]
+ * (the (i, j, k) of each harmonic), FinalIter / FinalRes: host arrays [nharm] (may be NULL).  Every harmonic performs exactly
+ * the iterations the per-harmonic reference loop would, so each grid equals gcb_finding_phi + gcb_GPUCG_lattice bit for bit. */
+int gcb_svl_phase_solve(gcb_ctx* ctx, float* d_phi_all, float* d_period, int nharm, const int* ijk, int x_dim, int y_dim, int z_dim, float dx, float dy, float dz,
+                        char latticetype_one, int unform_type, float const_peirod, float x_period, float y_period, float z_period, float lcon, float lcon_1,
+                        int sinewave_zaxis, int iter, float EndRes, int* FinalIter, float* FinalRes);
+
 /* File_output::file_write_obj (src/File_output.h:38, File_output.cu:5-81): d_pos device float4[totalVerts].
  * Same file bytes as the reference writer; the weld, the face filter and the text formatting run on the GPU
  * (GCB_OPT_OBJ_HOST selects the single-thread host restatement). */

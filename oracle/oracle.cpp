@@ -517,6 +517,133 @@ void orc_unit_spectrum(const float* f, int NX, int NY, int NZ, int range, float*
     }
 }
 
+
+/* ---------------- SVL phase solve ----------------
+ * finding_phi_kernel (lattice_files/Gratings.cu:100-417) and GPUCG_lattice (:875-974) with GPUMatvec_lattice_kernel (:420-597),
+ * GPUScalar_lattice_kernel + Reduction_lattice (:600-650, :22-74) and VecSMultAddKernel_lattice (:77-98).
+ * FMA contraction as the reference build carries it (checked against its kernels on the GPU): a*u + b*v = fma(b, v, a*u);
+ * axpy = fma(V, a1, a2*W); matvec = fma(phi1, x1+y1+z1, x2) followed by the remaining terms in source order.  The reductions
+ * reproduce the reference's trees, so given the same right-hand side the CG is bit-identical to the GPU kernels (only +,*,/);
+ * finding_phi itself goes through the host libm (atan2f/sinf/cosf) and is compared with a tolerance. */
+static inline void orc_dt_weights(int v, int n, float& a1, float& a2, int& v1, int& v2) {
+    if (v == 0) { a1 = -1; a2 = -0.5f; v1 = v; v2 = v + 1; }
+    else if (v == 1) { a1 = 1; a2 = -0.5f; v1 = v - 1; v2 = v + 1; }
+    else if (v == n - 2) { a1 = 0.5f; a2 = -1.0f; v1 = v - 1; v2 = v + 1; }
+    else if (v == n - 1) { a1 = 0.5f; a2 = 1; v1 = v - 1; v2 = v; }
+    else { a1 = 0.5f; a2 = -0.5f; v1 = v - 1; v2 = v + 1; }
+}
+static inline float orc_k_scaled(float per, float inner) { return (float)((6.283185307179586 / (double)per) * (double)inner); }
+static inline float orc_pair(float a, float u, float b, float v) { return fmaf(b, v, a * u); }
+void orc_finding_phi(float* phi, const float* period, int nx, int ny, int nz, int fi_, int fj_, int fk_, float dx, float dy, float dz, int latticetype,
+                     int uniform_type, float const_period, float x_period, float y_period, float z_period, float lcon, float lcon_1, int sinewave_zaxis) {
+    (void)dy;
+    const float fi = (float)fi_, fj = (float)fj_, fk = (float)fk_;
+#pragma omp parallel for schedule(static)
+    for (int tx = 0; tx < nx * ny * nz; ++tx) {
+        const int x = tx % nx, y = (tx % (nx * ny)) / nx, z = tx / (nx * ny);
+        float a1, a2, b1, b2, c1, c2;
+        int x1, x2, y1, y2, z1, z2;
+        orc_dt_weights(x, nx, a1, a2, x1, x2);
+        orc_dt_weights(y, ny, b1, b2, y1, y2);
+        orc_dt_weights(z, nz, c1, c2, z1, z2);
+        float t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0, t8 = 0;
+        if (latticetype == 'r' || latticetype == 'b') {
+            float mx = 0.f, my = 0.f;
+            if (latticetype == 'r') { mx = (nx + 1) / 2.0f; my = (ny + 1) / 2.0f; }
+            const float yy = ((y + 1) - my) * dx;
+            t1 = atan2f(yy, ((x1 + 1) - mx) * dx);
+            t2 = atan2f(yy, ((x2 + 1) - mx) * dx);
+            const float xx = ((x + 1) - mx) * dx;
+            t3 = atan2f(((y1 + 1) - my) * dx, xx);
+            t4 = atan2f(((y2 + 1) - my) * dx, xx);
+        } else if (latticetype == 's') {
+            auto th = [&](float c) { return lcon * sinf((float)(6.28 * lcon_1 * c)); };
+            t1 = th((x1 + 1) * dx); t5 = th((z1 + 1) * dz); t2 = th((x2 + 1) * dx); t6 = th((z2 + 1) * dz);
+            t3 = t4 = th((x + 1) * dx); t7 = t8 = th((z + 1) * dz);
+        }
+        float p1, p2, p3, p4, p5, p6;
+        if (uniform_type == 0) p1 = p2 = p3 = p4 = p5 = p6 = const_period;
+        else if (uniform_type == 1) { p1 = p2 = x_period; p3 = p4 = y_period; p5 = p6 = z_period; }
+        else {
+            const int sl = nx * ny;
+            p1 = period[x1 + y * nx + z * sl]; p2 = period[x2 + y * nx + z * sl];
+            p3 = period[x + y1 * nx + z * sl]; p4 = period[x + y2 * nx + z * sl];
+            p5 = period[x + y * nx + z1 * sl]; p6 = period[x + y * nx + z2 * sl];
+        }
+        auto rx = [&](float t) { return fmaf(-fj, sinf(t), fi * cosf(t)); };
+        auto ry = [&](float t) { return fmaf(fj, cosf(t), fi * sinf(t)); };
+        float kx1 = orc_k_scaled(p1, rx(t1)), kx2 = orc_k_scaled(p2, rx(t2)), ky1 = orc_k_scaled(p3, ry(t3)), ky2 = orc_k_scaled(p4, ry(t4));
+        float kz1 = (float)((6.283185307179586 / (double)p5) * (double)fk_), kz2 = (float)((6.283185307179586 / (double)p6) * (double)fk_);
+        float ph = (orc_pair(a1, kx1, a2, kx2) + orc_pair(b1, ky1, b2, ky2)) + orc_pair(c1, kz1, c2, kz2);
+        if (latticetype == 's' && sinewave_zaxis) {
+            kz1 = orc_k_scaled(p5, fmaf(fk, cosf(t5), fj * sinf(t5)));
+            kz2 = orc_k_scaled(p6, fmaf(fk, cosf(t6), fj * sinf(t6)));
+            ky1 = orc_k_scaled(p3, fmaf(-fk, sinf(t7), fj * cosf(t7)));
+            ky2 = orc_k_scaled(p4, fmaf(-fk, sinf(t8), fj * cosf(t8)));
+            kx1 = (float)((6.283185307179586 / (double)p1) * (double)fi_);
+            kx2 = (float)((6.283185307179586 / (double)p2) * (double)fi_);
+            ph = ph + ((orc_pair(a1, kx1, a2, kx2) + orc_pair(b1, ky1, b2, ky2)) + orc_pair(c1, kz1, c2, kz2));
+        }
+        phi[tx] = ph;
+    }
+}
+/* <a, b> with the reference's two-level tree: per 1024-element block a shared-memory halving tree, then Reduction_lattice */
+static float orc_dot_tree(const float* a, const float* b, int n) {
+    const int block_num = (n + 1023) / 1024;
+    std::vector<float> partial(block_num);
+#pragma omp parallel for schedule(static)
+    for (int blk = 0; blk < block_num; ++blk) {
+        float cc[1024];
+        for (int t = 0; t < 1024; ++t) { const int i = blk * 1024 + t; cc[t] = i < n ? a[i] * b[i] : 0.0f; }
+        for (int s = 512; s > 0; s >>= 1) for (int t = 0; t < s; ++t) cc[t] = cc[t] + cc[t + s];
+        partial[blk] = cc[0];
+    }
+    float cc[1024];
+    for (int t = 0; t < 1024; ++t) { float c = 0.0f; for (int i = t; i < block_num; i += 1024) c = c + partial[i]; cc[t] = c; }
+    for (int s = 512; s > 0; s >>= 1) for (int t = 0; t < s; ++t) cc[t] = cc[t] + cc[t + s];
+    return cc[0];
+}
+static inline void orc_stencil_axis(const float* d, int tx, int v, int n, int st, float& diag, float& t2, float& t3) {
+    if (v == 0) { diag = 1.25f; t2 = -d[tx + st]; t3 = d[tx + 2 * st] * -0.25f; }
+    else if (v == 1) { diag = 1.25f; t2 = -d[tx - st]; t3 = d[tx + 2 * st] * -0.25f; }
+    else if (v == n - 2) { diag = 1.25f; t2 = d[tx - 2 * st] * -0.25f; t3 = -d[tx + st]; }
+    else if (v == n - 1) { diag = 1.25f; t2 = d[tx - 2 * st] * -0.25f; t3 = -d[tx - st]; }
+    else { diag = 0.5f; t2 = d[tx - 2 * st] * -0.25f; t3 = d[tx + 2 * st] * -0.25f; }
+}
+void orc_cg(float* phi, int nx, int ny, int nz, int iter, float end_res, int* final_iter, float* final_res) {
+    const int n = nx * ny * nz;
+    std::vector<float> d(phi, phi + n), res(phi, phi + n), q(n, 0.0f);
+    std::fill(phi, phi + n, 0.0f);
+    float delta_new = orc_dot_tree(res.data(), d.data(), n);
+    const float term = end_res * end_res;
+    int counter = 1;
+    while (counter < iter && delta_new > term) {
+#pragma omp parallel for schedule(static)
+        for (int tx = 0; tx < n; ++tx) {
+            const int x = tx % nx, y = (tx % (nx * ny)) / nx, z = tx / (nx * ny);
+            float x1, x2, x3, y1, y2, y3, z1, z2, z3;
+            orc_stencil_axis(d.data(), tx, x, nx, 1, x1, x2, x3);
+            orc_stencil_axis(d.data(), tx, y, ny, nx, y1, y2, y3);
+            orc_stencil_axis(d.data(), tx, z, nz, nx * ny, z1, z2, z3);
+            float a = fmaf(d[tx], (x1 + y1) + z1, x2);
+            a = a + x3; a = a + y2; a = a + y3; a = a + z2; a = a + z3;
+            q[tx] = a;
+        }
+        const float temp = orc_dot_tree(d.data(), q.data(), n);
+        const float alpha = delta_new / temp, nalpha = (float)(-1.0 * (double)alpha);
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; ++i) { phi[i] = fmaf(phi[i], 1.0f, alpha * d[i]); res[i] = fmaf(res[i], 1.0f, nalpha * q[i]); }
+        const float delta_old = delta_new;
+        delta_new = orc_dot_tree(res.data(), res.data(), n);
+        const float beta = delta_new / delta_old;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; ++i) d[i] = fmaf(d[i], beta, 1.0f * res[i]);
+        ++counter;
+    }
+    if (final_iter) *final_iter = counter;
+    if (final_res) *final_res = sqrtf(delta_new);
+}
+
 /* ---------------- field producers ---------------- */
 
 /* create_lattice_kernel: lattice_files/Fft_lattice.cu:12-66 (3.14 literal, coordinates in double) */

@@ -74,6 +74,10 @@ int orc_count(const orc_mc_params* p, uint64_t* active_voxels, uint64_t* total_v
 
 /* ---- field producers ---- */
 void orc_create_lattice(float* out, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t type);
+/* SVL phase solve (Gratings.cu:100-417, :875-974): right-hand side of one harmonic; CG in place (rhs in, solution out) */
+void orc_finding_phi(float* phi, const float* period, int nx, int ny, int nz, int i, int j, int k, float dx, float dy, float dz, int latticetype,
+                     int uniform_type, float const_period, float x_period, float y_period, float z_period, float lcon, float lcon_1, int sinewave_zaxis);
+void orc_cg(float* phi, int nx, int ny, int nz, int iter, float end_res, int* final_iter, float* final_res);
 /* unit-cell spectrum (main.cu:3577-3706): (2*range+1)^3 lowest DFT coefficients / point count, order k, j, i; out = (re, im) pairs */
 void orc_unit_spectrum(const float* f, int nx, int ny, int nz, int range, float* out);
 void orc_sphere(float* out, const float center[3], float radius, float thickness,

@@ -300,4 +300,28 @@ int ref_write_obj(float4* d_pos, uint totalVerts, const char* filename) {
     return last_error("file_write_obj");
 }
 
+
+/* ---- SVL phase solve: Gratings::period_data + GPU_buffer_normalise_three, finding_phi, GPUCG_lattice as
+ * Multitopo::spatial_lattice_run calls them (main.cu:3927-3962) */
+int ref_period_data(float* d_period, int nx, int ny, int nz, float dx, float dy, float dz, float mx, float my, float mz, int axis) {
+    g_lat->period_data(d_period, nx, ny, nz, dx, dy, dz, mx, my, mz, (char)axis);
+    return last_error("period_data");
+}
+int ref_normalise_three(float* d_in, float* d_out, size_t size, float a1, float b1) {
+    g_lat->GPU_buffer_normalise_three(d_in, d_out, size, a1, b1);
+    return last_error("normalise_three");
+}
+int ref_finding_phi(float* d_phi, float* d_period, int nx, int ny, int nz, int i, int j, int k, float dx, float dy, float dz, int latticetype, int uniform_type,
+                    float const_period, float x_period, float y_period, float z_period, float lcon, float lcon_1, int sinewave_zaxis) {
+    g_lat->finding_phi(d_phi, d_period, nx, ny, nz, i, j, k, dx, dy, dz, (char)latticetype, uniform_type, const_period, x_period, y_period, z_period, lcon, lcon_1,
+                       sinewave_zaxis != 0);
+    return last_error("finding_phi");
+}
+int ref_cg(float* d_phi, int nx, int ny, int nz, int iter, float end_res, int* final_iter, float* final_res) {
+    g_lat->NX = nx; g_lat->NY = ny; g_lat->NZ = nz;   /* main.cu:4182-4184 */
+    int fi = 0; float fr = 0.f;
+    g_lat->GPUCG_lattice(d_phi, iter, 1, end_res, fi, fr);
+    *final_iter = fi; *final_res = fr;
+    return last_error("GPUCG_lattice");
+}
 } // extern "C"

@@ -41,3 +41,13 @@ def topo_coarse(cfg):
     from gpucadforam_b200 import synth
     cx, cy, cz = cfg["cdims"]
     return synth.cantilever_density(cx, cy, cz, struts=12, sigma=1.0).numpy()
+
+
+# SVL phase solve (f-2) in miniature: control grid 16x12x8, reference defaults latticetype 'r' / period_type 2 (main.cu:3959-3962)
+PHASE = dict(dims=(16, 12, 8), d=(1.0, 1.0, 1.0), harmonics=[(1, 0, 0), (0, 1, 0), (1, -2, 1), (-2, 1, 2)], iters=500, end_res=0.01)
+
+
+def phase_period(cfg):
+    nx, ny, nz = cfg["dims"]
+    rng = np.random.RandomState(41)
+    return rng.uniform(3.0, 7.0, nx * ny * nz).astype(np.float32)

@@ -130,6 +130,27 @@ def main(out):
                         **pack(scr, mesh, dims, a, t))
     print("topo", a, t)
 
+    # ---- SVL phase solve (f-2): right-hand sides and CG solutions of the reference kernels
+    P = cases.PHASE
+    per = cases.phase_period(P)
+    dper = dev(per)
+    npts = P["dims"][0] * P["dims"][1] * P["dims"][2]
+    ph = {}
+    for lt, ut in (("r", 2), ("b", 0), ("n", 1), ("s", 2)):
+        for hi, h in enumerate(P["harmonics"]):
+            b = torch.zeros(npts, device="cuda")
+            ref.finding_phi(b, dper, P["dims"], h, P["d"], latticetype=lt, uniform_type=ut, const_period=7.3, periods=(6.1, 7.7, 5.3), lcon=0.45, lcon_1=0.07,
+                            sinewave_zaxis=(lt == "s"))
+            ph["rhs_%s%d_%d" % (lt, ut, hi)] = b.cpu().numpy()
+            if lt == "r":
+                x = b.clone()
+                fi, fr = ref.cg(x, P["dims"], P["iters"], P["end_res"])
+                ph["sol_%d" % hi] = x.cpu().numpy()
+                ph["iters_%d" % hi] = np.int32(fi)
+                ph["res_%d" % hi] = np.float32(fr)
+    np.savez_compressed(os.path.join(out, "phase_solve.npz"), period=per, **ph)
+    print("phase_solve", [int(ph["iters_%d" % i]) for i in range(len(P["harmonics"]))])
+
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE))

@@ -91,6 +91,24 @@ def create_lattice(nx, ny, nz, typ):
     return out
 
 
+def finding_phi(period, dims, ijk, d, latticetype="r", uniform_type=2, const_period=8.0, periods=(8.0, 8.0, 8.0), lcon=0.5, lcon_1=0.05, sinewave_zaxis=False):
+    nx, ny, nz = dims
+    out = np.zeros(nx * ny * nz, np.float32)
+    per = None if period is None else np.ascontiguousarray(period, np.float32)
+    lib().orc_finding_phi(_p(out), _p(per), nx, ny, nz, int(ijk[0]), int(ijk[1]), int(ijk[2]), C.c_float(d[0]), C.c_float(d[1]), C.c_float(d[2]), ord(latticetype),
+                          uniform_type, C.c_float(const_period), C.c_float(periods[0]), C.c_float(periods[1]), C.c_float(periods[2]), C.c_float(lcon),
+                          C.c_float(lcon_1), int(sinewave_zaxis))
+    return out
+
+
+def cg(rhs, dims, iters=500, end_res=0.01):
+    """returns (solution, FinalIter, FinalRes)"""
+    x = np.ascontiguousarray(rhs, np.float32).copy()
+    fi, fr = C.c_int(0), C.c_float(0)
+    lib().orc_cg(_p(x), dims[0], dims[1], dims[2], iters, C.c_float(end_res), C.byref(fi), C.byref(fr))
+    return x, fi.value, fr.value
+
+
 def unit_spectrum(f, rng=2):
     """f: [nz, ny, nx] float32 -> complex64 [(2*rng+1)^3] in the reference's lattice_data order."""
     nz, ny, nx = f.shape

@@ -173,3 +173,23 @@ def isosurface_topo(with_disp_variant, pos, norm, iso, dims, voxel, center, s, m
 
 def write_obj(pos, total_verts, filename):
     _ok(lib().ref_write_obj(_p(pos), C.c_uint(total_verts), filename.encode()))
+
+
+# ---- SVL phase solve
+def period_data(d_period, dims, d, mean, axis="z"):
+    _ok(lib().ref_period_data(_p(d_period), dims[0], dims[1], dims[2], F(d[0]), F(d[1]), F(d[2]), F(mean[0]), F(mean[1]), F(mean[2]), ord(axis)))
+
+
+def normalise_three(d_in, d_out, size, a1, b1):
+    _ok(lib().ref_normalise_three(_p(d_in), _p(d_out), C.c_size_t(size), F(a1), F(b1)))
+
+
+def finding_phi(d_phi, d_period, dims, ijk, d, latticetype="r", uniform_type=2, const_period=8.0, periods=(8.0, 8.0, 8.0), lcon=0.5, lcon_1=0.05, sinewave_zaxis=False):
+    _ok(lib().ref_finding_phi(_p(d_phi), _p(d_period), dims[0], dims[1], dims[2], ijk[0], ijk[1], ijk[2], F(d[0]), F(d[1]), F(d[2]), ord(latticetype), uniform_type,
+                              F(const_period), F(periods[0]), F(periods[1]), F(periods[2]), F(lcon), F(lcon_1), int(sinewave_zaxis)))
+
+
+def cg(d_phi, dims, iters=500, end_res=0.01):
+    fi, fr = C.c_int(0), C.c_float(0)
+    _ok(lib().ref_cg(_p(d_phi), dims[0], dims[1], dims[2], iters, F(end_res), C.byref(fi), C.byref(fr)))
+    return fi.value, fr.value

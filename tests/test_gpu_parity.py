@@ -861,3 +861,56 @@ def test_extraction_general_voxel_size_and_centre_bit_exact(ctx, mode):
     assert tot > 3000 and (act, tot) == (a2, t2)
     assert_bits_equal(mesh.pos[:tot], mesh2.pos[:tot], "%s positions, general voxel size / centre" % mode)
     assert_bits_equal(mesh.norm[:tot], mesh2.norm[:tot], "%s normals, general voxel size / centre" % mode)
+
+
+# ------------------------------------------------------------------ SVL phase solve
+@needs_ref
+@pytest.mark.parametrize("lt,ut,sine", [("r", 2, False), ("b", 0, False), ("n", 1, False), ("s", 2, False), ("s", 2, True), ("r", 0, False), ("b", 2, False)])
+def test_finding_phi_matches_reference_bits(ctx, lt, ut, sine):
+    P = cases.PHASE
+    dims, d = P["dims"], P["d"]
+    n = dims[0] * dims[1] * dims[2]
+    per = dev(cases.phase_period(P))
+    kw = dict(latticetype=lt, uniform_type=ut, const_period=7.3, periods=(6.1, 7.7, 5.3), lcon=0.45, lcon_1=0.07, sinewave_zaxis=sine)
+    for h in P["harmonics"] + [(2, 2, -1), (0, 0, 1)]:
+        mine, theirs = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        g.finding_phi(ctx, mine, per, dims, h, d, **kw)
+        ref.finding_phi(theirs, per, dims, h, d, **kw)
+        assert_bits_equal(mine, theirs, "finding_phi %s/%d harmonic %s" % (lt, ut, h))
+        # the CPU oracle goes through the host libm (atan2f / sinf / cosf): tolerance, 1e-5 of the largest entry
+        o = orc.finding_phi(cases.phase_period(P), dims, h, d, **kw)
+        assert np.abs(mine.cpu().numpy() - o).max() <= 1e-5 * max(1.0, float(np.abs(o).max()))
+
+
+@needs_ref
+def test_phase_solve_cg_bit_exact_single_and_batched(ctx):
+    """GPUCG_lattice: same iterates as the reference's host-driven loop, bit for bit -- solution, iteration count and final
+    residual -- for the legacy per-harmonic call and for the batched all-harmonics solve; the oracle agrees bit for bit too."""
+    dims, d = (32, 32, 16), (1.0, 1.0, 1.0)
+    n = dims[0] * dims[1] * dims[2]
+    rng = np.random.RandomState(9)
+    per = dev(rng.uniform(3.0, 8.0, n).astype(np.float32))
+    harm = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, -2, 1), (-2, 1, 2), (2, 2, -1), (0, 0, 0)]   # (0,0,0): zero right-hand side, 1 "iteration"
+    batched = torch.zeros(len(harm), n, device="cuda")
+    fi_b, fr_b = g.svl_phase_solve(ctx, batched, per, harm, dims, d, latticetype="r", uniform_type=2, iters=500, end_res=0.01)
+    for hi, h in enumerate(harm):
+        rhs = torch.zeros(n, device="cuda")
+        ref.finding_phi(rhs, per, dims, h, d, latticetype="r", uniform_type=2)
+        theirs, mine = rhs.clone(), rhs.clone()
+        fi_r, fr_r = ref.cg(theirs, dims, 500, 0.01)
+        fi_m, fr_m = g.GPUCG_lattice(ctx, mine, dims, 500, 0.01)
+        assert (fi_m, fr_m) == (fi_r, fr_r) and (fi_b[hi], fr_b[hi]) == (fi_r, fr_r), "iterations / residual of harmonic %s" % (h,)
+        assert_bits_equal(mine, theirs, "CG solution %s (per-harmonic call)" % (h,))
+        assert_bits_equal(batched[hi], theirs, "CG solution %s (batched)" % (h,))
+        xo, fi_o, fr_o = orc.cg(rhs.cpu().numpy(), dims, 500, 0.01)
+        assert fi_o == fi_r and np.float32(fr_o) == np.float32(fr_r)
+        assert np.array_equal(xo.view(np.uint32), theirs.cpu().numpy().view(np.uint32)), "oracle CG %s" % (h,)
+    # iteration cap: every harmonic stops after exactly `iters - 1` updates like the reference
+    capped = rhs_all = torch.zeros(2, n, device="cuda")
+    fi_c, _ = g.svl_phase_solve(ctx, capped, per, harm[:2], dims, d, latticetype="r", uniform_type=2, iters=7, end_res=1e-9)
+    for hi, h in enumerate(harm[:2]):
+        theirs = torch.zeros(n, device="cuda")
+        ref.finding_phi(theirs, per, dims, h, d, latticetype="r", uniform_type=2)
+        fi_r, _ = ref.cg(theirs, dims, 7, 1e-9)
+        assert fi_c[hi] == fi_r == 7
+        assert_bits_equal(capped[hi], theirs, "capped CG %s" % (h,))

@@ -109,3 +109,24 @@ def test_topo_matches_reference():
     gp = np.ascontiguousarray(gd["vol_topo"]).view(orc.GP_DTYPE).reshape(-1)
     o = orc.extract(orc.MODE_TOPO, T["fdims"], T["d"], (0, 0, 0), T["iso"], f0=gd["density"], f1=gd["result"], gp=gp, iso1=0.0)
     check_mesh(o, gd, "topo")
+
+
+def test_phase_solve_against_reference_kernels():
+    """SVL phase solve: right-hand sides of the reference's finding_phi kernel (tolerance: host libm vs
+    libdevice atan2f/sinf/cosf) and its CG -- the oracle's CG on the reference's right-hand side must reproduce the reference's
+    solution, iteration count and residual bit for bit (only +, *, / and the reduction trees are involved)."""
+    G = np.load(os.path.join(GOLD, "phase_solve.npz"))
+    P = cases.PHASE
+    dims, d = P["dims"], P["d"]
+    per = G["period"]
+    assert np.array_equal(per, cases.phase_period(P))
+    for lt, ut in (("r", 2), ("b", 0), ("n", 1), ("s", 2)):
+        for hi, h in enumerate(P["harmonics"]):
+            want = G["rhs_%s%d_%d" % (lt, ut, hi)]
+            got = orc.finding_phi(per, dims, h, d, latticetype=lt, uniform_type=ut, const_period=7.3, periods=(6.1, 7.7, 5.3), lcon=0.45, lcon_1=0.07,
+                                  sinewave_zaxis=(lt == "s"))
+            assert np.abs(got - want).max() <= 1e-5 * max(1.0, float(np.abs(want).max())), "finding_phi %s/%d %s" % (lt, ut, h)
+    for hi, h in enumerate(P["harmonics"]):
+        x, fi, fr = orc.cg(G["rhs_r2_%d" % hi], dims, P["iters"], P["end_res"])
+        assert fi == int(G["iters_%d" % hi]) and np.float32(fr) == G["res_%d" % hi]
+        assert np.array_equal(x.view(np.uint32), G["sol_%d" % hi].view(np.uint32)), "CG solution of harmonic %s" % (h,)
