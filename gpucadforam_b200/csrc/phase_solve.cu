@@ -122,15 +122,29 @@ __global__ void __launch_bounds__(256) finding_phi_kernel(float* __restrict__ ph
 // Per-harmonic state on the device.  `run` is 1 while the reference's `while (iCounter < iter && delta_new > term)` holds.
 struct CgState { float delta_new, delta_old, temp, alpha, beta, res_best; int counter, run; };
 
-__device__ __forceinline__ float block_tree_sum_1024(float c, float* cc) {  // GPUScalar_lattice_kernel :620-650, blockDim.x = 1024
+// The reference reduces 1024 values with a shared-memory halving tree (GPUScalar_lattice_kernel :620-650: strides 512 ... 1, ten
+// barriers).  The same additions, in the same association, with ONE barrier: after the strides 512 ... 32 element t (< 32) holds
+// the tree sum of {c[t + 32 k]}, k paired as (k, k+16), (k, k+8), ..., which lane t of the first warp can form by itself from
+// 32 conflict-free loads; the strides 16 ... 1 are shuffles.  Valid in lane 0 of warp 0 (returned to every lane of warp 0; other
+// warps get an unspecified value).
+__device__ __forceinline__ float block_tree_sum_1024(float c, float* cc) {
     const int tx = threadIdx.x;
     cc[tx] = c;
     __syncthreads();
-    for (int stride = 512; stride > 0; stride >>= 1) {
-        if (tx < stride) cc[tx] = __fadd_rn(cc[tx], cc[tx + stride]);
-        __syncthreads();
+    float r = 0.0f;
+    if (tx < 32) {
+        float a[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) a[k] = cc[tx + 32 * k];
+#pragma unroll
+        for (int half = 16; half > 0; half >>= 1)
+#pragma unroll
+            for (int k = 0; k < half; ++k) a[k] = __fadd_rn(a[k], a[k + half]);
+        r = a[0];
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1) r = __fadd_rn(r, __shfl_down_sync(0xffffffffu, r, s2));
     }
-    return cc[0];
+    return r;
 }
 // Reduction_lattice (:22-74) on one harmonic's block partials: thread t sums partial[t], partial[t+1024], ... in order, then the tree
 __device__ __forceinline__ float second_level_sum(const float* partial, int block_num, float* cc) {
@@ -182,7 +196,7 @@ __global__ void __launch_bounds__(1024) cg_init_reduce_kernel(const float* __res
 }
 // stage 1: q = A d, partial <d, q>
 __global__ void __launch_bounds__(1024) cg_matvec_kernel(const float* __restrict__ d_all, float* __restrict__ q_all, float* __restrict__ partial, const CgState* __restrict__ st,
-                                                         int nx, int ny, int nz, int block_num) {
+                                                         int nx, int ny, int nz, int block_num, const Grid3 g3) {
     __shared__ float cc[1024];
     const int h = blockIdx.y;
     if (!st[h].run) return;
@@ -190,7 +204,8 @@ __global__ void __launch_bounds__(1024) cg_matvec_kernel(const float* __restrict
     const float* d = d_all + (size_t)h * n;
     float c = 0.0f;
     if (tx < n) {
-        const int x = tx % nx, y = (tx % (nx * ny)) / nx, z = tx / (nx * ny);
+        int x, y, z;
+        point_xyz((size_t)tx, g3, x, y, z);   // multiply-shift instead of two integer divisions per point
         const float phi1 = d[tx];
         float x1, x2, x3, y1, y2, y3, z1, z2, z3;
         stencil_axis(d, tx, x, nx, 1, x1, x2, x3);
@@ -313,6 +328,7 @@ int k_cg_batched(Ctx* c, float* phi_all, int nharm, int nx, int ny, int nz, int 
     CG_CHECK(cudaMalloc(&running, sizeof(int)));
     cudaStream_t s = c->stream;
     const dim3 grid(block_num, nharm);
+    const Grid3 g3 = make_grid3((size_t)nx, (size_t)ny, (size_t)nz);
     cg_init_kernel<<<grid, 1024, 0, s>>>(phi_all, d_d, d_res, partial, (int)n, block_num);
     cg_init_reduce_kernel<<<nharm, 1024, 0, s>>>(partial, block_num, st, iter, term);
     cg_count_running_kernel<<<1, 1, 0, s>>>(st, nharm, running);
@@ -321,7 +337,7 @@ int k_cg_batched(Ctx* c, float* phi_all, int nharm, int nx, int ny, int nz, int 
     const int poll = 8;  // iterations between two looks at the "still running" counter
     for (int it = 1; it < iter && h_running > 0; it += poll) {
         for (int k = 0; k < poll && it + k < iter; ++k) {
-            cg_matvec_kernel<<<grid, 1024, 0, s>>>(d_d, d_q, partial, st, nx, ny, nz, block_num);
+            cg_matvec_kernel<<<grid, 1024, 0, s>>>(d_d, d_q, partial, st, nx, ny, nz, block_num, g3);
             cg_alpha_kernel<<<nharm, 1024, 0, s>>>(partial, block_num, st);
             cg_update_kernel<<<grid, 1024, 0, s>>>(phi_all, d_res, d_d, d_q, partial, st, (int)n, block_num);
             cg_beta_kernel<<<nharm, 1024, 0, s>>>(partial, block_num, st, iter, term, running);
