@@ -220,6 +220,126 @@ __global__ void __launch_bounds__(1024) cg_matvec_kernel(const float* __restrict
     const float s = block_tree_sum_1024(c, cc);
     if (threadIdx.x == 0) partial[(size_t)h * block_num + blockIdx.x] = s;
 }
+
+// ---- float4 variants (nx % 4 == 0): a block is 256 threads x 4 consecutive points = the same 1024-point range, so the block
+// partial goes through the same tree; a thread loads its row segment and the neighbouring segments as float4 (7 vector loads per
+// 4 points in the interior instead of 13 scalar loads per point)
+__device__ __forceinline__ float block_tree_sum_1024_from4(const float c[4], float* cc) {
+    *reinterpret_cast<float4*>(cc + 4 * threadIdx.x) = make_float4(c[0], c[1], c[2], c[3]);
+    __syncthreads();
+    float r = 0.0f;
+    if (threadIdx.x < 32) {
+        float a[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) a[k] = cc[threadIdx.x + 32 * k];
+#pragma unroll
+        for (int half = 16; half > 0; half >>= 1)
+#pragma unroll
+            for (int k = 0; k < half; ++k) a[k] = __fadd_rn(a[k], a[k + half]);
+        r = a[0];
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1) r = __fadd_rn(r, __shfl_down_sync(0xffffffffu, r, s2));
+    }
+    return r;
+}
+// the two off-diagonal terms of one axis for a whole float4 segment: which neighbour rows and which coefficients (Gratings.cu:
+// 440-579); sa/sb = signed row offsets in units of `stride`
+__device__ __forceinline__ void axis_case(int v, int n, int& oa, int& ob, bool& nega, bool& negb, float& diag) {
+    if (v == 0) { oa = 1; ob = 2; nega = true; negb = false; diag = 1.25f; }
+    else if (v == 1) { oa = -1; ob = 2; nega = true; negb = false; diag = 1.25f; }
+    else if (v == n - 2) { oa = -2; ob = 1; nega = false; negb = true; diag = 1.25f; }
+    else if (v == n - 1) { oa = -2; ob = -1; nega = false; negb = true; diag = 1.25f; }
+    else { oa = -2; ob = 2; nega = false; negb = false; diag = 0.5f; }
+}
+__device__ __forceinline__ float off_term(float p, bool neg) { return neg ? -p : __fmul_rn(p, -0.25f); }
+
+__global__ void __launch_bounds__(256) cg_matvec4_kernel(const float* __restrict__ d_all, float* __restrict__ q_all, float* __restrict__ partial,
+                                                         const CgState* __restrict__ st, int nx, int ny, int nz, int block_num, const Grid3 g3) {
+    __shared__ __align__(16) float cc[1024];
+    const int h = blockIdx.y;
+    if (!st[h].run) return;
+    const int n = nx * ny * nz, e0 = blockIdx.x * 1024 + threadIdx.x * 4;
+    const float* d = d_all + (size_t)h * n;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e0 < n) {
+        int x0, y, z;
+        point_xyz((size_t)e0, g3, x0, y, z);
+        const float4 own = *reinterpret_cast<const float4*>(d + e0);
+        const float4 lf = x0 >= 4 ? *reinterpret_cast<const float4*>(d + e0 - 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 rt = x0 + 4 < nx ? *reinterpret_cast<const float4*>(d + e0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float w[12] = {lf.x, lf.y, lf.z, lf.w, own.x, own.y, own.z, own.w, rt.x, rt.y, rt.z, rt.w};
+        int oa, ob;
+        bool nega, negb;
+        float y1, z1;
+        axis_case(y, ny, oa, ob, nega, negb, y1);
+        const float4 ya = *reinterpret_cast<const float4*>(d + e0 + oa * nx), yb = *reinterpret_cast<const float4*>(d + e0 + ob * nx);
+        const float y2[4] = {off_term(ya.x, nega), off_term(ya.y, nega), off_term(ya.z, nega), off_term(ya.w, nega)};
+        const float y3[4] = {off_term(yb.x, negb), off_term(yb.y, negb), off_term(yb.z, negb), off_term(yb.w, negb)};
+        const int sl = nx * ny;
+        axis_case(z, nz, oa, ob, nega, negb, z1);
+        const float4 za = *reinterpret_cast<const float4*>(d + e0 + oa * sl), zb = *reinterpret_cast<const float4*>(d + e0 + ob * sl);
+        const float z2[4] = {off_term(za.x, nega), off_term(za.y, nega), off_term(za.z, nega), off_term(za.w, nega)};
+        const float z3[4] = {off_term(zb.x, negb), off_term(zb.y, negb), off_term(zb.z, negb), off_term(zb.w, negb)};
+        float q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + j;
+            int xa, xb;
+            bool nxa, nxb;
+            float x1;
+            axis_case(x, nx, xa, xb, nxa, nxb, x1);
+            const float x2 = off_term(w[4 + j + xa], nxa), x3 = off_term(w[4 + j + xb], nxb);
+            const float phi1 = w[4 + j];
+            // reference SASS: FADD, FADD, FFMA(phi1, s, x2), then five FADDs in source order
+            float a = __fmaf_rn(phi1, __fadd_rn(__fadd_rn(x1, y1), z1), x2);
+            a = __fadd_rn(a, x3); a = __fadd_rn(a, y2[j]); a = __fadd_rn(a, y3[j]); a = __fadd_rn(a, z2[j]); a = __fadd_rn(a, z3[j]);
+            q[j] = a;
+            c[j] = __fmul_rn(phi1, a);
+        }
+        *reinterpret_cast<float4*>(q_all + (size_t)h * n + e0) = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    const float s = block_tree_sum_1024_from4(c, cc);
+    if (threadIdx.x == 0) partial[(size_t)h * block_num + blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) cg_update4_kernel(float* __restrict__ phi_all, float* __restrict__ res_all, const float* __restrict__ d_all,
+                                                         const float* __restrict__ q_all, float* __restrict__ partial, const CgState* __restrict__ st, int n, int block_num) {
+    __shared__ __align__(16) float cc[1024];
+    const int h = blockIdx.y;
+    if (!st[h].run) return;
+    const int e0 = blockIdx.x * 1024 + threadIdx.x * 4;
+    const float alpha = st[h].alpha, nalpha = (float)(-1.0 * (double)alpha);
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e0 < n) {
+        const size_t o = (size_t)h * n + e0;
+        const float4 p = *reinterpret_cast<const float4*>(phi_all + o), r = *reinterpret_cast<const float4*>(res_all + o);
+        const float4 dd = *reinterpret_cast<const float4*>(d_all + o), qq = *reinterpret_cast<const float4*>(q_all + o);
+        const float pv[4] = {p.x, p.y, p.z, p.w}, rv[4] = {r.x, r.y, r.z, r.w}, dv[4] = {dd.x, dd.y, dd.z, dd.w}, qv[4] = {qq.x, qq.y, qq.z, qq.w};
+        float po[4], ro[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            po[j] = __fmaf_rn(pv[j], 1.0f, __fmul_rn(alpha, dv[j]));
+            ro[j] = __fmaf_rn(rv[j], 1.0f, __fmul_rn(nalpha, qv[j]));
+            c[j] = __fmul_rn(ro[j], ro[j]);
+        }
+        *reinterpret_cast<float4*>(phi_all + o) = make_float4(po[0], po[1], po[2], po[3]);
+        *reinterpret_cast<float4*>(res_all + o) = make_float4(ro[0], ro[1], ro[2], ro[3]);
+    }
+    const float s = block_tree_sum_1024_from4(c, cc);
+    if (threadIdx.x == 0) partial[(size_t)h * block_num + blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) cg_direction4_kernel(float* __restrict__ d_all, const float* __restrict__ res_all, const CgState* __restrict__ st, int n) {
+    const int h = blockIdx.y;
+    if (!st[h].run) return;
+    const int e0 = blockIdx.x * 1024 + threadIdx.x * 4;
+    const float beta = st[h].beta;
+    if (e0 < n) {
+        const size_t o = (size_t)h * n + e0;
+        const float4 dd = *reinterpret_cast<const float4*>(d_all + o), r = *reinterpret_cast<const float4*>(res_all + o);
+        *reinterpret_cast<float4*>(d_all + o) = make_float4(__fmaf_rn(dd.x, beta, __fmul_rn(1.0f, r.x)), __fmaf_rn(dd.y, beta, __fmul_rn(1.0f, r.y)),
+                                                            __fmaf_rn(dd.z, beta, __fmul_rn(1.0f, r.z)), __fmaf_rn(dd.w, beta, __fmul_rn(1.0f, r.w)));
+    }
+}
+
 // stage 2: temp = <d, q>, alpha = delta_new / temp
 __global__ void __launch_bounds__(1024) cg_alpha_kernel(const float* __restrict__ partial, int block_num, CgState* st) {
     __shared__ float cc[1024];
@@ -329,6 +449,7 @@ int k_cg_batched(Ctx* c, float* phi_all, int nharm, int nx, int ny, int nz, int 
     cudaStream_t s = c->stream;
     const dim3 grid(block_num, nharm);
     const Grid3 g3 = make_grid3((size_t)nx, (size_t)ny, (size_t)nz);
+    const bool vec4 = (nx % 4 == 0) && (((uintptr_t)phi_all & 15) == 0) && g3.small;  // rows are whole float4 groups
     cg_init_kernel<<<grid, 1024, 0, s>>>(phi_all, d_d, d_res, partial, (int)n, block_num);
     cg_init_reduce_kernel<<<nharm, 1024, 0, s>>>(partial, block_num, st, iter, term);
     cg_count_running_kernel<<<1, 1, 0, s>>>(st, nharm, running);
@@ -337,11 +458,14 @@ int k_cg_batched(Ctx* c, float* phi_all, int nharm, int nx, int ny, int nz, int 
     const int poll = 8;  // iterations between two looks at the "still running" counter
     for (int it = 1; it < iter && h_running > 0; it += poll) {
         for (int k = 0; k < poll && it + k < iter; ++k) {
-            cg_matvec_kernel<<<grid, 1024, 0, s>>>(d_d, d_q, partial, st, nx, ny, nz, block_num, g3);
+            if (vec4) cg_matvec4_kernel<<<grid, 256, 0, s>>>(d_d, d_q, partial, st, nx, ny, nz, block_num, g3);
+            else cg_matvec_kernel<<<grid, 1024, 0, s>>>(d_d, d_q, partial, st, nx, ny, nz, block_num, g3);
             cg_alpha_kernel<<<nharm, 1024, 0, s>>>(partial, block_num, st);
-            cg_update_kernel<<<grid, 1024, 0, s>>>(phi_all, d_res, d_d, d_q, partial, st, (int)n, block_num);
+            if (vec4) cg_update4_kernel<<<grid, 256, 0, s>>>(phi_all, d_res, d_d, d_q, partial, st, (int)n, block_num);
+            else cg_update_kernel<<<grid, 1024, 0, s>>>(phi_all, d_res, d_d, d_q, partial, st, (int)n, block_num);
             cg_beta_kernel<<<nharm, 1024, 0, s>>>(partial, block_num, st, iter, term, running);
-            cg_direction_kernel<<<grid, 1024, 0, s>>>(d_d, d_res, st, (int)n, iter, term, running);
+            if (vec4) cg_direction4_kernel<<<grid, 256, 0, s>>>(d_d, d_res, st, (int)n);
+            else cg_direction_kernel<<<grid, 1024, 0, s>>>(d_d, d_res, st, (int)n, iter, term, running);
             cg_advance_kernel<<<(nharm + 63) / 64, 64, 0, s>>>(st, nharm, iter, term, running);
             c->launches += 6;
         }

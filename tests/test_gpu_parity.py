@@ -883,10 +883,12 @@ def test_finding_phi_matches_reference_bits(ctx, lt, ut, sine):
 
 
 @needs_ref
-def test_phase_solve_cg_bit_exact_single_and_batched(ctx):
+@pytest.mark.parametrize("dims", [(32, 32, 16), (18, 14, 10)], ids=["float4_rows", "scalar_rows_ragged_blocks"])
+def test_phase_solve_cg_bit_exact_single_and_batched(ctx, dims):
     """GPUCG_lattice: same iterates as the reference's host-driven loop, bit for bit -- solution, iteration count and final
-    residual -- for the legacy per-harmonic call and for the batched all-harmonics solve; the oracle agrees bit for bit too."""
-    dims, d = (32, 32, 16), (1.0, 1.0, 1.0)
+    residual -- for the legacy per-harmonic call and for the batched all-harmonics solve; the oracle agrees bit for bit too.
+    (18, 14, 10): rows that are not float4 multiples (scalar kernels) and a point count that is not a multiple of 1024."""
+    d = (1.0, 1.0, 1.0)
     n = dims[0] * dims[1] * dims[2]
     rng = np.random.RandomState(9)
     per = dev(rng.uniform(3.0, 8.0, n).astype(np.float32))
