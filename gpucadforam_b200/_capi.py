@@ -54,6 +54,8 @@ SIGNATURES = {
     "gcb_tables": (None, [PU, PU]),
     "gcb_computeIsosurface": (I, [P, P, Uint3, P, P, F, U, P, P, P, P, Uint3, Uint3, Uint3, Float3, Float3, PU, PU, P, U,
                                   P, P, P, P, F, F, I, I, I, I, I, I, I, I, I, C.POINTER(C.c_size_t)]),
+    "gcb_computeIsosurface_region": (I, [P, P, P, F, U, P, P, P, P, Uint3, Uint3, Uint3, Float3, Float3, PU, PU, P, U,
+                                         P, P, P, P, P, F, F, I, I, I, I, I, I, I, I, I, I, I, P]),
     "gcb_computeIsosurface_lattice": (I, [P, P, P, P, F, U, P, P, P, P, Uint3, Uint3, Uint3, Float3, Float3, PU, PU, P, U,
                                           P, P, F, F, F, F]),
     "gcb_computeIsosurface_latticeone": (I, [P, P, P, P, F, U, P, P, P, P, Uint3, Uint3, Uint3, Float3, Float3, PU, PU, P, U,

@@ -134,6 +134,20 @@ class Isosurface:
             int(obj_intersect), 1, 0, 0, int(fixed), int(dynamic), int(make_region), C.byref(nf)))
         return act.value, tot.value, nf.value
 
+    def computeIsosurface_region(self, pos, norm, isoValue, scratch, gridSize, voxelSize, gridcenter, maxVerts, vol_topo, primitive_fixed,
+                                 primitive_dynamic, make_region=False, show_region=False, show_domain=False, triangle_data=None):
+        """Isosurface::computeIsosurface_region (Isosurface.cu:150-239).  triangle_data: device buffer of 64-byte triangle_metadata
+        records (torch tensor of shape [n, 16] int32), written when show_region is set."""
+        gs, sh, mk, nv = grid_desc(*gridSize)
+        act, tot = C.c_uint(0), C.c_uint(0)
+        s = scratch
+        self.ctx.check(lib().gcb_computeIsosurface_region(
+            self.ctx._h, _ptr(pos), _ptr(norm), isoValue, nv, _ptr(s.voxelVerts), _ptr(s.voxelVertsScan), _ptr(s.voxelOccupied), _ptr(s.voxelOccupiedScan),
+            _u3(gs), _u3(sh), _u3(mk), _f3(voxelSize), _f3(gridcenter), C.byref(act), C.byref(tot), _ptr(s.compVoxelArray), maxVerts, _ptr(vol_topo),
+            _ptr(primitive_fixed), _ptr(primitive_dynamic), None, None, 0.0, 0.0, 1, 0, 0, 1, 0, 0, 0, 0, int(make_region), int(show_region),
+            int(show_domain), _ptr(triangle_data)))
+        return act.value, tot.value
+
     def computeIsosurface_lattice(self, vol, pos, norm, isoValue, scratch, gridSize, voxelSize, gridcenter, maxVerts, vol_one, vol_two, isovalue1,
                                   isovalue2, iso1=0.0, iso2=0.0):
         gs, sh, mk, nv = grid_desc(*gridSize)

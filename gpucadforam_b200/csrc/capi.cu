@@ -164,6 +164,33 @@ int gcb_computeIsosurface(gcb_ctx* ctx, float* vol, gcb_uint3 raster_grid, void*
     return 0;
 }
 
+int gcb_computeIsosurface_region(gcb_ctx* ctx, void* pos, void* norm, float isoValue, unsigned int numVoxels, unsigned int* d_voxelVerts,
+                                 unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan, gcb_uint3 gridSize,
+                                 gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter, unsigned int* activeVoxels,
+                                 unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts, gcb_grid_points* vol_topo,
+                                 gcb_grid_points* primitive_fixed, float* primitive_dynamic, float* topo_field, float* lattice_field, float iso1, float iso2,
+                                 int obj_union, int obj_diff, int obj_intersect, int primitive, int topo, int compute_lattice, int fixed, int dynamic,
+                                 int make_region, int show_region, int show_domain, gcb_triangle_metadata* triangle_data) {
+    CTX(ctx);
+    // dead parameters of the reference kernels (MarchingCubes_kernel.cu:1163-1167, :2222-2228): everything but the three flags below
+    (void)numVoxels; (void)gridSizeShift; (void)gridSizeMask; (void)topo_field; (void)lattice_field; (void)iso1; (void)iso2; (void)obj_union; (void)obj_diff;
+    (void)obj_intersect; (void)primitive; (void)topo; (void)compute_lattice; (void)fixed; (void)dynamic;
+    // with none of the three flags the reference classifies an uninitialised cube index (:1214-1285): refuse instead of guessing
+    if (!make_region && !show_region && !show_domain) return fail_msg(C, "computeIsosurface_region: one of make_region / show_region / show_domain must be set");
+    if (!vol_topo || !primitive_fixed || !primitive_dynamic) return fail_msg(C, "computeIsosurface_region: null field");
+    if (show_region && !triangle_data) return fail_msg(C, "computeIsosurface_region: show_region needs triangle_data");
+    McArgs a;
+    base_args(a, M_REGION, gridSize, voxelSize, gridcenter, isoValue);
+    // precedence as the reference's if / else-if chain: show_region, then show_domain, then make_region
+    a.flags = show_region ? F_SHOW_REGION : show_domain ? F_SHOW_DOMAIN : F_MAKE_REGION;
+    a.f0 = primitive_dynamic;
+    a.gp = (const GridPoint*)primitive_fixed;
+    a.gp2 = (const GridPoint*)vol_topo;
+    a.meta = (TriangleMetadata*)triangle_data;
+    return run_legacy(C, a, pos, norm, maxVerts, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan, d_compVoxelArray, activeVoxels, totalVerts,
+                      true);  // Isosurface.cu:217-218 clears maxVerts bytes like the CSG variant
+}
+
 static int lattice_common(Ctx* C, int mode, float* vol, void* pos, void* norm, float isoValue, unsigned* d_voxelVerts, unsigned* d_voxelVertsScan,
                           unsigned* d_voxelOccupied, unsigned* d_voxelOccupiedScan, gcb_uint3 gridSize, gcb_float3 voxelSize, gcb_float3 gridcenter,
                           unsigned* activeVoxels, unsigned* totalVerts, unsigned* d_compVoxelArray, unsigned maxVerts, float* vol_one, float* vol_two,

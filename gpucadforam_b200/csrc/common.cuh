@@ -19,11 +19,19 @@ enum Mode : int {
     M_LATTICE = 1,      // computeIsosurface_lattice     (+ vol_two, iso1/iso2)
     M_CSG = 2,          // computeIsosurface             (grid_points + dynamic + lattice)
     M_TOPO = 3,         // computeIsosurface_2 / _topo   (vol_topo + density + result [+disp])
-    M_BAND_RAW = 4      // fused: raw field -> normalise + domain faces + band mask -> latticeone
+    M_BAND_RAW = 4,     // fused: raw field -> normalise + domain faces + band mask -> latticeone
+    M_REGION = 5        // computeIsosurface_region      (vol_topo + primitive_fixed + dynamic, triangle_metadata)
 };
 enum : uint32_t {
-    F_UNION = 1, F_DIFF = 2, F_INTERSECT = 4, F_FIXED = 8, F_DYNAMIC = 16, F_MAKE_REGION = 32, F_DISP = 64
+    F_UNION = 1, F_DIFF = 2, F_INTERSECT = 4, F_FIXED = 8, F_DYNAMIC = 16, F_MAKE_REGION = 32, F_DISP = 64,
+    F_SHOW_REGION = 128, F_SHOW_DOMAIN = 256
 };
+// 64-byte per-triangle record of the region variant; reference src/MarchingCubes_kernel.h:20-32
+struct TriangleMetadata {
+    unsigned int index, voxel, l_index, edge_1, edge_2, edge_3, load_group;
+    float centroid[3], normal[3], force_dir[3];
+};
+static_assert(sizeof(TriangleMetadata) == sizeof(gcb_triangle_metadata) && sizeof(TriangleMetadata) == 64, "layout");
 
 // Arguments of the fused extraction kernel (by value, < 4 KB).
 struct McArgs {
@@ -37,7 +45,9 @@ struct McArgs {
     const float* f0;       // TMA-staged interpolation field (k | dynamic | density | raw)
     const float* f1;       // mask (lattice) | lattice_field (CSG) | d_result (topo)
     const float* f2;       // vol_two (M_LATTICE)
-    const GridPoint* gp;   // primitive_fixed (CSG) | vol_topo (topo)
+    const GridPoint* gp;   // primitive_fixed (CSG, region) | vol_topo (topo)
+    const GridPoint* gp2;  // vol_topo (region)
+    TriangleMetadata* meta;  // region + show_region: one record per triangle
     const float4* disp;    // topo displaced positions
     float na, nb;          // M_BAND_RAW: k = (f - na) / (nb - na)
     uint32_t gz0, gnz;     // global z offset of local point layer 0, global number of point layers

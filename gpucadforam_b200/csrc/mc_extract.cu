@@ -113,6 +113,7 @@ struct Smem {
     float* val[2];
     unsigned char* bit[2];
     unsigned char* cube;
+    unsigned char* cls;   // M_REGION: which cascade level produced the cube index (0: vol_topo, 1: second test, 2: third test)
     unsigned long long* tri;
     unsigned char* nv;
     uint32_t* queue;      // kWarps * kQueue
@@ -278,6 +279,13 @@ __device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& n
         else m = ((k >= A.iso1) && (k <= A.iso2)) ? 1.0f : 0.0f;
         bits = (m == 1.f ? 1u : 0u) | ((m < A.iso) ? 4u : 0u);
         val = k;
+    } else if (MODE == M_REGION) {
+        // classifyVoxel_region_kernel :1163-1290: three candidate inside tests per point, the cascade is resolved per cell
+        const float iso = A.iso;
+        const float ft = A.gp2 ? (float)A.gp2[gi].val : 0.f;  // sampleVolume_2 :98-108
+        const float fx = A.gp ? (float)A.gp[gi].val : 0.f;
+        bits = ((ft < iso) ? 4u : 0u) | ((fx < iso) ? 8u : 0u) | (((fx < iso) & (raw < iso)) ? 16u : 0u);
+        val = raw;  // primitive_dynamic
     } else if (MODE == M_TOPO) {
         // classifyVoxel_kernel_topo :1492-1499
         const float fx = A.gp ? (float)A.gp[gi].val : 0.f;
@@ -320,7 +328,7 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const uint32_t e = (uint32_t)(tri >> (4 * (3 * j + k))) & 15u;
-        const bool own = (MODE == M_TOPO) || (MODE == M_CSG && !(A.flags & F_FIXED));
+        const bool own = (MODE == M_TOPO) || (MODE == M_REGION) || (MODE == M_CSG && !(A.flags & F_FIXED));
         const uint32_t ab = S.edge[(own ? 16u : 0u) + e];
         const uint32_t ca = ab & 7u, cb = ab >> 3;
         // corner positions: v[0] = p, v[i] = p + (voxel or 0) per component (:1892-1900).  p + 0.0f == p bit for bit for every
@@ -331,7 +339,22 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
         const uint32_t za = (ca >> 2) & 1u, zb = (cb >> 2) & 1u;
         const float fa = (za ? S.val[1] : S.val[0])[sa], fb = (zb ? S.val[1] : S.val[0])[sb];
         w[k] = 0.f;
-        if (MODE == M_BAND_RAW) {
+        if (MODE == M_REGION) {
+            // generateTriangles_region_kernel :2391-2490: stored crossing parameter of the edge's owning point, from vol_topo
+            // (first test fired) or primitive_fixed; make_region's second test blends it with the dynamic field's crossing
+            const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
+            const uint32_t cl = S.cls[c];
+            const GridPoint* src = cl == 0u ? A.gp2 : A.gp;
+            float et = 0.f;
+            if (src) {
+                const GridPoint g = src[ga];
+                const uint32_t ax = edge_axis(e);
+                et = ax == 0 ? g.t_x : ax == 1 ? g.t_y : g.t_z;
+            }
+            const float t = (cl == 1u && !(A.flags & F_SHOW_DOMAIN)) ? t_primitive(A.iso, fa, fb, et) : et;
+            v[k] = lerp3(pa, pb, t);
+            w[k] = cl == 0u ? 1.0f : cl == 1u ? 0.25f : 0.5f;  // `aa`
+        } else if (MODE == M_BAND_RAW) {
             v[k] = interp_band_crossing(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb);
         } else if (MODE == M_LATTICE_ONE) {
             v[k] = interp_band(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb, ((za ? S.bit[1] : S.bit[0])[sa] & 3u), ((zb ? S.bit[1] : S.bit[0])[sb] & 3u));
@@ -377,6 +400,28 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
     if (MODE == M_CSG) {  // calcNormal(ver0, ver2, ver1), w = 0.5 (:2178-2185)
         n = cross3(sub3(v[2], v[0]), sub3(v[1], v[0]));
         w[0] = w[1] = w[2] = 0.5f;
+    } else if (MODE == M_REGION) {
+        // normalize(calcNormal(v0, v1, v2)) :2576; helper_math.h normalize = v * rsqrtf(dot(v, v)).  The reference build
+        // (sm_100a SASS) evaluates the dot product as FMUL y*y, FFMA x*x + ., FFMA z*z + . and rsqrtf through MUFU.RSQ with
+        // the denormal pre/post scaling -- rsqrtf() here compiles to the same sequence.
+        n = cross3(sub3(v[1], v[0]), sub3(v[2], v[0]));
+        const float inv = rsqrtf(__fmaf_rn(n.z, n.z, __fmaf_rn(n.x, n.x, __fmul_rn(n.y, n.y))));
+        n = make_float3(__fmul_rn(n.x, inv), __fmul_rn(n.y, inv), __fmul_rn(n.z, inv));
+        if ((A.flags & F_SHOW_REGION) && A.meta) {
+            // triangle_metadata :2528-2584, written whether or not the vertices fit into maxVerts; load_group / force_dir untouched
+            const uint32_t ind = (uint32_t)(vidx / 3ull);
+            TriangleMetadata* m = A.meta + ind;
+            m->index = ind;
+            m->voxel = (z + A.gz0) * A.cx * A.cy + y0 * A.cx + c;
+            m->l_index = j;
+            m->edge_1 = (uint32_t)(tri >> (12 * j)) & 15u;
+            m->edge_2 = (uint32_t)(tri >> (12 * j + 4)) & 15u;
+            m->edge_3 = (uint32_t)(tri >> (12 * j + 8)) & 15u;
+            m->centroid[0] = __fdiv_rn(__fadd_rn(__fadd_rn(v[0].x, v[1].x), v[2].x), 3.0f);
+            m->centroid[1] = __fdiv_rn(__fadd_rn(__fadd_rn(v[0].y, v[1].y), v[2].y), 3.0f);
+            m->centroid[2] = __fdiv_rn(__fadd_rn(__fadd_rn(v[0].z, v[1].z), v[2].z), 3.0f);
+            m->normal[0] = n.x; m->normal[1] = n.y; m->normal[2] = n.z;
+        }
     } else {
         n = cross3(sub3(v[1], v[0]), sub3(v[2], v[0]));
     }
@@ -410,7 +455,8 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
         S.nv = p; p += 256;
         S.bit[0] = p; p += A.prow_stride;
         S.bit[1] = p; p += A.prow_stride;
-        S.cube = p;
+        S.cube = p; p += (size_t)A.rows_per_tile * A.cx;
+        S.cls = p;  // only backed by shared memory in M_REGION launches
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
@@ -511,8 +557,23 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
                 const uint32_t pi = r * A.nx + x;
                 const unsigned char* b0 = S.bit[0] + pi;
                 const unsigned char* b1 = S.bit[1] + pi;
-                uint32_t cube = ((b0[0] >> 2) & 1u) | (((b0[1] >> 2) & 1u) << 1) | (((b0[A.nx + 1] >> 2) & 1u) << 2) | (((b0[A.nx] >> 2) & 1u) << 3) |
-                                (((b1[0] >> 2) & 1u) << 4) | (((b1[1] >> 2) & 1u) << 5) | (((b1[A.nx + 1] >> 2) & 1u) << 6) | (((b1[A.nx] >> 2) & 1u) << 7);
+                uint32_t cube;
+                if (MODE == M_REGION) {
+                    // the eight corner bytes, then one cube index per candidate test (bits 2, 3, 4) and the reference's cascade
+                    const uint32_t cb[8] = {b0[0], b0[1], b0[A.nx + 1], b0[A.nx], b1[0], b1[1], b1[A.nx + 1], b1[A.nx]};
+                    uint32_t k0 = 0, k1 = 0, k2 = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { k0 |= ((cb[q] >> 2) & 1u) << q; k1 |= ((cb[q] >> 3) & 1u) << q; k2 |= ((cb[q] >> 4) & 1u) << q; }
+                    uint32_t cl = 0;
+                    cube = k0;
+                    if (!(A.flags & F_SHOW_REGION) && cube == 0u) {
+                        if (A.flags & F_SHOW_DOMAIN) { cube = k1; cl = 1; }
+                        else { cube = k2; cl = 1; if (cube == 0u) { cube = k1; cl = 2; } }
+                    }
+                    S.cls[c] = (unsigned char)cl;
+                } else
+                    cube = ((b0[0] >> 2) & 1u) | (((b0[1] >> 2) & 1u) << 1) | (((b0[A.nx + 1] >> 2) & 1u) << 2) | (((b0[A.nx] >> 2) & 1u) << 3) |
+                           (((b1[0] >> 2) & 1u) << 4) | (((b1[1] >> 2) & 1u) << 5) | (((b1[A.nx + 1] >> 2) & 1u) << 6) | (((b1[A.nx] >> 2) & 1u) << 7);
                 S.cube[c] = (unsigned char)cube;
                 const uint32_t nv = S.nv[cube];
                 my_verts += nv;
@@ -651,7 +712,7 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     const size_t fixed_bytes = 256 * 8 + 16 + 8 + 8 + 32 + kWarps * kQueue * 4 + kWarps * 8 + 256 + 256 /*slack*/;
     auto smem_for = [&](uint32_t r) {
         const size_t stride = (((size_t)(r + 1) * a.nx) + 15) & ~(size_t)15;
-        return stride * 4 * 2 + stride * 2 + (size_t)r * a.cx + 16 + fixed_bytes;
+        return stride * 4 * 2 + stride * 2 + (size_t)r * a.cx * (a.mode == M_REGION ? 2 : 1) + 16 + fixed_bytes;
     };
     while (R > 1 && smem_for(R) > 100 * 1024) --R;
     const size_t smem = smem_for(R);
@@ -698,6 +759,7 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     case M_CSG: occ = occupancy<M_CSG>(smem); break;
     case M_TOPO: occ = occupancy<M_TOPO>(smem); break;
     case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem); break;
+    case M_REGION: occ = occupancy<M_REGION>(smem); break;
     default: return fail_msg(c, "bad mode");
     }
     if (occ < 1) return fail_msg(c, "extraction kernel does not fit on an SM");
@@ -712,6 +774,7 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     case M_LATTICE: e = launch_mode<M_LATTICE>(a, (int)grid, smem, c->stream); break;
     case M_CSG: e = launch_mode<M_CSG>(a, (int)grid, smem, c->stream); break;
     case M_TOPO: e = launch_mode<M_TOPO>(a, (int)grid, smem, c->stream); break;
+    case M_REGION: e = launch_mode<M_REGION>(a, (int)grid, smem, c->stream); break;
     default: e = launch_mode<M_BAND_RAW>(a, (int)grid, smem, c->stream); break;
     }
     if (e != cudaSuccess) return fail(c, "mc_fused_kernel launch", e);

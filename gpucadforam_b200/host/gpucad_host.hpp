@@ -19,7 +19,11 @@
 #endif
 typedef unsigned int uint;
 struct grid_points { int val = 0; float t_x = 0.0f, t_y = 0.0f, t_z = 0.0f; };  // src/MarchingCubes_kernel.h:12-18
-struct triangle_metadata;                                                          // only passed through
+struct triangle_metadata {                                                         // src/MarchingCubes_kernel.h:20-32
+    uint index, voxel, l_index, edge_1, edge_2, edge_3, load_group;
+    float3 centroid, normal, force_dir;
+};
+static_assert(sizeof(triangle_metadata) == sizeof(gcb_triangle_metadata), "triangle_metadata layout");
 
 namespace gpucad {
 inline gcb_ctx*& ctx_slot() { static gcb_ctx* c = nullptr; return c; }
@@ -69,6 +73,20 @@ public:
                                     make_region, nfacets),
               "computeIsosurface");
     }
+    void computeIsosurface_region(float4* pos, float4* norm, float isoValue, uint numVoxels, uint* d_voxelVerts, uint* d_voxelVertsScan, uint* d_voxelOccupied,
+                                  uint* d_voxelOccupiedScan, uint3 gridSize, uint3 gridSizeShift, uint3 gridSizeMask, float3 voxelSize, float3 gridcenter,
+                                  uint* activeVoxels, uint* totalVerts, uint* d_compVoxelArray, uint maxVerts, grid_points* vol_topo,
+                                  grid_points* primitive_fixed, float* primitive_dynamic, float* topo_field, float* lattice_field, float iso1, float iso2,
+                                  bool obj_union, bool obj_diff, bool obj_intersect, bool primitive, bool topo, bool compute_lattice, bool fixed, bool dynamic,
+                                  bool make_region, bool show_region, bool show_domain, triangle_metadata* triangle_data) {
+        using namespace gpucad;
+        check(gcb_computeIsosurface_region(ctx(), pos, norm, isoValue, numVoxels, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan,
+                                           u3(gridSize), u3(gridSizeShift), u3(gridSizeMask), f3(voxelSize), f3(gridcenter), activeVoxels, totalVerts,
+                                           d_compVoxelArray, maxVerts, (gcb_grid_points*)vol_topo, (gcb_grid_points*)primitive_fixed, primitive_dynamic,
+                                           topo_field, lattice_field, iso1, iso2, obj_union, obj_diff, obj_intersect, primitive, topo, compute_lattice, fixed,
+                                           dynamic, make_region, show_region, show_domain, (gcb_triangle_metadata*)triangle_data),
+              "computeIsosurface_region");
+    }
     void computeIsosurface_2(float4* pos, float4* norm, float isoValue, uint numVoxels, uint* d_voxelVerts, uint* d_voxelVertsScan, uint* d_voxelOccupied,
                              uint* d_voxelOccupiedScan, uint3 gridSize, uint3 gridSizeShift, uint3 gridSizeMask, float3 voxelSize, float3 gridcenter,
                              uint* activeVoxels, uint* totalVerts, uint* d_compVoxelArray, uint maxVerts, grid_points* vol_topo, grid_points* vol_one,
@@ -77,7 +95,7 @@ public:
         check(gcb_computeIsosurface_2(ctx(), pos, norm, isoValue, numVoxels, d_voxelVerts, d_voxelVertsScan, d_voxelOccupied, d_voxelOccupiedScan,
                                       u3(gridSize), u3(gridSizeShift), u3(gridSizeMask), f3(voxelSize), f3(gridcenter), activeVoxels, totalVerts,
                                       d_compVoxelArray, maxVerts, (gcb_grid_points*)vol_topo, (gcb_grid_points*)vol_one, vol_two, d_solid, isovalue1,
-                                      d_result, triangle_data),
+                                      d_result, (void*)triangle_data),
               "computeIsosurface_2");
     }
     void computeIsosurface_topo(float4* pos, float4* norm, float isoValue, uint numVoxels, uint* d_voxelVerts, uint* d_voxelVertsScan,

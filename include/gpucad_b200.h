@@ -33,6 +33,13 @@ typedef struct gcb_pitched_ptr { void* ptr; size_t pitch, xsize, ysize; } gcb_pi
 /* reference: struct grid_points, src/MarchingCubes_kernel.h:12-18 (16-byte AoS) */
 typedef struct gcb_grid_points { int val; float t_x, t_y, t_z; } gcb_grid_points;
 
+/* reference: struct triangle_metadata, src/MarchingCubes_kernel.h:20-32 (64 bytes, 4-byte aligned).  computeIsosurface_region
+ * writes index .. edge_3, centroid and normal; load_group and force_dir belong to the picking code and are left untouched. */
+typedef struct gcb_triangle_metadata {
+    unsigned int index, voxel, l_index, edge_1, edge_2, edge_3, load_group;
+    float centroid[3], normal[3], force_dir[3];
+} gcb_triangle_metadata;
+
 typedef struct gcb_ctx gcb_ctx;
 
 /* ------------------------------------------------------------------ context */
@@ -75,6 +82,20 @@ int gcb_computeIsosurface(gcb_ctx* ctx, float* vol, gcb_uint3 raster_grid, void*
     unsigned int* d_compVoxelArray, unsigned int maxVerts, gcb_grid_points* primitive_fixed, float* primitive_dynamic,
     float* topo_field, float* lattice_field, float iso1, float iso2, int obj_union, int obj_diff, int obj_intersect,
     int primitive, int topo, int compute_lattice, int fixed, int dynamic, int make_region, size_t* nfacets);
+
+/* Isosurface::computeIsosurface_region  (src/Isosurface.h:38-43, Isosurface.cu:150-239; kernels MarchingCubes_kernel.cu:1163-1302,
+ * :2222-2605) -- the GUI's region / domain display and load-support picking.  Cascade per cell: vol_topo (norm.w = 1), then
+ * primitive_fixed [& primitive_dynamic for make_region] (0.25), then primitive_fixed (0.5); normals are normalised; with
+ * show_region one gcb_triangle_metadata record per triangle (index, voxel, l_index, edge_1..3, centroid, normal) is written to
+ * triangle_data, which must hold totalVerts/3 records.  Flag precedence show_region > show_domain > make_region as in the
+ * reference; with none set the reference reads an uninitialised cube index, this entry point returns an error instead. */
+int gcb_computeIsosurface_region(gcb_ctx* ctx, void* pos, void* norm, float isoValue, unsigned int numVoxels, unsigned int* d_voxelVerts,
+    unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied, unsigned int* d_voxelOccupiedScan, gcb_uint3 gridSize,
+    gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask, gcb_float3 voxelSize, gcb_float3 gridcenter, unsigned int* activeVoxels,
+    unsigned int* totalVerts, unsigned int* d_compVoxelArray, unsigned int maxVerts, gcb_grid_points* vol_topo,
+    gcb_grid_points* primitive_fixed, float* primitive_dynamic, float* topo_field, float* lattice_field, float iso1, float iso2,
+    int obj_union, int obj_diff, int obj_intersect, int primitive, int topo, int compute_lattice, int fixed, int dynamic,
+    int make_region, int show_region, int show_domain, gcb_triangle_metadata* triangle_data);
 
 /* Isosurface::computeIsosurface_lattice  (Isosurface.h:60-64, Isosurface.cu:401-486) */
 int gcb_computeIsosurface_lattice(gcb_ctx* ctx, float* vol, void* pos, void* norm, float isoValue, unsigned int numVoxels,

@@ -91,8 +91,33 @@ inline void cell_pos(const Grid& g, uint32_t i, uint32_t& x, uint32_t& y, uint32
 
 inline bool band(float v, float lo, float hi) { return (v > lo) & (v < hi); }
 
+/* classifyVoxel_region_kernel :1163-1290 (and the identical cascade of generateTriangles_region_kernel :2305-2385):
+ * cube index from vol_topo; when that is 0, show_domain retries with primitive_fixed (aa = 0.25), make_region with
+ * primitive_fixed & primitive_dynamic (aa = 0.25) and then primitive_fixed alone (aa = 0.5).  cls = 0 / 1 / 2 names the test
+ * that produced the index. */
+inline uint32_t region_cube(const orc_mc_params& p, const Grid& g, uint32_t x, uint32_t y, uint32_t z, int* cls) {
+    const float iso = p.iso;
+    uint32_t k0 = 0, k1 = 0, k2 = 0;
+    for (int c = 0; c < 8; ++c) {
+        size_t i = g.idx(x + kCorner[c][0], y + kCorner[c][1], z + kCorner[c][2]);
+        const float ft = (float)p.gp2[i].val, fx = (float)p.gp[i].val, dy = p.f0[i]; /* sampleVolume_2 :98-108 */
+        k0 |= (uint32_t)(ft < iso) << c;
+        k1 |= (uint32_t)(fx < iso) << c;
+        k2 |= ((uint32_t)(fx < iso) & (uint32_t)(dy < iso)) << c;
+    }
+    uint32_t ci = k0;
+    int cl = 0;
+    if (!(p.flags & ORC_F_SHOW_REGION) && ci == 0) {
+        if (p.flags & ORC_F_SHOW_DOMAIN) { ci = k1; cl = 1; }
+        else { ci = k2; cl = 1; if (ci == 0) { ci = k1; cl = 2; } }
+    }
+    if (cls) *cls = cl;
+    return ci;
+}
+
 /* cube index of cell (x,y,z) for each mode */
 inline uint32_t cube_index(const orc_mc_params& p, const Grid& g, uint32_t x, uint32_t y, uint32_t z) {
+    if (p.mode == ORC_MODE_REGION) return region_cube(p, g, x, y, z, nullptr);
     uint32_t ci = 0;
     const float iso = p.iso;
     for (int c = 0; c < 8; ++c) {
@@ -254,6 +279,8 @@ void emit_cell(const orc_mc_params& p, const Grid& g, uint32_t voxel, uint32_t b
         pi[c] = g.idx(x + kCorner[c][0], y + kCorner[c][1], z + kCorner[c][2]);
     }
 
+    int region_cls = 0;
+    if (p.mode == ORC_MODE_REGION) region_cube(p, g, x, y, z, &region_cls);
     f3 vert[12];
     float col[12];
     bool have[12] = {false};
@@ -292,6 +319,13 @@ void emit_cell(const orc_mc_params& p, const Grid& g, uint32_t voxel, uint32_t b
             }
             break;
         }
+        case ORC_MODE_REGION: { /* :2391-2490 */
+            int a = kEdgeOwn[e][0], b = kEdgeOwn[e][1];
+            const float et = gp_t((region_cls == 0 ? p.gp2 : p.gp)[pi[a]], kEdgeAxis[e]);
+            const float t = (region_cls == 1 && !(p.flags & ORC_F_SHOW_DOMAIN)) ? t_primitive(p.iso, p.f0[pi[a]], p.f0[pi[b]], et) : et;
+            vert[e] = lerp3(v[a], v[b], t);
+            break;
+        }
         case ORC_MODE_TOPO: {
             int a = kEdgeOwn[e][0], b = kEdgeOwn[e][1];
             float t = t_analysis(p.iso, p.f0[pi[a]], p.f0[pi[b]], gp_t(p.gp[pi[a]], kEdgeAxis[e]));
@@ -315,6 +349,22 @@ void emit_cell(const orc_mc_params& p, const Grid& g, uint32_t voxel, uint32_t b
         if (p.mode == ORC_MODE_CSG) { /* calcNormal(ver0, ver2, ver1) :2178, w = 0.5 :2185 */
             n = cross3(vert[e2] - vert[e0], vert[e1] - vert[e0]);
             w[0] = w[1] = w[2] = 0.5f;
+        } else if (p.mode == ORC_MODE_REGION) {
+            /* normalize(calcNormal(v0, v1, v2)) :2576; helper_math.h normalize = v * rsqrtf(dot(v, v)); dot contracted as in the
+             * reference build: fma(z, z, fma(x, x, y*y)).  rsqrtf is MUFU.RSQ on the GPU (2 ulp); 1/sqrtf here. */
+            n = cross3(vert[e1] - vert[e0], vert[e2] - vert[e0]);
+            const float inv = 1.0f / sqrtf(fmaf(n.z, n.z, fmaf(n.x, n.x, n.y * n.y)));
+            n = {n.x * inv, n.y * inv, n.z * inv};
+            w[0] = w[1] = w[2] = region_cls == 0 ? 1.0f : region_cls == 1 ? 0.25f : 0.5f; /* aa */
+            if ((p.flags & ORC_F_SHOW_REGION) && p.meta) { /* :2528-2584, outside the maxVerts guard */
+                orc_triangle_metadata& m = p.meta[index / 3];
+                m.index = index / 3; m.voxel = voxel; m.l_index = (uint32_t)j / 3;
+                m.edge_1 = (uint32_t)e0; m.edge_2 = (uint32_t)e1; m.edge_3 = (uint32_t)e2;
+                m.centroid[0] = ((vert[e0].x + vert[e1].x) + vert[e2].x) / 3.0f;
+                m.centroid[1] = ((vert[e0].y + vert[e1].y) + vert[e2].y) / 3.0f;
+                m.centroid[2] = ((vert[e0].z + vert[e1].z) + vert[e2].z) / 3.0f;
+                m.normal[0] = n.x; m.normal[1] = n.y; m.normal[2] = n.z;
+            }
         } else {
             n = cross3(vert[e1] - vert[e0], vert[e2] - vert[e0]);
             if (p.mode == ORC_MODE_TOPO) { w[0] = col[e0]; w[1] = col[e1]; w[2] = col[e2]; }

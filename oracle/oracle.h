@@ -29,15 +29,23 @@ enum {
     ORC_MODE_LATTICE_ONE = 0, /* Isosurface::computeIsosurface_latticeone  Isosurface.cu:488-572 */
     ORC_MODE_LATTICE     = 1, /* Isosurface::computeIsosurface_lattice     Isosurface.cu:401-486 */
     ORC_MODE_CSG         = 2, /* Isosurface::computeIsosurface             Isosurface.cu:44-134  */
-    ORC_MODE_TOPO        = 3  /* Isosurface::computeIsosurface_2 / _topo   Isosurface.cu:243-398 */
+    ORC_MODE_TOPO        = 3, /* Isosurface::computeIsosurface_2 / _topo   Isosurface.cu:243-398 */
+    ORC_MODE_REGION      = 5  /* Isosurface::computeIsosurface_region      Isosurface.cu:150-239 */
 };
 
 /* flag bits of orc_mc_params.flags (CSG mode) */
 enum {
     ORC_F_UNION = 1, ORC_F_DIFF = 2, ORC_F_INTERSECT = 4,
     ORC_F_FIXED = 8, ORC_F_DYNAMIC = 16, ORC_F_MAKE_REGION = 32,
-    ORC_F_DISP = 64 /* TOPO: positions interpolated from disp field (computeIsosurface_topo disp=true) */
+    ORC_F_DISP = 64, /* TOPO: positions interpolated from disp field (computeIsosurface_topo disp=true) */
+    ORC_F_SHOW_REGION = 128, ORC_F_SHOW_DOMAIN = 256 /* REGION: show_region / show_domain (else ORC_F_MAKE_REGION) */
 };
+
+/* per-triangle record of the region variant: reference src/MarchingCubes_kernel.h:20-32 */
+typedef struct orc_triangle_metadata {
+    uint32_t index, voxel, l_index, edge_1, edge_2, edge_3, load_group;
+    float centroid[3], normal[3], force_dir[3];
+} orc_triangle_metadata;
 
 typedef struct orc_mc_params {
     int32_t mode;
@@ -55,6 +63,8 @@ typedef struct orc_mc_params {
     const float* f2;            /* LATTICE : vol_two                                                   */
     const orc_grid_point* gp;   /* CSG: primitive_fixed;  TOPO: vol_topo                               */
     const float* disp;          /* TOPO+DISP: float4 per point                                         */
+    const orc_grid_point* gp2;  /* REGION: vol_topo (gp = primitive_fixed, f0 = primitive_dynamic)     */
+    orc_triangle_metadata* meta;/* REGION + SHOW_REGION: one record per triangle                       */
 } orc_mc_params;
 
 /* Marching-cubes tables (Bourke): tri is 256x16 with 255 terminators, nverts is 256. */

@@ -278,6 +278,38 @@ int ref_isosurface_csg(int fix_grid, float4* pos, float4* norm, float iso, uint 
     return last_error("csg(fixed grid)");
 }
 
+/* Isosurface::computeIsosurface_region as shipped (Isosurface.cu:150-239); fix_grid replays it with a grid covering every cell */
+int ref_isosurface_region(int fix_grid, float4* pos, float4* norm, float iso, uint nx, uint ny, uint nz, float vx, float vy, float vz,
+                          float gx, float gy, float gz, uint* d_verts, uint* d_vertsScan, uint* d_occ, uint* d_occScan, uint* d_comp,
+                          uint maxVerts, grid_points* vol_topo, grid_points* fixed_f, float* dynamic_f, int make_region, int show_region,
+                          int show_domain, triangle_metadata* triangle_data, uint* activeVoxels, uint* totalVerts) {
+    GridDesc g = make_grid(nx, ny, nz);
+    float3 vs = make_float3(vx, vy, vz), gc = make_float3(gx, gy, gz);
+    bool M = make_region != 0, R = show_region != 0, D = show_domain != 0;
+    if (!fix_grid) {
+        g_iso->computeIsosurface_region(pos, norm, iso, g.numVoxels, d_verts, d_vertsScan, d_occ, d_occScan, g.size, g.shift, g.mask, vs, gc,
+                                        activeVoxels, totalVerts, d_comp, maxVerts, vol_topo, fixed_f, dynamic_f, nullptr, nullptr, 0.f, 0.f,
+                                        true, false, false, true, false, false, false, false, M, R, D, triangle_data);
+        return last_error("computeIsosurface_region");
+    }
+    dim3 threads(1024, 1, 1);
+    g_iso->classifyVoxel_region(fixed_grid(g.numVoxels), threads, d_verts, d_occ, vol_topo, fixed_f, dynamic_f, nullptr, nullptr, g.size, g.shift,
+                                g.mask, g.numVoxels, 0.f, 0.f, vs, iso, true, false, false, true, false, false, false, false, M, R, D);
+    g_iso->ThrustScanWrapper_lattice(d_occScan, d_occ, g.numVoxels);
+    *activeVoxels = scan_total(d_occScan, d_occ, g.numVoxels);
+    if (*activeVoxels == 0) { *totalVerts = 0; return last_error("region(empty)"); }
+    g_iso->compactVoxels_lattice(fixed_grid(g.numVoxels), threads, d_comp, d_occ, d_occScan, g.numVoxels);
+    g_iso->ThrustScanWrapper_lattice(d_vertsScan, d_verts, g.numVoxels);
+    *totalVerts = scan_total(d_vertsScan, d_verts, g.numVoxels);
+    cudaMemset(pos, 0, maxVerts);
+    cudaMemset(norm, 0, maxVerts);
+    dim3 grid2((*activeVoxels + NTHREADS - 1) / NTHREADS, 1, 1), tids2(NTHREADS, 1, 1);
+    g_iso->generateTriangles_region(grid2, tids2, pos, norm, d_comp, d_vertsScan, g.size, g.shift, g.mask, vs, gc, iso, *activeVoxels, maxVerts,
+                                    *totalVerts, vol_topo, fixed_f, dynamic_f, nullptr, nullptr, 0.f, 0.f, d_verts, true, false, false, true, false,
+                                    false, false, false, M, R, D, triangle_data);
+    return last_error("region(fixed grid)");
+}
+
 int ref_isosurface_topo(int with_disp_variant, float4* pos, float4* norm, float iso, uint nx, uint ny, uint nz, float vx, float vy,
                         float vz, float gx, float gy, float gz, uint* d_verts, uint* d_vertsScan, uint* d_occ, uint* d_occScan,
                         uint* d_comp, uint maxVerts, grid_points* vol_topo, grid_points* vol_one, float* vol_two, float* d_solid,

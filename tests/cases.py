@@ -15,6 +15,14 @@ CSG = dict(dims=(48, 48, 48), d=(0.5, 0.5, 0.5),
            cuboid=dict(center=(1.0, 0.5, -0.5), angles=(0.3, 0.2, 0.1), xw=17.0, yw=9.0, zw=11.0),
            cylinder=dict(center=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), radius=3.4, tr=2.0, ta=40.0))
 
+# region / domain display (f-4): vol_topo <- retained sphere, primitive_fixed <- retained rotated cuboid, dynamic <- sphere field
+# (32*32*24 points is a multiple of 1024: the reference's cuboid kernel has no bounds guard)
+REGION = dict(dims=(32, 32, 24), d=(0.5, 0.5, 0.5),
+              topo_sphere=dict(center=(-2.5, 1.0, 0.5), radius=3.0, thickness=1.0),
+              cuboid=dict(center=(0.5, 0.0, 0.0), angles=(0.1, 0.2, 0.3), xw=9.0, yw=7.0, zw=6.0),
+              dyn_sphere=dict(center=(2.0, 0.0, 0.0), radius=4.0, thickness=1.0))
+REGION_MODES = ["make_region", "show_region", "show_domain"]
+
 PRIMS = dict(dims=(40, 36, 44), d=(0.5, 0.5, 0.5), center=(0.7, -0.4, 0.3), angles=(0.3, 0.2, 0.1))
 
 # configs 3/4 in miniature: control 16x16x8 -> fine 32x32x16 (ratio 2, the app's own), and control 8^3 -> fine 32^3 (ratio 4)

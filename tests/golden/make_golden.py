@@ -30,8 +30,41 @@ def pack(scr, mesh, dims, act, tot):
     return d
 
 
-def main(out):
+def region(out):
+    """computeIsosurface_region (f-4): the three display modes on retained grids, incl. the triangle_metadata records."""
+    R = cases.REGION
+    dims, d = R["dims"], R["d"]
+    npts = dims[0] * dims[1] * dims[2]
+    zero = torch.zeros(npts, device="cuda")
+    f = torch.zeros(npts, device="cuda")
+    vol_topo, vol_one = gp_zeros(npts), gp_zeros(npts)
+    s, c, y = R["topo_sphere"], R["cuboid"], R["dyn_sphere"]
+    ref.sphere(f, s["center"], s["radius"], s["thickness"], dims, d, False)
+    ref.copy_parameter(vol_topo, f, zero, dims, d, 0.0, obj_union=True)
+    ref.cuboid(f, c["center"], c["angles"], c["xw"], c["yw"], c["zw"], dims, d)
+    ref.copy_parameter(vol_one, f, zero, dims, d, 0.0, obj_union=True)
+    dyn = torch.zeros(npts, device="cuda")
+    ref.sphere(dyn, y["center"], y["radius"], y["thickness"], dims, d, False)
+    mv = max_verts_for(dims)
+    ncell = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)
+    res = dict(vol_topo=vol_topo.cpu().numpy(), vol_one=vol_one.cpu().numpy(), dynamic=dyn.cpu().numpy())
+    for mode in cases.REGION_MODES:
+        scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+        meta = torch.full((mv // 3, 16), 0x7f7f7f7f, dtype=torch.int32, device="cuda")
+        a, t = ref.isosurface_region(False, mesh.pos, mesh.norm, 0.0, dims, d, (0, 0, 0), scr, mv, vol_topo, vol_one, dyn, triangle_data=meta,
+                                     **{mode: True})
+        for k, v in pack(scr, mesh, dims, a, t).items():
+            res[mode + "_" + k] = v
+        res[mode + "_meta"] = meta[:t // 3].cpu().numpy()
+        print("region", mode, a, t)
+    np.savez_compressed(os.path.join(out, "region.npz"), **res)
+
+
+def main(out, only=None):
     os.makedirs(out, exist_ok=True)
+    if only == "region":
+        return region(out)
+    region(out)
     # ---- gyroid unit cell, band extraction (config 1 in miniature)
     n = cases.GYROID["n"]
     raw = torch.zeros(n ** 3, device="cuda")
@@ -153,4 +186,4 @@ def main(out):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE), sys.argv[2] if len(sys.argv) > 2 else None)

@@ -7,17 +7,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _lib = None
 
-MODE_LATTICE_ONE, MODE_LATTICE, MODE_CSG, MODE_TOPO = 0, 1, 2, 3
-F_UNION, F_DIFF, F_INTERSECT, F_FIXED, F_DYNAMIC, F_MAKE_REGION, F_DISP = 1, 2, 4, 8, 16, 32, 64
+MODE_LATTICE_ONE, MODE_LATTICE, MODE_CSG, MODE_TOPO, MODE_REGION = 0, 1, 2, 3, 5
+F_UNION, F_DIFF, F_INTERSECT, F_FIXED, F_DYNAMIC, F_MAKE_REGION, F_DISP, F_SHOW_REGION, F_SHOW_DOMAIN = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 GP_DTYPE = np.dtype([("val", np.int32), ("t_x", np.float32), ("t_y", np.float32), ("t_z", np.float32)])
+# triangle_metadata, MarchingCubes_kernel.h:20-32 (64 bytes)
+META_DTYPE = np.dtype([("index", np.uint32), ("voxel", np.uint32), ("l_index", np.uint32), ("edge_1", np.uint32), ("edge_2", np.uint32),
+                       ("edge_3", np.uint32), ("load_group", np.uint32), ("centroid", np.float32, 3), ("normal", np.float32, 3),
+                       ("force_dir", np.float32, 3)])
+assert META_DTYPE.itemsize == 64
 
 
 class McParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("nx", C.c_uint32), ("ny", C.c_uint32), ("nz", C.c_uint32), ("voxel", C.c_float * 3),
                 ("center", C.c_float * 3), ("iso", C.c_float), ("iso1", C.c_float), ("iso2", C.c_float), ("iso1b", C.c_float),
                 ("iso2b", C.c_float), ("flags", C.c_uint32), ("max_verts", C.c_uint32), ("f0", C.c_void_p), ("f1", C.c_void_p),
-                ("f2", C.c_void_p), ("gp", C.c_void_p), ("disp", C.c_void_p)]
+                ("f2", C.c_void_p), ("gp", C.c_void_p), ("disp", C.c_void_p), ("gp2", C.c_void_p), ("meta", C.c_void_p)]
 
 
 def lib():
@@ -48,7 +53,7 @@ def tables():
 
 
 def extract(mode, dims, voxel, center, iso, f0=None, f1=None, f2=None, gp=None, disp=None, iso1=0.0, iso2=0.0, iso1b=0.0, iso2b=0.0,
-            flags=0, max_verts=None, stages=True):
+            flags=0, max_verts=None, stages=True, gp2=None, meta=None):
     """dims = (nx, ny, nz) points.  Returns dict with stage arrays, pos, norm, active, total."""
     nx, ny, nz = dims
     ncell = max((nx - 1) * (ny - 1) * (nz - 1), 1)
@@ -57,8 +62,9 @@ def extract(mode, dims, voxel, center, iso, f0=None, f1=None, f2=None, gp=None, 
     keep = [None if a is None else _f(a) for a in (f0, f1, f2)]
     gpc = None if gp is None else np.ascontiguousarray(gp)
     dispc = None if disp is None else _f(disp)
+    gp2c = None if gp2 is None else np.ascontiguousarray(gp2)
     p = McParams(mode, nx, ny, nz, _v3(voxel), _v3(center), iso, iso1, iso2, iso1b, iso2b, flags, max_verts, _p(keep[0]), _p(keep[1]), _p(keep[2]),
-                 _p(gpc), _p(dispc))
+                 _p(gpc), _p(dispc), _p(gp2c), _p(meta))  # meta: caller-allocated META_DTYPE array (REGION + SHOW_REGION)
     out = {}
     names = ["voxelVerts", "voxelOccupied", "voxelVertsScan", "voxelOccupiedScan", "compVoxelArray"]
     arrs = [np.zeros(ncell, np.uint32) if stages else None for _ in names]

@@ -162,6 +162,16 @@ def isosurface_csg(fix_grid, pos, norm, iso, dims, voxel, center, s, max_verts, 
     return act.value, tot.value
 
 
+def isosurface_region(fix_grid, pos, norm, iso, dims, voxel, center, s, max_verts, vol_topo, fixed_f, dynamic_f, make_region=False, show_region=False,
+                      show_domain=False, triangle_data=None):
+    act, tot = C.c_uint(0), C.c_uint(0)
+    _ok(lib().ref_isosurface_region(int(fix_grid), _p(pos), _p(norm), F(iso), C.c_uint(dims[0]), C.c_uint(dims[1]), C.c_uint(dims[2]), F(voxel[0]),
+                                    F(voxel[1]), F(voxel[2]), F(center[0]), F(center[1]), F(center[2]), *_scr(s), C.c_uint(max_verts), _p(vol_topo),
+                                    _p(fixed_f), _p(dynamic_f), int(make_region), int(show_region), int(show_domain), _p(triangle_data),
+                                    C.byref(act), C.byref(tot)))
+    return act.value, tot.value
+
+
 def isosurface_topo(with_disp_variant, pos, norm, iso, dims, voxel, center, s, max_verts, vol_topo, vol_two, isovalue1, d_result, disp=False, disp_two=None,
                     vol_one=None, d_solid=None):
     act, tot = C.c_uint(0), C.c_uint(0)

@@ -916,3 +916,119 @@ def test_phase_solve_cg_bit_exact_single_and_batched(ctx, dims):
         fi_r, _ = ref.cg(theirs, dims, 7, 1e-9)
         assert fi_c[hi] == fi_r == 7
         assert_bits_equal(capped[hi], theirs, "capped CG %s" % (h,))
+
+
+# ------------------------------------------------------------------ region / domain display
+def _region_inputs(ctx):
+    R = cases.REGION
+    dims, d = R["dims"], R["d"]
+    nx, ny, nz = dims
+    npts = nx * ny * nz
+    f = torch.zeros(npts, device="cuda")
+    vol_topo, vol_one = gp_zeros(npts), gp_zeros(npts)
+    s, c, y = R["topo_sphere"], R["cuboid"], R["dyn_sphere"]
+    g.Modelling(ctx).sphere_with_center(f, s["center"], s["radius"], s["thickness"], nx, ny, nz, *d, False)
+    g.Isosurface(ctx).copy_parameter(0.0, dims, d, vol_topo, f, None, obj_union=True)
+    g.Modelling(ctx).cuboid(f, c["center"], c["angles"], c["xw"], c["yw"], c["zw"], nx, ny, nz, *d)
+    g.Isosurface(ctx).copy_parameter(0.0, dims, d, vol_one, f, None, obj_union=True)
+    dyn = torch.zeros(npts, device="cuda")
+    g.Modelling(ctx).sphere_with_center(dyn, y["center"], y["radius"], y["thickness"], nx, ny, nz, *d, False)
+    return dims, d, vol_topo, vol_one, dyn
+
+
+META_FILL = 0x7f7f7f7f
+
+
+def _meta_view(t, ntri):
+    return t[:ntri].cpu().numpy().view(orc.META_DTYPE).reshape(-1)
+
+
+def compare_region_vs_oracle(mine, o, meta_mine, meta_o, what):
+    """counts / stage arrays / norm.w / integer metadata bit-exact; vertices 1e-5 relative; unit normals 1e-4 absolute where the
+    triangle is not degenerate (rsqrtf of a zero cross product gives NaN on both sides -- the NaN sets must coincide)."""
+    assert (mine["active"], mine["total"]) == (o["active"], o["total"]), what
+    for k in ("voxelVerts", "voxelOccupied", "voxelVertsScan", "voxelOccupiedScan", "compVoxelArray"):
+        assert np.array_equal(mine[k], o[k]), "%s: %s" % (what, k)
+    t = mine["total"]
+    pa, pb = mine["pos"][:t], o["pos"][:t]
+    scale = max(1.0, float(np.abs(pb[:, :3]).max()))
+    assert np.allclose(pa, pb, rtol=0, atol=1e-5 * scale), what
+    na, nb = mine["norm"][:t], o["norm"][:t]
+    assert np.array_equal(na[:, 3], nb[:, 3]), "%s: norm.w (aa)" % what
+    nan_a, nan_b = np.isnan(na[:, :3]).any(axis=1), np.isnan(nb[:, :3]).any(axis=1)
+    # a cross product that is exactly zero on one side is exactly zero on the other (same fp32 operations up to the vertices' ulps);
+    # compare only triangles that are clearly non-degenerate
+    good = ~(nan_a | nan_b)
+    e1 = pb[1::3, :3] - pb[0::3, :3]
+    e2 = pb[2::3, :3] - pb[0::3, :3]
+    area = np.linalg.norm(np.cross(e1.astype(np.float64), e2.astype(np.float64)), axis=1)
+    solid = np.repeat(area > 1e-3, 3) & good
+    assert solid.sum() > 0.5 * t, "%s: too few non-degenerate triangles (%d of %d)" % (what, solid.sum() // 3, t // 3)
+    assert np.allclose(na[solid, :3], nb[solid, :3], rtol=0, atol=1e-4), "%s: normals" % what
+    if meta_mine is not None:
+        for k in ("index", "voxel", "l_index", "edge_1", "edge_2", "edge_3", "load_group"):
+            assert np.array_equal(meta_mine[k], meta_o[k]), "%s: metadata %s" % (what, k)
+        assert np.allclose(meta_mine["centroid"], meta_o["centroid"], rtol=0, atol=1e-5 * scale), "%s: centroid" % what
+        assert np.array_equal(meta_mine["force_dir"].view(np.uint32), meta_o["force_dir"].view(np.uint32)), "%s: force_dir must stay untouched" % what
+
+
+@pytest.mark.parametrize("mode", cases.REGION_MODES)
+def test_region_three_way(ctx, mode):
+    """computeIsosurface_region: classifyVoxel_region cascade, generateTriangles_region vertices / unit normals / aa, triangle_metadata."""
+    dims, d, vol_topo, vol_one, dyn = _region_inputs(ctx)
+    mv = max_verts_for(dims)
+    ncell = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)
+    scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+    meta = torch.full((mv // 3, 16), META_FILL, dtype=torch.int32, device="cuda")
+    act, tot = g.Isosurface(ctx).computeIsosurface_region(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv, vol_topo, vol_one, dyn, triangle_data=meta,
+                                                          **{mode: True})
+    assert tot > 0 and tot % 3 == 0
+    mine = mine_result(scr, mesh, dims, act, tot)
+    aa = set(np.unique(mine["norm"][:tot, 3]).tolist())
+    assert aa == {"make_region": {1.0, 0.25, 0.5}, "show_region": {1.0}, "show_domain": {1.0, 0.25}}[mode], aa  # every cascade level exercised
+    ometa = np.full(mv // 3, 0, orc.META_DTYPE)
+    ometa.view(np.int32)[:] = META_FILL
+    flags = {"make_region": orc.F_MAKE_REGION, "show_region": orc.F_SHOW_REGION, "show_domain": orc.F_SHOW_DOMAIN}[mode]
+    o = orc.extract(orc.MODE_REGION, dims, d, (0, 0, 0), 0.0, f0=dyn.cpu().numpy(), gp=gp_to_numpy(vol_one), gp2=gp_to_numpy(vol_topo), flags=flags, max_verts=mv,
+                    meta=ometa)
+    show = mode == "show_region"
+    compare_region_vs_oracle(mine, o, _meta_view(meta, tot // 3) if show else None, ometa[:tot // 3], "region %s vs oracle" % mode)
+    if not show:  # triangle_data is only written by show_region
+        assert bool((meta == META_FILL).all())
+    if HAVE_REF:
+        scr2, mesh2 = g.Scratch(ncell), g.MeshBuffers(mv)
+        meta2 = torch.full((mv // 3, 16), META_FILL, dtype=torch.int32, device="cuda")
+        a2, t2 = ref.isosurface_region(False, mesh2.pos, mesh2.norm, 0.0, dims, d, (0, 0, 0), scr2, mv, vol_topo, vol_one, dyn, triangle_data=meta2,
+                                       **{mode: True})
+        compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "region %s vs reference" % mode, exact_mesh=True)
+        assert torch.equal(meta, meta2), "region %s: triangle_metadata not bit-identical to the reference" % mode
+
+
+def test_region_needs_a_mode_flag_and_metadata_buffer(ctx):
+    dims, d, vol_topo, vol_one, dyn = _region_inputs(ctx)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)), g.MeshBuffers(mv)
+    with pytest.raises(RuntimeError, match="make_region / show_region / show_domain"):
+        g.Isosurface(ctx).computeIsosurface_region(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv, vol_topo, vol_one, dyn)
+    with pytest.raises(RuntimeError, match="triangle_data"):
+        g.Isosurface(ctx).computeIsosurface_region(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv, vol_topo, vol_one, dyn, show_region=True)
+
+
+def test_region_metadata_written_past_max_verts(ctx):
+    """the reference writes triangle_data outside the `index < maxVerts - 3` guard (MarchingCubes_kernel.cu:2528-2584)."""
+    dims, d, vol_topo, vol_one, dyn = _region_inputs(ctx)
+    mv_full = max_verts_for(dims)
+    ncell = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)
+    scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv_full)
+    meta = torch.full((mv_full // 3, 16), META_FILL, dtype=torch.int32, device="cuda")
+    act, tot = g.Isosurface(ctx).computeIsosurface_region(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv_full, vol_topo, vol_one, dyn, show_region=True,
+                                                          triangle_data=meta)
+    small = 300  # capacity in vertices, far below tot
+    assert tot > small
+    mesh2 = g.MeshBuffers(mv_full)
+    meta2 = torch.full((mv_full // 3, 16), META_FILL, dtype=torch.int32, device="cuda")
+    a2, t2 = g.Isosurface(ctx).computeIsosurface_region(mesh2.pos, mesh2.norm, 0.0, scr, dims, d, (0, 0, 0), small, vol_topo, vol_one, dyn, show_region=True,
+                                                        triangle_data=meta2)
+    assert (a2, t2) == (act, tot)
+    assert torch.equal(meta, meta2)
+    assert torch.equal(mesh.pos[:small - 3], mesh2.pos[:small - 3]) and bool((mesh2.pos[small - 3:] == 0).all())

@@ -130,3 +130,37 @@ def test_phase_solve_against_reference_kernels():
         x, fi, fr = orc.cg(G["rhs_r2_%d" % hi], dims, P["iters"], P["end_res"])
         assert fi == int(G["iters_%d" % hi]) and np.float32(fr) == G["res_%d" % hi]
         assert np.array_equal(x.view(np.uint32), G["sol_%d" % hi].view(np.uint32)), "CG solution of harmonic %s" % (h,)
+
+
+@pytest.mark.parametrize("mode", cases.REGION_MODES)
+def test_region_matches_reference(mode):
+    """computeIsosurface_region on the reference's own retained grids: cascade / counts / stage arrays / aa / integer
+    metadata bit-exact, vertices 1e-5 relative, unit normals 1e-4 (rsqrtf is MUFU.RSQ on the GPU, 1/sqrtf here)."""
+    gd = load("region")
+    R = cases.REGION
+    dims, d = R["dims"], R["d"]
+    gp = np.ascontiguousarray(gd["vol_one"]).view(orc.GP_DTYPE).reshape(-1)
+    gp2 = np.ascontiguousarray(gd["vol_topo"]).view(orc.GP_DTYPE).reshape(-1)
+    flags = {"make_region": orc.F_MAKE_REGION, "show_region": orc.F_SHOW_REGION, "show_domain": orc.F_SHOW_DOMAIN}[mode]
+    tot = int(gd[mode + "_total"])
+    meta = np.zeros(max(tot // 3, 1), orc.META_DTYPE)
+    meta.view(np.int32)[:] = 0x7f7f7f7f
+    o = orc.extract(orc.MODE_REGION, dims, d, (0, 0, 0), 0.0, f0=gd["dynamic"], gp=gp, gp2=gp2, flags=flags, meta=meta)
+    assert (o["active"], o["total"]) == (int(gd[mode + "_active"]), tot)
+    for k in ("voxelVerts", "voxelOccupied", "voxelVertsScan", "voxelOccupiedScan", "compVoxelArray"):
+        assert np.array_equal(o[k], gd[mode + "_" + k]), k
+    pos, norm = gd[mode + "_pos"], gd[mode + "_norm"]
+    scale = max(1.0, float(np.abs(pos[:, :3]).max()))
+    assert np.allclose(o["pos"][:tot], pos, rtol=0, atol=1e-5 * scale)
+    assert np.array_equal(o["norm"][:tot, 3], norm[:, 3])
+    e1, e2 = (pos[1::3, :3] - pos[0::3, :3]).astype(np.float64), (pos[2::3, :3] - pos[0::3, :3]).astype(np.float64)
+    solid = np.repeat(np.linalg.norm(np.cross(e1, e2), axis=1) > 1e-3, 3)
+    assert solid.sum() > 0.5 * tot
+    assert np.allclose(o["norm"][:tot][solid, :3], norm[solid, :3], rtol=0, atol=1e-4)
+    gm = np.ascontiguousarray(gd[mode + "_meta"]).view(orc.META_DTYPE).reshape(-1)
+    if mode == "show_region":
+        for k in ("index", "voxel", "l_index", "edge_1", "edge_2", "edge_3", "load_group"):
+            assert np.array_equal(meta[:tot // 3][k], gm[k]), k
+        assert np.allclose(meta[:tot // 3]["centroid"], gm["centroid"], rtol=0, atol=1e-5 * scale)
+    else:
+        assert (gm.view(np.int32) == 0x7f7f7f7f).all()  # the reference leaves triangle_data alone outside show_region
