@@ -66,7 +66,8 @@ struct McArgs {
     uint32_t prow_stride;          // floats between the two staged slices in smem ( (R+1)*nx rounded )
     int use_tma;
     int count_only;
-    uint32_t magic_cx_mul, magic_cx_shift;  // c / cx == (c * mul) >> shift for c < 2^28
+    uint32_t ppr, cpr;                      // 128-point chunks per staged row, 128-cell chunks per cell row
+    uint32_t cstride;                       // bytes between cell rows of the cube-index array in smem (128 * cpr)
     float snap_thr;                         // smallest float >= 0.0005 (endpoint snapping threshold)
 };
 

@@ -10,20 +10,26 @@
 // A tile is R consecutive y-rows of one z-slice = a CONTIGUOUS range of R*(Nx-1) linear cell ids,
 // and tiles are numbered in the same linear order.  Per tile:
 //   1. stage-in : the interpolation field rows [y0, y0+R] of point slices z and z+1 are copied
-//                 global -> shared with TMA bulk copies (cp.async.bulk + mbarrier); each staged
-//                 point is turned into {value, inside-bit, id-class} (mode specific);
-//   2. classify : cube index per cell from the staged bits, vertex count from the table (smem
-//                 copy of the __constant__ table: per-lane indices diverge), warp/block totals;
+//                 global -> shared with TMA bulk copies (cp.async.bulk + mbarrier); a warp turns 128
+//                 staged points at a time into values + inside bits, and the bits leave the warp as
+//                 four ballot words = a contiguous bit mask of the row (16 bytes per 128 points);
+//   2. classify : a warp classifies 128 cells of a row per step, four consecutive cells per lane:
+//                 five mask bits per (slice, row) come from one funnel shift, the four cube indices
+//                 are assembled as the bytes of one word (bit spreading by multiply), a step whose
+//                 masks are all-0 / all-1 is skipped after the mask test (empty space costs ~25
+//                 instructions per 128 cells); vertex counts from a shared-memory table;
 //   3. look-back: single-pass decoupled look-back over tiles publishes {active, vertex} prefixes,
 //                 so offsets are exactly the reference's exclusive scans;
-//   4. emit     : active cells append their triangles to a per-warp queue; the warp drains the
-//                 queue 32 triangles at a time (one triangle per lane, vertices interpolated from
-//                 the STAGED field) and writes float4 pos/norm at the reference's indices.
+//   4. emit     : non-empty steps scan their triangle counts (one packed warp scan per 128 cells),
+//                 append their triangles to a per-warp ring; the warp drains the ring 32 triangles at
+//                 a time (one triangle per lane, vertices interpolated from the STAGED field) and
+//                 writes float4 pos/norm at the reference's indices.
 // The field is read from HBM once; no per-cell scratch arrays are written (the reference moves
 // 36-56 B/cell through them).
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace gcb {
 
@@ -111,17 +117,19 @@ __device__ __forceinline__ uint32_t edge_axis(uint32_t e) { return e >= 8 ? 2u :
 
 struct Smem {
     float* val[2];
-    unsigned char* bit[2];
-    unsigned char* cube;
-    unsigned char* cls;   // M_REGION: which cascade level produced the cube index (0: vol_topo, 1: second test, 2: third test)
+    unsigned char* idb[2];  // lattice modes: id class of the mask value per staged point (0:==0, 1:==1, 2:==2, 3:other)
+    uint32_t* plane;        // inside bits: [plane][slice][staged row][128-point chunk][4 words], bit x%128 of a row chunk
+    unsigned char* cube;    // cube index per cell, [row][cstride]
+    unsigned char* cls;     // M_REGION: which cascade level produced the cube index (0: vol_topo, 1: second test, 2: third test)
     unsigned long long* tri;
-    unsigned char* nv;
+    unsigned short* nv;     // numVertsTable[c] | (numVertsTable[c] > 0) << 8
     uint32_t* queue;      // kWarps * kQueue
     uint32_t* warp_tot;   // kWarps * 2
     unsigned long long* prefix;  // [0]=active prefix, [1]=vertex prefix (exclusive, for this tile)
     uint32_t* tile_id;
     uint64_t* mbar;
-    unsigned char* edge;  // [0..11] lattice edge order, [16..27] owner edge order: corner bits ca | cb << 3
+    uint2* edge;          // [0..11] lattice edge order, [16..27] owner edge order.  x: corner bits ca | cb << 3;
+                          // y: staged-point offsets of the two endpoints from the cell's (x, y, z) point, a | b << 16 (slice z+1 = + prow_stride)
 };
 
 __device__ __forceinline__ float3 lerp3(float3 a, float3 b, float t) {
@@ -139,13 +147,22 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {  // helper_math.h
 // `fabs(d) < 0.0005` in the reference compares a float against a double literal; kSnap is the smallest float whose value is
 // >= 0.0005, so `fabsf(d) < kSnap` decides identically for every float d without leaving the FP32 pipe.
 __device__ __forceinline__ bool snap(float d, float thr) { return fabsf(d) < thr; }
-__device__ __forceinline__ float3 interp_band(float thr, float l1, float l2, float3 p0, float3 p1, float f0, float f1, uint32_t id0, uint32_t id1) {
-    // Branch-free restatement (lanes of a warp hold unrelated edges, so every if/else of the reference would serialise):
-    // all candidates are computed, the reference's decision tree only selects.
-    const bool crossing = (id0 == 1u && id1 == 0u) || (id0 == 0u && id1 == 1u);
+// Cell edges are axis aligned: the endpoints p0, p1 the reference hands to vertexInterp2_new differ in ONE coordinate.  Its
+// lerp `a + t*(b-a)` leaves the other two untouched (a + t*0 == a for every finite t and a != -0; positions are never -0),
+// the snap branches return an endpoint as a whole, and the only non-finite t this function can produce (0/0 when lo == hi ==
+// level) is overridden by the first snap test.  So only the coordinate ALONG the edge is interpolated: a / b are that
+// coordinate at the two endpoints, za / zb their z coordinates (the reference's `p0.z == 0` special case looks at z).
+// Branch-free (lanes of a warp hold unrelated edges): all candidates are computed, the reference's decision tree only selects.
+// CHECK_IDS: the id test of the reference (mask ids {1,0}); M_BAND_RAW builds the mask in-kernel from the band test, there an
+// edge named by the triangle table joins a point with mask 0 to a point with mask 1 (the cube bits ARE "mask < iso" and the
+// mask only takes the values 0 and 1), so the test is true for every edge that gets here and the ids are not even staged.
+template <bool CHECK_IDS>
+__device__ __forceinline__ float interp_band_axis(float thr, float l1, float l2, float a, float b, float za, float zb, float f0, float f1, uint32_t id0,
+                                                  uint32_t id1) {
+    const bool crossing = !CHECK_IDS || (id0 == 1u && id1 == 0u) || (id0 == 0u && id1 == 1u);
     const bool sw = f1 < f0;
     const float lo = sw ? f1 : f0, hi = sw ? f0 : f1;
-    const float3 plo = sw ? p1 : p0, phi = sw ? p0 : p1;
+    const float clo = sw ? b : a, chi = sw ? a : b, zlo = sw ? zb : za;
     const bool c1 = (hi >= l1) && (lo <= l1);
     const bool c2 = !c1 && (hi >= l2) && (lo <= l2);
     const float lv = c1 ? l1 : l2;
@@ -153,36 +170,14 @@ __device__ __forceinline__ float3 interp_band(float thr, float l1, float l2, flo
     const bool s_lo = snap(dn, thr) || (!snap(__fsub_rn(lv, hi), thr) && snap(dd, thr));  // -> p0 (1st or 3rd test)
     const bool s_hi = !snap(dn, thr) && snap(__fsub_rn(lv, hi), thr);                        // -> p1 (2nd test)
     float t = __fdiv_rn(dn, dd);
-    if (!(c1 || c2)) t = (hi == lo && plo.z == 0.0f) ? 1.f : 0.f;  // reference: t = 1 / t = 0 / (unset -> 0 here)
+    if (!(c1 || c2)) t = (hi == lo && zlo == 0.0f) ? 1.f : 0.f;  // reference: t = 1 / t = 0 / (unset -> 0 here)
     if (!crossing) t = 0.f;
     // without a crossing the reference lerps the UNSWAPPED endpoints with t = 0, i.e. returns p0 + 0*(p1-p0)
-    const float3 a = crossing ? plo : p0, bb = crossing ? phi : p1;
-    float3 r = lerp3(a, bb, t);
+    const float ea = crossing ? clo : a, eb = crossing ? chi : b;
+    float r = __fmaf_rn(__fsub_rn(eb, ea), t, ea);  // lerp, helper_math.h:1145-1148 as the reference build contracts it
     if (crossing && (c1 || c2)) {
-        if (s_lo) r = plo;
-        else if (s_hi) r = phi;
-    }
-    return r;
-}
-// The same for M_BAND_RAW, where the mask is built in-kernel from the band test: an edge named by the triangle table joins
-// a point with mask 0 to a point with mask 1 (the cube bits ARE "mask < iso" and the mask only takes the values 0 and 1), so
-// the reference's id test is true for every edge that reaches this function and the ids need not be staged or looked at.
-__device__ __forceinline__ float3 interp_band_crossing(float thr, float l1, float l2, float3 p0, float3 p1, float f0, float f1) {
-    const bool sw = f1 < f0;
-    const float lo = sw ? f1 : f0, hi = sw ? f0 : f1;
-    const float3 plo = sw ? p1 : p0, phi = sw ? p0 : p1;
-    const bool c1 = (hi >= l1) && (lo <= l1);
-    const bool c2 = !c1 && (hi >= l2) && (lo <= l2);
-    const float lv = c1 ? l1 : l2;
-    const float dn = __fsub_rn(lv, lo), dd = __fsub_rn(hi, lo);
-    const bool s_lo = snap(dn, thr) || (!snap(__fsub_rn(lv, hi), thr) && snap(dd, thr));
-    const bool s_hi = !snap(dn, thr) && snap(__fsub_rn(lv, hi), thr);
-    float t = __fdiv_rn(dn, dd);
-    if (!(c1 || c2)) t = (hi == lo && plo.z == 0.0f) ? 1.f : 0.f;
-    float3 r = lerp3(plo, phi, t);
-    if (c1 || c2) {
-        if (s_lo) r = plo;
-        else if (s_hi) r = phi;
+        if (s_lo) r = clo;
+        else if (s_hi) r = chi;
     }
     return r;
 }
@@ -264,10 +259,24 @@ __device__ __forceinline__ float div_by_uniform(float n, const UniformDiv& u) {
     return q2;
 }
 
+// What one point needs from global memory besides the TMA-staged field: fetched ahead of use (stage_fetch), turned into
+// {value, bits} later (stage_point), so a warp keeps the loads of its next 128 points in flight while it evaluates the current ones.
 template <int MODE>
-__device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& nd, size_t gi, uint32_t x, bool row_face, float raw, float& val, uint32_t& bits) {
+__device__ __forceinline__ void stage_fetch(const McArgs& A, size_t gi, float& a, float& b) {
+    if (MODE == M_LATTICE_ONE || MODE == M_LATTICE) a = __ldg(A.f1 + gi);  // mask `vol`
+    else if (MODE == M_REGION) {
+        a = A.gp2 ? (float)A.gp2[gi].val : 0.f;  // sampleVolume_2 :98-108
+        b = A.gp ? (float)A.gp[gi].val : 0.f;
+    } else if (MODE == M_TOPO) a = A.gp ? (float)A.gp[gi].val : 0.f;
+    else if (MODE == M_CSG) {
+        a = A.gp ? (float)A.gp[gi].val : 0.f;
+        if ((A.flags & (F_FIXED | F_DYNAMIC)) && A.f1) b = __ldg(A.f1 + gi);
+    }
+}
+template <int MODE>
+__device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& nd, uint32_t x, bool row_face, float raw, float in_a, float in_b, float& val, uint32_t& bits) {
     if (MODE == M_LATTICE_ONE || MODE == M_LATTICE) {
-        const float m = __ldg(A.f1 + gi);  // mask `vol`; classifyVoxel_new :3232-3239
+        const float m = in_a;  // classifyVoxel_new :3232-3239
         uint32_t id = (m == 1.f) ? 1u : (m == 0.f) ? 0u : (m == 2.f) ? 2u : 3u;
         bits = id | ((m < A.iso) ? 4u : 0u);
         val = raw;  // k `vol_one`
@@ -282,22 +291,20 @@ __device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& n
     } else if (MODE == M_REGION) {
         // classifyVoxel_region_kernel :1163-1290: three candidate inside tests per point, the cascade is resolved per cell
         const float iso = A.iso;
-        const float ft = A.gp2 ? (float)A.gp2[gi].val : 0.f;  // sampleVolume_2 :98-108
-        const float fx = A.gp ? (float)A.gp[gi].val : 0.f;
+        const float ft = in_a, fx = in_b;
         bits = ((ft < iso) ? 4u : 0u) | ((fx < iso) ? 8u : 0u) | (((fx < iso) & (raw < iso)) ? 16u : 0u);
         val = raw;  // primitive_dynamic
     } else if (MODE == M_TOPO) {
         // classifyVoxel_kernel_topo :1492-1499
-        const float fx = A.gp ? (float)A.gp[gi].val : 0.f;
+        const float fx = in_a;
         bits = ((fx < A.iso1) | (raw >= A.iso)) ? 4u : 0u;
         val = raw;
     } else {  // M_CSG  classifyVoxel :922-1052
         const float iso = A.iso;
-        const float fx = A.gp ? (float)A.gp[gi].val : 0.f;
+        const float fx = in_a;
         const float dy = raw;
         const bool fixed = A.flags & F_FIXED, dyn = A.flags & F_DYNAMIC;
-        float la = 0.f;
-        if ((fixed || dyn) && A.f1) la = __ldg(A.f1 + gi);
+        const float la = in_b;
         const bool inb = (la > A.iso1) & (la < A.iso2);
         bool b = false;
         if (A.flags & F_MAKE_REGION) b = fx < iso;
@@ -310,11 +317,14 @@ __device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& n
 }
 
 // ---------------------------------------------------------------- one triangle
+// ring entry: triangle number within the cell << 29 | tile row << 16 | x
 template <int MODE>
-__device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, uint32_t z, uint32_t y0, uint32_t c, uint32_t j,
-                                              unsigned long long vidx) {
-    const uint32_t r = (uint32_t)(((unsigned long long)c * A.magic_cx_mul) >> A.magic_cx_shift), x = c - r * A.cx;  // c / cx, exact for c < 2^28
-    const uint32_t cube = S.cube[c];
+__device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, uint32_t z, uint32_t y0, uint32_t ent, unsigned long long vidx) {
+    float3 v[3], n;
+    float w[3];
+    const uint32_t j = ent >> 29, r = (ent >> 16) & 0x1fffu, x = ent & 0xffffu;
+    const uint32_t c = r * A.cx + x;  // cell id within the tile
+    const uint32_t cube = S.cube[r * A.cstride + x];
     const unsigned long long tri = S.tri[cube];
     const uint32_t y = y0 + r;
     // MarchingCubes_kernel.cu:1888-1890 : (uint -> float) - center, times voxel
@@ -323,27 +333,55 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
 
     const float3 pmax = make_float3(__fadd_rn(p.x, A.voxel.x), __fadd_rn(p.y, A.voxel.y), __fadd_rn(p.z, A.voxel.z));
     const uint32_t sbase = r * A.nx + x;
-    float3 v[3];
-    float w[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const uint32_t e = (uint32_t)(tri >> (4 * (3 * j + k))) & 15u;
         const bool own = (MODE == M_TOPO) || (MODE == M_REGION) || (MODE == M_CSG && !(A.flags & F_FIXED));
-        const uint32_t ab = S.edge[(own ? 16u : 0u) + e];
-        const uint32_t ca = ab & 7u, cb = ab >> 3;
+        const uint2 ed = S.edge[(own ? 16u : 0u) + e];
+        const uint32_t ca = ed.x & 7u, cb = ed.x >> 3;
         // corner positions: v[0] = p, v[i] = p + (voxel or 0) per component (:1892-1900).  p + 0.0f == p bit for bit for every
         // p this kernel can produce (x - center is never -0, voxel sizes are positive), so each component is a select.
         const float3 pa = make_float3((ca & 1u) ? pmax.x : p.x, (ca & 2u) ? pmax.y : p.y, (ca & 4u) ? pmax.z : p.z);
-        const float3 pb = make_float3((cb & 1u) ? pmax.x : p.x, (cb & 2u) ? pmax.y : p.y, (cb & 4u) ? pmax.z : p.z);
-        const uint32_t sa = sbase + ((ca & 2u) ? A.nx : 0u) + (ca & 1u), sb = sbase + ((cb & 2u) ? A.nx : 0u) + (cb & 1u);
+        const uint32_t sa = sbase + (ed.y & 0xffffu), sb = sbase + (ed.y >> 16);  // both staged slices are one array: val[1] == val[0] + prow_stride
         const uint32_t za = (ca >> 2) & 1u, zb = (cb >> 2) & 1u;
-        const float fa = (za ? S.val[1] : S.val[0])[sa], fb = (zb ? S.val[1] : S.val[0])[sb];
+        const float fa = S.val[0][sa], fb = S.val[0][sb];
         w[k] = 0.f;
+        if (MODE == M_BAND_RAW || MODE == M_LATTICE_ONE || MODE == M_LATTICE) {
+            // band interpolation along the edge's axis (see interp_band_axis)
+            const uint32_t ax = ca ^ cb;  // 1: x, 2: y, 4: z
+            const float c0 = ax == 1u ? p.x : ax == 2u ? p.y : p.z, c1 = ax == 1u ? pmax.x : ax == 2u ? pmax.y : pmax.z;
+            const float ea = (ca & ax) ? c1 : c0, eb = (cb & ax) ? c1 : c0;
+            const float pzb = (cb & 4u) ? pmax.z : p.z;
+            uint32_t ida = 0, idb = 0;
+            if (MODE != M_BAND_RAW) { ida = S.idb[0][sa]; idb = S.idb[0][sb]; }  // idb[1] == idb[0] + prow_stride
+            bool done = false;
+            if (MODE == M_LATTICE) {
+                if ((ida == 2u && idb == 0u) || (idb == 2u && ida == 0u)) {
+                    // ids {2,0}: first block of vertexInterp3_new does not fire, second one does
+                    const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
+                    const size_t gb = ((size_t)(z + zb) * A.ny + y + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
+                    const float3 pb = make_float3((cb & 1u) ? pmax.x : p.x, (cb & 2u) ? pmax.y : p.y, (cb & 4u) ? pmax.z : p.z);
+                    float t = 0.f;
+                    float3 out;
+                    float3 q0 = pa, q1 = pb;
+                    if (interp_band_two(A.snap_thr, A.iso1b, A.iso2b, q0, q1, __ldg(A.f2 + ga), __ldg(A.f2 + gb), t, out)) v[k] = out;
+                    else v[k] = lerp3(q0, q1, t);
+                    done = true;
+                }
+            }
+            if (!done) {
+                const float rr = (MODE == M_BAND_RAW) ? interp_band_axis<false>(A.snap_thr, A.iso1, A.iso2, ea, eb, pa.z, pzb, fa, fb, 0u, 0u)
+                                                      : interp_band_axis<true>(A.snap_thr, A.iso1, A.iso2, ea, eb, pa.z, pzb, fa, fb, ida, idb);
+                v[k] = make_float3(ax == 1u ? rr : pa.x, ax == 2u ? rr : pa.y, ax == 4u ? rr : pa.z);
+            }
+            continue;
+        }
+        const float3 pb = make_float3((cb & 1u) ? pmax.x : p.x, (cb & 2u) ? pmax.y : p.y, (cb & 4u) ? pmax.z : p.z);
         if (MODE == M_REGION) {
             // generateTriangles_region_kernel :2391-2490: stored crossing parameter of the edge's owning point, from vol_topo
             // (first test fired) or primitive_fixed; make_region's second test blends it with the dynamic field's crossing
             const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
-            const uint32_t cl = S.cls[c];
+            const uint32_t cl = S.cls[r * A.cstride + x];
             const GridPoint* src = cl == 0u ? A.gp2 : A.gp;
             float et = 0.f;
             if (src) {
@@ -354,22 +392,6 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
             const float t = (cl == 1u && !(A.flags & F_SHOW_DOMAIN)) ? t_primitive(A.iso, fa, fb, et) : et;
             v[k] = lerp3(pa, pb, t);
             w[k] = cl == 0u ? 1.0f : cl == 1u ? 0.25f : 0.5f;  // `aa`
-        } else if (MODE == M_BAND_RAW) {
-            v[k] = interp_band_crossing(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb);
-        } else if (MODE == M_LATTICE_ONE) {
-            v[k] = interp_band(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb, ((za ? S.bit[1] : S.bit[0])[sa] & 3u), ((zb ? S.bit[1] : S.bit[0])[sb] & 3u));
-        } else if (MODE == M_LATTICE) {
-            const uint32_t ida = ((za ? S.bit[1] : S.bit[0])[sa] & 3u), idb = ((zb ? S.bit[1] : S.bit[0])[sb] & 3u);
-            if ((ida == 2u && idb == 0u) || (idb == 2u && ida == 0u)) {
-                // ids {2,0}: first block of vertexInterp3_new does not fire, second one does
-                const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
-                const size_t gb = ((size_t)(z + zb) * A.ny + y + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
-                float t = 0.f;
-                float3 out;
-                float3 q0 = pa, q1 = pb;
-                if (interp_band_two(A.snap_thr, A.iso1b, A.iso2b, q0, q1, __ldg(A.f2 + ga), __ldg(A.f2 + gb), t, out)) v[k] = out;
-                else v[k] = lerp3(q0, q1, t);
-            } else v[k] = interp_band(A.snap_thr, A.iso1, A.iso2, pa, pb, fa, fb, ida, idb);
         } else {
             const size_t ga = ((size_t)(z + za) * A.ny + y + ((ca >> 1) & 1u)) * A.nx + x + (ca & 1u);
             const size_t gb = ((size_t)(z + zb) * A.ny + y + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
@@ -396,7 +418,6 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
             v[k] = lerp3(qa, qb, t);
         }
     }
-    float3 n;
     if (MODE == M_CSG) {  // calcNormal(ver0, ver2, ver1), w = 0.5 (:2178-2185)
         n = cross3(sub3(v[2], v[0]), sub3(v[1], v[0]));
         w[0] = w[1] = w[2] = 0.5f;
@@ -437,10 +458,30 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
+template <int MODE> struct ModeTraits {
+    static constexpr int kPlanes = (MODE == M_REGION) ? 3 : 1;                          // inside tests per point
+    static constexpr bool kIds = (MODE == M_LATTICE_ONE || MODE == M_LATTICE);          // emission looks at mask ids
+#ifndef GCB_MC_MINB
+#define GCB_MC_MINB 4
+#endif
+    static constexpr int kMinBlocks = (MODE == M_BAND_RAW) ? GCB_MC_MINB : 3;  // CTAs per SM the register budget allows
+};
+// bit u of a 4-bit value -> bit 8u (the four partial products land on distinct bits, so the multiply cannot carry)
+__device__ __forceinline__ uint32_t spread4(uint32_t n) { return (n * 0x00204081u) & 0x01010101u; }
+// the four cube indices of four consecutive cells of a row as the bytes of one word.  n00/n01: five consecutive inside bits
+// (points x..x+4) of rows y / y+1 in slice z, n10/n11 the same in slice z+1.  Corner order MarchingCubes_kernel.cu:889-896.
+__device__ __forceinline__ uint32_t cubes4(uint32_t n00, uint32_t n01, uint32_t n10, uint32_t n11) {
+    return spread4(n00 & 15u) | (spread4(n00 >> 1) << 1) | (spread4(n01 >> 1) << 2) | (spread4(n01 & 15u) << 3) | (spread4(n10 & 15u) << 4) |
+           (spread4(n10 >> 1) << 5) | (spread4(n11 >> 1) << 6) | (spread4(n11 & 15u) << 7);
+}
+
+// TMA: the interpolation field is staged by bulk copies (rows 16-byte aligned: nx % 4 == 0); otherwise through LDG.
+template <int MODE, bool TMA>
+__global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fused_kernel(const McArgs A) {
+    constexpr int NP = ModeTraits<MODE>::kPlanes;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem S;
+    const uint32_t R1 = A.rows_per_tile + 1;  // staged rows per slice
     {
         unsigned char* p = smem_raw;
         S.val[0] = (float*)p; p += (size_t)A.prow_stride * 4;
@@ -449,14 +490,15 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
         S.prefix = (unsigned long long*)p; p += 16;
         S.mbar = (uint64_t*)p; p += 8;
         S.tile_id = (uint32_t*)p; p += 8;
-        S.edge = p; p += 32;
+        S.edge = (uint2*)p; p += 32 * 8;
         S.queue = (uint32_t*)p; p += kWarps * kQueue * 4;
         S.warp_tot = (uint32_t*)p; p += kWarps * 2 * 4;
-        S.nv = p; p += 256;
-        S.bit[0] = p; p += A.prow_stride;
-        S.bit[1] = p; p += A.prow_stride;
-        S.cube = p; p += (size_t)A.rows_per_tile * A.cx;
-        S.cls = p;  // only backed by shared memory in M_REGION launches
+        S.nv = (unsigned short*)p; p += 512;
+        S.plane = (uint32_t*)p; p += (size_t)NP * 2 * R1 * A.ppr * 16 + 16;
+        S.cube = p; p += (size_t)A.rows_per_tile * A.cstride;
+        S.cls = p; if (MODE == M_REGION) p += (size_t)A.rows_per_tile * A.cstride;
+        S.idb[0] = p; if (ModeTraits<MODE>::kIds) p += A.prow_stride;
+        S.idb[1] = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
@@ -466,12 +508,18 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
         // number of used nibbles = numVertsTable[i]
         unsigned long long u = ~t;                      // used nibble != 0xF  <=> ~nibble != 0
         u = (u | (u >> 1) | (u >> 2) | (u >> 3)) & 0x1111111111111111ull;
-        S.nv[i] = (unsigned char)__popcll(u);
+        const uint32_t n = (uint32_t)__popcll(u);
+        S.nv[i] = (unsigned short)(n | (n ? 256u : 0u));
     }
     if (tid < 12) {
         const uint32_t l = edge_lat(tid), o = edge_own(tid);
-        S.edge[tid] = (unsigned char)(corner_bits(l & 15u) | (corner_bits(l >> 4) << 3));
-        S.edge[16 + tid] = (unsigned char)(corner_bits(o & 15u) | (corner_bits(o >> 4) << 3));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t ab = t ? o : l, ca = corner_bits(ab & 15u), cb = corner_bits(ab >> 4);
+            const uint32_t oa = ((ca & 4u) ? A.prow_stride : 0u) + ((ca & 2u) ? A.nx : 0u) + (ca & 1u);
+            const uint32_t ob = ((cb & 4u) ? A.prow_stride : 0u) + ((cb & 2u) ? A.nx : 0u) + (cb & 1u);
+            S.edge[16 * t + tid] = make_uint2(ca | (cb << 3), oa | (ob << 16));
+        }
     }
     if (tid == 0) { mbar_init(S.mbar, 1); fence_mbar_init(); }
     __syncthreads();
@@ -479,6 +527,9 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
     uint32_t parity = 0;
     const uint32_t slice_pts = A.nx * A.ny;
     const UniformDiv nd = make_uniform_div(__fsub_rn(A.nb, A.na));  // M_BAND_RAW normalisation range
+    const uint32_t ppr = A.ppr, cpr = A.cpr;
+    const uint32_t plane_words = 2u * R1 * ppr * 4u;  // words per bit plane
+    constexpr bool tma = TMA;
 
     for (;;) {
         if (tid == 0) *S.tile_id = atomicAdd(A.tile_counter, 1u);
@@ -489,11 +540,10 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
         const uint32_t y0 = ty * A.rows_per_tile;
         const uint32_t rows = min(A.rows_per_tile, A.cy - y0);
         const uint32_t npts = (rows + 1) * A.nx;   // staged points per slice
-        const uint32_t ncell = rows * A.cx;
         const size_t g0 = (size_t)z * slice_pts + (size_t)y0 * A.nx;  // first staged point, slice z
 
         // ---- 1. stage-in
-        if (A.use_tma && A.f0) {
+        if (TMA) {
             if (tid == 0) {
                 fence_proxy_async();  // generic-proxy accesses of the previous tile precede the async writes
                 mbar_expect_tx(S.mbar, 2u * npts * 4u);
@@ -503,83 +553,188 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
             mbar_wait(S.mbar, parity);
             parity ^= 1u;
         }
-#pragma unroll 1
-        for (uint32_t s = 0; s < 2; ++s) {
-            float* sv = s ? S.val[1] : S.val[0];
-            unsigned char* sb = s ? S.bit[1] : S.bit[0];
-            const size_t gs = g0 + (size_t)s * slice_pts;
-            for (uint32_t rr = warp; rr <= rows; rr += kWarps) {
+        if (MODE == M_BAND_RAW && TMA) {
+            // the hot configuration: raw field staged by TMA, normalisation + domain faces + band test fused in.  Work item = 128 points
+            // of one staged row, dealt round-robin to the warps; lane l takes points 4l .. 4l+3 (one LDS.128 / STS.128), its four
+            // inside bits form a nibble, and an OR over each group of eight lanes assembles the 32-point words of the row's bit mask.
+            const uint32_t lim = 2u * (rows + 1u);
+            const bool in0 = 0.f < A.iso, in1 = 1.f < A.iso;  // "mask < iso" for the two values the mask takes
+            uint32_t k = warp % ppr, rs = warp / ppr;         // rs: staged row over both slices, [0, lim)
+            while (rs < lim) {
+                const uint32_t s = rs > rows ? 1u : 0u, rr = rs - s * (rows + 1u);
+                float* sv = (s ? S.val[1] : S.val[0]) + rr * A.nx;
                 const uint32_t yy = y0 + rr, gz = z + s + A.gz0;
                 const bool row_face = yy == 0 || yy == A.ny - 1 || gz == 0 || gz == A.gnz - 1;  // domain faces in GLOBAL coordinates
-                if (A.use_tma && A.f0) {
-                    // TMA path: nx % 4 == 0 and rows are 16-byte aligned in shared memory -> four points per lane and iteration
-                    for (uint32_t x = lane * 4; x < A.nx; x += 128) {
-                        const uint32_t pnt = rr * A.nx + x;
-                        float4 v4 = *reinterpret_cast<const float4*>(sv + pnt);
-                        float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-                        uint32_t packed = 0;
+                const uint32_t x = 128u * k + 4u * lane;
+                uint32_t nib = 0;
+                if (x < A.nx) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(sv + x);
+                    float nn[4] = {__fsub_rn(v4.x, A.na), __fsub_rn(v4.y, A.na), __fsub_rn(v4.z, A.na), __fsub_rn(v4.w, A.na)}, kk[4];
+                    bool fast = nd.ok;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float val;
-                            uint32_t bits;
-                            stage_point<MODE>(A, nd, gs + pnt + u, x + u, row_face, vv[u], val, bits);
-                            vv[u] = val;
-                            packed |= bits << (8 * u);
-                        }
-                        *reinterpret_cast<float4*>(sv + pnt) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                        *reinterpret_cast<uint32_t*>(sb + pnt) = packed;
+                    for (int u = 0; u < 4; ++u) {  // div_by_uniform, the four range checks folded into one branch
+                        const float q0 = __fmul_rn(nn[u], nd.y);
+                        const float r0 = __fmaf_rn(-q0, nd.d, nn[u]);
+                        const float q1 = __fmaf_rn(r0, nd.y, q0);
+                        const float r1 = __fmaf_rn(-q1, nd.d, nn[u]);
+                        kk[u] = __fmaf_rn(r1, nd.y, q1);
+                        fast = fast && fabsf(nn[u]) >= 1.0e-30f && fabsf(kk[u]) >= 1.0e-30f && fabsf(kk[u]) <= 1.0e30f;
                     }
-                    continue;
+                    if (!fast) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) kk[u] = div_by_uniform(nn[u], nd);
+                    }
+                    // device_bufferfour (Gratings.cu:1089-1134): band mask, the six domain faces forced to k = 0, m = 0
+                    bool m[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) m[u] = (kk[u] >= A.iso1) && (kk[u] <= A.iso2);
+                    if (row_face) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { kk[u] = 0.f; m[u] = false; }
+                    }
+                    if (x == 0u) { kk[0] = 0.f; m[0] = false; }
+                    if (x + 4u == A.nx) { kk[3] = 0.f; m[3] = false; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) nib |= ((m[u] ? in1 : in0) ? 1u : 0u) << u;
+                    *reinterpret_cast<float4*>(sv + x) = make_float4(kk[0], kk[1], kk[2], kk[3]);
                 }
-                for (uint32_t x = lane; x < A.nx; x += 32) {
-                    const uint32_t pnt = rr * A.nx + x;
-                    float raw;
-                    if (A.use_tma && A.f0) raw = sv[pnt];
-                    else raw = A.f0 ? __ldg(A.f0 + gs + pnt) : 0.f;
-                    float val;
-                    uint32_t bits;
-                    stage_point<MODE>(A, nd, gs + pnt, x, row_face, raw, val, bits);
-                    sv[pnt] = val;
-                    sb[pnt] = (unsigned char)bits;
+                uint32_t wd = nib << (4u * (lane & 7u));
+                wd |= __shfl_xor_sync(0xffffffffu, wd, 1);
+                wd |= __shfl_xor_sync(0xffffffffu, wd, 2);
+                wd |= __shfl_xor_sync(0xffffffffu, wd, 4);
+                if ((lane & 7u) == 0u) S.plane[((s * R1 + rr) * ppr + k) * 4u + (lane >> 3)] = wd;
+                k += kWarps;
+                while (k >= ppr) { k -= ppr; ++rs; }
+            }
+        } else {
+            // work item = 128 points of one staged row; items are dealt round-robin to the warps.  Lane l takes points
+            // 32u + l (u = 0..3) of the chunk, so the four ballots ARE the row's bit mask, 32 points per word.
+#ifndef GCB_MC_AHEAD
+#define GCB_MC_AHEAD 1
+#endif
+            constexpr bool kAhead = GCB_MC_AHEAD && MODE != M_BAND_RAW;  // modes with global loads per point fetch one item ahead
+            const uint32_t lim = 2u * (rows + 1u);
+            uint32_t k = warp % ppr, rs = warp / ppr;  // rs: staged row over both slices, [0, lim)
+            float craw[4], ca[4], cb[4], nraw[4], na[4], nb[4];
+#define GCB_FETCH(fk, frs, RAW, FA, FB)                                                                     \
+    {                                                                                                       \
+        const uint32_t s_ = (frs) > rows ? 1u : 0u, rr_ = (frs) - s_ * (rows + 1u);                         \
+        const float* sv_ = (s_ ? S.val[1] : S.val[0]) + rr_ * A.nx;                                         \
+        const size_t grow_ = g0 + (size_t)s_ * slice_pts + (size_t)rr_ * A.nx;                              \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                     \
+            const uint32_t x_ = 128u * (fk) + 32u * u + lane;                                               \
+            RAW[u] = 0.f; FA[u] = 0.f; FB[u] = 0.f;                                                         \
+            if (x_ < A.nx) {                                                                                \
+                RAW[u] = tma ? sv_[x_] : (A.f0 ? __ldg(A.f0 + grow_ + x_) : 0.f);                           \
+                stage_fetch<MODE>(A, grow_ + x_, FA[u], FB[u]);                                             \
+            }                                                                                               \
+        }                                                                                                   \
+    }
+            if (kAhead && rs < lim) GCB_FETCH(k, rs, craw, ca, cb)
+            while (rs < lim) {
+                uint32_t nk = 0, nrs = 0;
+                if (kAhead) {
+                    nk = k + kWarps; nrs = rs;
+                    while (nk >= ppr) { nk -= ppr; ++nrs; }
+                    if (nrs < lim) GCB_FETCH(nk, nrs, nraw, na, nb)
+                } else GCB_FETCH(k, rs, craw, ca, cb)
+                const uint32_t s = rs > rows ? 1u : 0u, rr = rs - s * (rows + 1u);
+                float* sv = (s ? S.val[1] : S.val[0]) + rr * A.nx;
+                const uint32_t yy = y0 + rr, gz = z + s + A.gz0;
+                const bool row_face = yy == 0 || yy == A.ny - 1 || gz == 0 || gz == A.gnz - 1;  // domain faces in GLOBAL coordinates
+                uint32_t bits[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t x = 128u * k + 32u * u + lane;
+                    bits[u] = 0u;
+                    if (x < A.nx) {
+                        float val;
+                        stage_point<MODE>(A, nd, x, row_face, craw[u], ca[u], cb[u], val, bits[u]);
+                        if (MODE == M_BAND_RAW || !tma) sv[x] = val;  // the other modes interpolate the staged values as they are
+                        if (ModeTraits<MODE>::kIds) (s ? S.idb[1] : S.idb[0])[rr * A.nx + x] = (unsigned char)(bits[u] & 3u);
+                    }
+                }
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl) {
+                    uint4 wd;
+                    wd.x = __ballot_sync(0xffffffffu, bits[0] & (4u << pl));
+                    wd.y = __ballot_sync(0xffffffffu, bits[1] & (4u << pl));
+                    wd.z = __ballot_sync(0xffffffffu, bits[2] & (4u << pl));
+                    wd.w = __ballot_sync(0xffffffffu, bits[3] & (4u << pl));
+                    if (lane == 0) *reinterpret_cast<uint4*>(S.plane + pl * plane_words + ((s * R1 + rr) * ppr + k) * 4u) = wd;
+                }
+                if (kAhead) {
+                    k = nk; rs = nrs;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { craw[u] = nraw[u]; ca[u] = na[u]; cb[u] = nb[u]; }
+                } else {
+                    k += kWarps;
+                    while (k >= ppr) { k -= ppr; ++rs; }
                 }
             }
+#undef GCB_FETCH
         }
         __syncthreads();
 
-        // ---- 2. classify: cube index + counts.  Warp w owns a contiguous cell range of the tile.
-        const uint32_t seg = (((ncell + kWarps - 1) / kWarps) + 31u) & ~31u;
-        const uint32_t cbeg = min(warp * seg, ncell), cend = min(cbeg + seg, ncell);
-        uint32_t my_verts = 0, my_act = 0;
+        // ---- 2. classify: cube indices + counts.  Warp w owns a contiguous range of 128-cell steps (row r, chunk k) of the tile;
+        //         lane l owns cells 128k + 4l .. + 3 of the step.
+        const uint32_t nsteps = rows * cpr;
+        const uint32_t spw = (nsteps + kWarps - 1) / kWarps;
+        const uint32_t st_beg = min(warp * spw, nsteps), st_end = min(st_beg + spw, nsteps);
+        const bool track = spw <= 32u && !A.st_verts;  // remember empty steps in a register mask
+        const uint32_t r_beg = st_beg / cpr, k_beg = st_beg - r_beg * cpr;
+        const uint32_t wj = lane >> 3, wsh = 4u * (lane & 7u);
+        uint32_t emptymask = 0, my_verts = 0, my_act = 0;
         {
-            uint32_t c = cbeg + lane;
-            uint32_t r = c / A.cx, x = c - r * A.cx;
-            for (; c < cend; c += 32) {
-                const uint32_t pi = r * A.nx + x;
-                const unsigned char* b0 = S.bit[0] + pi;
-                const unsigned char* b1 = S.bit[1] + pi;
-                uint32_t cube;
-                if (MODE == M_REGION) {
-                    // the eight corner bytes, then one cube index per candidate test (bits 2, 3, 4) and the reference's cascade
-                    const uint32_t cb[8] = {b0[0], b0[1], b0[A.nx + 1], b0[A.nx], b1[0], b1[1], b1[A.nx + 1], b1[A.nx]};
-                    uint32_t k0 = 0, k1 = 0, k2 = 0;
+            uint32_t r = r_beg, k = k_beg;
+            for (uint32_t st = st_beg; st < st_end; ++st) {
+                const int left = (int)A.cx - (int)(128u * k + 4u * lane);
+                const uint32_t vc = (uint32_t)max(0, min(4, left));          // valid cells of this lane
+                const uint32_t rm = vc ? ((2u << vc) - 1u) : 0u;            // mask bits those cells look at
+                uint32_t n[NP][4];
+                bool lane_empty = true;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { k0 |= ((cb[q] >> 2) & 1u) << q; k1 |= ((cb[q] >> 3) & 1u) << q; k2 |= ((cb[q] >> 4) & 1u) << q; }
-                    uint32_t cl = 0;
-                    cube = k0;
-                    if (!(A.flags & F_SHOW_REGION) && cube == 0u) {
-                        if (A.flags & F_SHOW_DOMAIN) { cube = k1; cl = 1; }
-                        else { cube = k2; cl = 1; if (cube == 0u) { cube = k1; cl = 2; } }
+                for (int pl = 0; pl < NP; ++pl) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {  // q: slice << 1 | row offset
+                        const uint32_t* w = S.plane + pl * plane_words + ((((uint32_t)q >> 1) * R1 + r + (q & 1)) * ppr + k) * 4u + wj;
+                        n[pl][q] = __funnelshift_r(w[0], w[1], wsh) & 31u;
                     }
-                    S.cls[c] = (unsigned char)cl;
+                    const uint32_t any = (n[pl][0] | n[pl][1] | n[pl][2] | n[pl][3]) & rm, all = n[pl][0] & n[pl][1] & n[pl][2] & n[pl][3] & rm;
+                    lane_empty = lane_empty && (any == 0u || all == rm);
+                }
+                const bool empty = __all_sync(0xffffffffu, lane_empty);
+                if (!(empty && track)) {
+                    const uint32_t vmask = vc >= 4u ? 0xffffffffu : ((1u << (8u * vc)) - 1u);
+                    uint32_t cw;
+                    if (MODE == M_REGION) {
+                        // one cube index per candidate test, then the reference's cascade per cell
+                        constexpr int P1 = NP > 1 ? 1 : 0, P2 = NP > 2 ? 2 : 0;  // (only instantiated with NP == 3)
+                        const uint32_t c0 = cubes4(n[0][0], n[0][1], n[0][2], n[0][3]) & vmask, c1 = cubes4(n[P1][0], n[P1][1], n[P1][2], n[P1][3]) & vmask,
+                                       c2 = cubes4(n[P2][0], n[P2][1], n[P2][2], n[P2][3]) & vmask;
+                        uint32_t clw = 0;
+                        cw = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t k0 = (c0 >> (8 * u)) & 255u, k1 = (c1 >> (8 * u)) & 255u, k2 = (c2 >> (8 * u)) & 255u;
+                            uint32_t cl = 0, cube = k0;
+                            if (!(A.flags & F_SHOW_REGION) && cube == 0u) {
+                                if (A.flags & F_SHOW_DOMAIN) { cube = k1; cl = 1; }
+                                else { cube = k2; cl = 1; if (cube == 0u) { cube = k1; cl = 2; } }
+                            }
+                            cw |= cube << (8 * u);
+                            clw |= cl << (8 * u);
+                        }
+                        *reinterpret_cast<uint32_t*>(S.cls + r * A.cstride + 128u * k + 4u * lane) = clw;
+                    } else
+                        cw = cubes4(n[0][0], n[0][1], n[0][2], n[0][3]) & vmask;
+                    *reinterpret_cast<uint32_t*>(S.cube + r * A.cstride + 128u * k + 4u * lane) = cw;
+                    const uint32_t e = (uint32_t)S.nv[cw & 255u] + S.nv[(cw >> 8) & 255u] + S.nv[(cw >> 16) & 255u] + S.nv[cw >> 24];
+                    my_verts += e & 255u;
+                    my_act += e >> 8;
                 } else
-                    cube = ((b0[0] >> 2) & 1u) | (((b0[1] >> 2) & 1u) << 1) | (((b0[A.nx + 1] >> 2) & 1u) << 2) | (((b0[A.nx] >> 2) & 1u) << 3) |
-                           (((b1[0] >> 2) & 1u) << 4) | (((b1[1] >> 2) & 1u) << 5) | (((b1[A.nx + 1] >> 2) & 1u) << 6) | (((b1[A.nx] >> 2) & 1u) << 7);
-                S.cube[c] = (unsigned char)cube;
-                const uint32_t nv = S.nv[cube];
-                my_verts += nv;
-                my_act += nv > 0;
-                x += 32;
-                while (x >= A.cx) { x -= A.cx; ++r; }
+                    emptymask |= 1u << (st - st_beg);
+                if (++k == cpr) { k = 0; ++r; }
             }
         }
 #pragma unroll
@@ -641,94 +796,154 @@ __global__ void __launch_bounds__(kThreads) mc_fused_kernel(const McArgs A) {
             uint32_t* q = S.queue + warp * kQueue;
             uint32_t head = 0, tail = 0, act_run = 0;  // triangles consumed / enqueued, active cells seen
             const size_t cell0 = (size_t)z * A.cx * A.cy + (size_t)y0 * A.cx;  // global id of tile cell 0 (local slab)
-            for (uint32_t cb = cbeg; cb < cend; cb += 32) {
-                const uint32_t c = cb + lane;
-                const bool valid = c < cend;
-                const uint32_t nv = valid ? S.nv[S.cube[c]] : 0u;
-                const uint32_t nt = (nv * 11u) >> 5;  // nv / 3 for nv in {0,3,..,15}
-                const uint32_t amask = __ballot_sync(0xffffffffu, nv > 0);
-                if (amask == 0u && !A.st_verts) continue;  // nothing to scan, enqueue or drain in this 32-cell step
-                uint32_t incl = nt;
+            uint32_t r = r_beg, k = k_beg;
+            for (uint32_t st = st_beg; st < st_end; ++st, k = (k + 1 == cpr) ? 0u : k + 1u, r += (k == 0u)) {
+                if ((emptymask >> (st - st_beg)) & 1u) continue;
+                const uint32_t x0 = 128u * k + 4u * lane;
+                const uint32_t cw = *reinterpret_cast<const uint32_t*>(S.cube + r * A.cstride + x0);
+                uint32_t nt[4], ntl = 0, nactl = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = S.nv[(cw >> (8 * u)) & 255u];
+                    nt[u] = ((e & 255u) * 11u) >> 5;  // nv / 3 for nv in {0,3,..,15}
+                    ntl += nt[u];
+                    nactl += e >> 8;
+                }
+                // one packed inclusive scan: triangles in the low half, active cells in the high half (<= 640 / 128 per step)
+                const uint32_t pk = ntl | (nactl << 16);
+                uint32_t incl = pk;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t n2 = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= (uint32_t)o) incl += n2;
                 }
-                const uint32_t excl = incl - nt;
-                const uint32_t step_tris = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t rank = __popc(amask & ((1u << lane) - 1u));
-                if (nv > 0 && A.comp) A.comp[act_base + act_run + rank] = (uint32_t)(cell0 + c) + A.gz0 * A.cx * A.cy;
-                if (A.st_verts && valid) {
-                    const size_t gc = cell0 + c;
-                    A.st_verts[gc] = nv;
-                    A.st_occ[gc] = nv > 0;
-                    A.st_verts_scan[gc] = (uint32_t)(vert_base + 3ull * (tail + excl));
-                    A.st_occ_scan[gc] = (uint32_t)(act_base + act_run + rank);
+                const uint32_t excl = incl - pk;
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t step_tris = tot & 0xffffu, step_act = tot >> 16;
+                if (step_act == 0u && !A.st_verts) continue;
+                if (A.comp || A.st_verts) {
+                    uint32_t rank = excl >> 16, tp = excl & 0xffffu;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool valid = x0 + u < A.cx;
+                        const size_t gc = cell0 + (size_t)r * A.cx + x0 + u;
+                        if (nt[u] > 0 && A.comp) A.comp[act_base + act_run + rank] = (uint32_t)gc + A.gz0 * A.cx * A.cy;
+                        if (A.st_verts && valid) {
+                            A.st_verts[gc] = 3u * nt[u];
+                            A.st_occ[gc] = nt[u] > 0;
+                            A.st_verts_scan[gc] = (uint32_t)(vert_base + 3ull * (tail + tp));
+                            A.st_occ_scan[gc] = (uint32_t)(act_base + act_run + rank);
+                        }
+                        rank += nt[u] > 0;
+                        tp += nt[u];
+                    }
                 }
-                for (uint32_t jj = 0; __any_sync(0xffffffffu, jj < nt); ++jj)  // at most 5 rounds, warp-uniform trip count
-                    if (jj < nt) q[(tail + excl + jj) & (kQueue - 1)] = (jj << 28) | c;
-                tail += step_tris;
-                act_run += __popc(amask);
-                __syncwarp();
-                while (tail - head >= 32u) {
-                    const uint32_t ent = q[(head + lane) & (kQueue - 1)];
-                    emit_triangle<MODE>(A, S, z, y0, ent & 0x0fffffffu, ent >> 28, vert_base + 3ull * (head + lane));
-                    head += 32u;
+                const uint32_t first = tail + (excl & 0xffffu), end = tail + step_tris;
+                const uint32_t ebase = (r << 16) | x0;
+                if (end - head <= (uint32_t)kQueue) {
+                    // usual case: the whole step fits into the ring
+                    uint32_t pos = first;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (nt[u] > 0) q[pos & (kQueue - 1)] = ebase + u;
+                        if (nt[u] > 1) q[(pos + 1) & (kQueue - 1)] = (ebase + u) | (1u << 29);
+                        if (__any_sync(0xffffffffu, nt[u] > 2)) {
+                            if (nt[u] > 2) q[(pos + 2) & (kQueue - 1)] = (ebase + u) | (2u << 29);
+                            if (nt[u] > 3) q[(pos + 3) & (kQueue - 1)] = (ebase + u) | (3u << 29);
+                            if (nt[u] > 4) q[(pos + 4) & (kQueue - 1)] = (ebase + u) | (4u << 29);
+                        }
+                        pos += nt[u];
+                    }
+                    tail = end;
+                    __syncwarp();
+                    while (tail - head >= 32u) {
+                        emit_triangle<MODE>(A, S, z, y0, q[(head + lane) & (kQueue - 1)], vert_base + 3ull * (head + lane));
+                        head += 32u;
+                    }
+                    __syncwarp();
+                } else {
+                    // a step with more triangles than ring slots: enqueue position windows [lo, hi) and drain in between
+                    uint32_t lo = tail;
+                    for (;;) {
+                        const uint32_t hi = (end - head <= (uint32_t)kQueue) ? end : head + kQueue;
+                        uint32_t pos = first;
+                        for (int u = 0; u < 4; ++u)
+                            for (uint32_t jj = 0; jj < nt[u]; ++jj, ++pos)
+                                if (pos - lo < hi - lo) q[pos & (kQueue - 1)] = (ebase + u) | (jj << 29);
+                        tail = hi;
+                        __syncwarp();
+                        while (tail - head >= 32u) {
+                            emit_triangle<MODE>(A, S, z, y0, q[(head + lane) & (kQueue - 1)], vert_base + 3ull * (head + lane));
+                            head += 32u;
+                        }
+                        __syncwarp();
+                        if (hi == end) break;
+                        lo = hi;
+                    }
                 }
-                __syncwarp();
+                act_run += step_act;
             }
-            if (lane < tail - head) {
-                const uint32_t ent = q[(head + lane) & (kQueue - 1)];
-                emit_triangle<MODE>(A, S, z, y0, ent & 0x0fffffffu, ent >> 28, vert_base + 3ull * (head + lane));
-            }
+            if (lane < tail - head) emit_triangle<MODE>(A, S, z, y0, q[(head + lane) & (kQueue - 1)], vert_base + 3ull * (head + lane));
         }
     }
 }
 
 // ---------------------------------------------------------------- host side
-template <int MODE>
-static cudaError_t launch_mode(const McArgs& a, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(mc_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int MODE, bool TMA>
+static cudaError_t launch_one(const McArgs& a, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(mc_fused_kernel<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    mc_fused_kernel<MODE><<<grid, kThreads, smem, st>>>(a);
+    mc_fused_kernel<MODE, TMA><<<grid, kThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
-
 template <int MODE>
-static int occupancy(size_t smem) {
+static cudaError_t launch_mode(const McArgs& a, int grid, size_t smem, cudaStream_t st) {
+    return a.use_tma ? launch_one<MODE, true>(a, grid, smem, st) : launch_one<MODE, false>(a, grid, smem, st);
+}
+
+template <int MODE, bool TMA>
+static int occupancy_one(size_t smem) {
     int n = 0;
-    cudaFuncSetAttribute(mc_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_fused_kernel<MODE>, kThreads, smem);
+    cudaFuncSetAttribute(mc_fused_kernel<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_fused_kernel<MODE, TMA>, kThreads, smem);
     return n;
 }
+template <int MODE>
+static int occupancy(size_t smem, bool tma) { return tma ? occupancy_one<MODE, true>(smem) : occupancy_one<MODE, false>(smem); }
 
 int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts) {
     if (a.nx < 2 || a.ny < 2 || a.nz < 2) { *active = 0; *verts = 0; return 0; }
     a.cx = a.nx - 1; a.cy = a.ny - 1; a.cz = a.nz - 1;
     // tile height: ~4096 cells per tile, staged rows must fit in shared memory
+    if (a.nx > 65535u) return fail_msg(c, "grid row too wide (nx > 65535)");
+    a.ppr = (a.nx + 127u) / 128u;
+    a.cpr = (a.cx + 127u) / 128u;
+    a.cstride = 128u * a.cpr;
     uint32_t R = 4096u / a.cx;
     if (R < 1) R = 1;
     if (R > a.cy) R = a.cy;
-    const size_t fixed_bytes = 256 * 8 + 16 + 8 + 8 + 32 + kWarps * kQueue * 4 + kWarps * 8 + 256 + 256 /*slack*/;
+    const bool ids = a.mode == M_LATTICE_ONE || a.mode == M_LATTICE;
+    const size_t planes = a.mode == M_REGION ? 3 : 1;
+    const size_t fixed_bytes = 256 * 8 + 16 + 8 + 8 + 32 * 8 + kWarps * kQueue * 4 + kWarps * 8 + 512 + 64 /*slack*/;
     auto smem_for = [&](uint32_t r) {
         const size_t stride = (((size_t)(r + 1) * a.nx) + 15) & ~(size_t)15;
-        return stride * 4 * 2 + stride * 2 + (size_t)r * a.cx * (a.mode == M_REGION ? 2 : 1) + 16 + fixed_bytes;
+        return stride * 4 * 2 + (ids ? stride * 2 : 0) + planes * 2 * (r + 1) * a.ppr * 16 + 16 + (size_t)r * a.cstride * (a.mode == M_REGION ? 2 : 1) + fixed_bytes;
     };
-    while (R > 1 && smem_for(R) > 100 * 1024) --R;
+    // 228 KB shared memory per SM, 1 KB reserved per CTA: 56 KB keeps four CTAs on an SM (M_BAND_RAW's register budget; 6-row tiles
+    // for 512-wide rows), 75 KB three (the other modes)
+    size_t cap = (a.mode == M_BAND_RAW ? 56 : 75) * 1024;
+    if (const char* e = getenv("GCB_MC_SMEM_CAP_KB")) cap = (size_t)atoi(e) * 1024;  // A/B measurements of tile height vs CTAs per SM
+    while (R > 1 && smem_for(R) > cap) --R;
     const size_t smem = smem_for(R);
     if (smem > 227 * 1024) return fail_msg(c, "grid row too wide for one shared-memory tile (nx too large)");
-    if ((size_t)R * a.cx >= (1u << 28)) return fail_msg(c, "tile too large");
+    if (R > 8191u) return fail_msg(c, "tile too tall");
     a.rows_per_tile = R;
     a.tiles_per_slice = (a.cy + R - 1) / R;
     const unsigned long long nt = (unsigned long long)a.tiles_per_slice * a.cz;
     if (nt >= 0xffffffffull) return fail_msg(c, "too many tiles");
     a.num_tiles = (uint32_t)nt;
     a.prow_stride = (uint32_t)((((size_t)(R + 1) * a.nx) + 15) & ~(size_t)15);
-    {   // c / cx for c < 2^28 as (c * mul) >> shift  (round-up method: mul = ceil(2^shift / cx), shift = 28 + ceil(log2 cx))
-        uint32_t l = 0;
-        while ((1u << l) < a.cx) ++l;
-        a.magic_cx_shift = 28 + l;
-        a.magic_cx_mul = (uint32_t)(((1ull << a.magic_cx_shift) + a.cx - 1) / a.cx);
+    {
         float thr = (float)0.0005;
         if ((double)thr < 0.0005) thr = nextafterf(thr, 1.0f);
         a.snap_thr = thr;
@@ -754,12 +969,12 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
 
     int occ = 1;
     switch (a.mode) {
-    case M_LATTICE_ONE: occ = occupancy<M_LATTICE_ONE>(smem); break;
-    case M_LATTICE: occ = occupancy<M_LATTICE>(smem); break;
-    case M_CSG: occ = occupancy<M_CSG>(smem); break;
-    case M_TOPO: occ = occupancy<M_TOPO>(smem); break;
-    case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem); break;
-    case M_REGION: occ = occupancy<M_REGION>(smem); break;
+    case M_LATTICE_ONE: occ = occupancy<M_LATTICE_ONE>(smem, a.use_tma); break;
+    case M_LATTICE: occ = occupancy<M_LATTICE>(smem, a.use_tma); break;
+    case M_CSG: occ = occupancy<M_CSG>(smem, a.use_tma); break;
+    case M_TOPO: occ = occupancy<M_TOPO>(smem, a.use_tma); break;
+    case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem, a.use_tma); break;
+    case M_REGION: occ = occupancy<M_REGION>(smem, a.use_tma); break;
     default: return fail_msg(c, "bad mode");
     }
     if (occ < 1) return fail_msg(c, "extraction kernel does not fit on an SM");
