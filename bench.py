@@ -251,15 +251,21 @@ def main():
                     "note": "control grids copied from pinned host memory each step; counts and min/max read back; the mesh stays in device memory "
                             "as in the reference (Vulkan-exported vertex buffers)"},
             "gpu_launches": g_launch,
-            "roofline": {"bound": "hbm", "kernel": "mc_fused_kernel<M_BAND_RAW>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "mc_fused_kernel<M_BAND_RAW, TMA>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES if (F, R, NH, world) == (512, 4, 62, 1) else None,
                          "traffic_source": "profiles/r01_ncu_mc_fused.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch, this workload)",
                          "kernel_ms": ext_k_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
             # the field kernel moves 4 B/point and is bound by instruction issue (exact texture model in fp64 + libdevice-identical
             # sincosf): reported as issue slots per (point, harmonic), not against the HBM roofline
             "field_kernel": {"kernel": "svl_field_tile_kernel", "bound": "instruction issue (fp64 lerps + sincosf polynomial)", "kernel_ms": fld_k_ms,
+                             "share_of_step": fld_k_ms / ms,
                              "sincos_pairs_per_s": sincos / (fld_k_ms * 1e-3),
-                             "issue_slots_per_point_harmonic": 148 * 4 * 32 * sm_mhz * 1e6 * (fld_k_ms * 1e-3) / sincos},
+                             "issue_slots_per_point_harmonic": 148 * 4 * 32 * sm_mhz * 1e6 * (fld_k_ms * 1e-3) / sincos,
+                             # against the HBM roofline it is nowhere: it writes 4 B/point and reads the control grids once
+                             "hbm": {"algorithmic_bytes": 4.0 * F * F * nzl + 4.0 * phi.numel(),
+                                     "achieved_gbs": (4.0 * F * F * nzl + 4.0 * phi.numel()) / (fld_k_ms * 1e-3) / 1e9,
+                                     "frac": (4.0 * F * F * nzl + 4.0 * phi.numel()) / (fld_k_ms * 1e-3) / 1e9 / peak},
+                             "ncu": "profiles/r01_ncu_svl_field.txt: issue slots 66 % busy, FMA / ALU / FP64 / XU pipes 26-27 % each"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
@@ -269,8 +275,8 @@ def main():
         dist.destroy_process_group()
 
 
-# measured once with `ncu --set full` on the default workload (profiles/r01_ncu_mc_fused.txt): 0.539 GB read + 5.466 GB written
-NCU_TRAFFIC_BYTES = 538731520 + 5465742000
+# measured once with `ncu --set full` on the default workload (profiles/r01_ncu_mc_fused.txt): 0.540 GB read + 5.468 GB written
+NCU_TRAFFIC_BYTES = 539927808 + 5467993000
 
 
 def cpu_baseline(nh, budget_s=12.0):

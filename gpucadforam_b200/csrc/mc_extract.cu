@@ -553,12 +553,14 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
             mbar_wait(S.mbar, parity);
             parity ^= 1u;
         }
-        if (MODE == M_BAND_RAW && TMA) {
-            // the hot configuration: raw field staged by TMA, normalisation + domain faces + band test fused in.  Work item = 128 points
-            // of one staged row, dealt round-robin to the warps; lane l takes points 4l .. 4l+3 (one LDS.128 / STS.128), its four
-            // inside bits form a nibble, and an OR over each group of eight lanes assembles the 32-point words of the row's bit mask.
+        if (TMA && MODE != M_REGION) {
+            // Field staged by TMA (rows 16-byte aligned in shared memory, nx % 4 == 0).  Work item = 128 points of one staged row,
+            // dealt round-robin to the warps; lane l takes points 4l .. 4l+3 (one LDS.128), its four inside bits form a nibble, and
+            // an OR over each group of eight lanes assembles the 32-point words of the row's bit mask.  M_BAND_RAW (the hot
+            // configuration) fuses normalisation + domain faces + band test here and writes k back with one STS.128; the other
+            // modes fetch what else a point needs from global memory (four independent loads per lane) and leave the values alone.
             const uint32_t lim = 2u * (rows + 1u);
-            const bool in0 = 0.f < A.iso, in1 = 1.f < A.iso;  // "mask < iso" for the two values the mask takes
+            const bool in0 = 0.f < A.iso, in1 = 1.f < A.iso;  // M_BAND_RAW: "mask < iso" for the two values the mask takes
             uint32_t k = warp % ppr, rs = warp / ppr;         // rs: staged row over both slices, [0, lim)
             while (rs < lim) {
                 const uint32_t s = rs > rows ? 1u : 0u, rr = rs - s * (rows + 1u);
@@ -569,34 +571,52 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
                 uint32_t nib = 0;
                 if (x < A.nx) {
                     const float4 v4 = *reinterpret_cast<const float4*>(sv + x);
-                    float nn[4] = {__fsub_rn(v4.x, A.na), __fsub_rn(v4.y, A.na), __fsub_rn(v4.z, A.na), __fsub_rn(v4.w, A.na)}, kk[4];
-                    bool fast = nd.ok;
+                    if (MODE == M_BAND_RAW) {
+                        float nn[4] = {__fsub_rn(v4.x, A.na), __fsub_rn(v4.y, A.na), __fsub_rn(v4.z, A.na), __fsub_rn(v4.w, A.na)}, kk[4];
+                        bool fast = nd.ok;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {  // div_by_uniform, the four range checks folded into one branch
-                        const float q0 = __fmul_rn(nn[u], nd.y);
-                        const float r0 = __fmaf_rn(-q0, nd.d, nn[u]);
-                        const float q1 = __fmaf_rn(r0, nd.y, q0);
-                        const float r1 = __fmaf_rn(-q1, nd.d, nn[u]);
-                        kk[u] = __fmaf_rn(r1, nd.y, q1);
-                        fast = fast && fabsf(nn[u]) >= 1.0e-30f && fabsf(kk[u]) >= 1.0e-30f && fabsf(kk[u]) <= 1.0e30f;
+                        for (int u = 0; u < 4; ++u) {  // div_by_uniform, the four range checks folded into one branch
+                            const float q0 = __fmul_rn(nn[u], nd.y);
+                            const float r0 = __fmaf_rn(-q0, nd.d, nn[u]);
+                            const float q1 = __fmaf_rn(r0, nd.y, q0);
+                            const float r1 = __fmaf_rn(-q1, nd.d, nn[u]);
+                            kk[u] = __fmaf_rn(r1, nd.y, q1);
+                            fast = fast && fabsf(nn[u]) >= 1.0e-30f && fabsf(kk[u]) >= 1.0e-30f && fabsf(kk[u]) <= 1.0e30f;
+                        }
+                        if (!fast) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) kk[u] = div_by_uniform(nn[u], nd);
+                        }
+                        // device_bufferfour (Gratings.cu:1089-1134): band mask, the six domain faces forced to k = 0, m = 0
+                        bool m[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) m[u] = (kk[u] >= A.iso1) && (kk[u] <= A.iso2);
+                        if (row_face) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) { kk[u] = 0.f; m[u] = false; }
+                        }
+                        if (x == 0u) { kk[0] = 0.f; m[0] = false; }
+                        if (x + 4u == A.nx) { kk[3] = 0.f; m[3] = false; }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) nib |= ((m[u] ? in1 : in0) ? 1u : 0u) << u;
+                        *reinterpret_cast<float4*>(sv + x) = make_float4(kk[0], kk[1], kk[2], kk[3]);
+                    } else {
+                        const size_t gi = g0 + (size_t)s * slice_pts + (size_t)rr * A.nx + x;
+                        const float raw[4] = {v4.x, v4.y, v4.z, v4.w};
+                        float fa[4] = {0.f, 0.f, 0.f, 0.f}, fb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) stage_fetch<MODE>(A, gi + u, fa[u], fb[u]);
+                        uint32_t idw = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            float val;
+                            uint32_t bits;
+                            stage_point<MODE>(A, nd, x + u, row_face, raw[u], fa[u], fb[u], val, bits);
+                            nib |= ((bits >> 2) & 1u) << u;
+                            idw |= (bits & 3u) << (8 * u);
+                        }
+                        if (ModeTraits<MODE>::kIds) *reinterpret_cast<uint32_t*>((s ? S.idb[1] : S.idb[0]) + rr * A.nx + x) = idw;
                     }
-                    if (!fast) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) kk[u] = div_by_uniform(nn[u], nd);
-                    }
-                    // device_bufferfour (Gratings.cu:1089-1134): band mask, the six domain faces forced to k = 0, m = 0
-                    bool m[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) m[u] = (kk[u] >= A.iso1) && (kk[u] <= A.iso2);
-                    if (row_face) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) { kk[u] = 0.f; m[u] = false; }
-                    }
-                    if (x == 0u) { kk[0] = 0.f; m[0] = false; }
-                    if (x + 4u == A.nx) { kk[3] = 0.f; m[3] = false; }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) nib |= ((m[u] ? in1 : in0) ? 1u : 0u) << u;
-                    *reinterpret_cast<float4*>(sv + x) = make_float4(kk[0], kk[1], kk[2], kk[3]);
                 }
                 uint32_t wd = nib << (4u * (lane & 7u));
                 wd |= __shfl_xor_sync(0xffffffffu, wd, 1);
