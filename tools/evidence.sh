@@ -11,7 +11,7 @@ timeout 300 python bench.py 2>gpurun_out/${t}_bench_ours.err | tail -1 > gpurun_
 cat gpurun_out/${t}_bench_ours.json
 (timeout 300 python tools/config_bench.py 2>&1 | tail -3) > gpurun_out/${t}_configs.json
 timeout 200 python tools/topo_probe.py > gpurun_out/${t}_topo_probe.json 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${t}_launches.csv python bench.py --steps 2 --warmup 3 --profile > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"svl_|mc_fused|minmax" -c 60 --csv --log-file gpurun_out/${t}_launches.csv python bench.py --steps 2 --warmup 3 --profile > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mc_fused -s 4 -c 1 -f -o gpurun_out/${t}_mc python bench.py --steps 2 --warmup 3 --profile > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:svl_field -s 4 -c 1 -f -o gpurun_out/${t}_field python bench.py --steps 2 --warmup 3 --profile > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mc_fused -s 4 -c 1 -f -o gpurun_out/${t}_topo python tools/topo_probe.py --steps 1 > /dev/null 2>&1
