@@ -673,6 +673,55 @@ def test_ragged_and_tiny_grids(ctx, dims):
     ctx.set_options(_capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET)
 
 
+@pytest.mark.parametrize("dims", [(132, 9, 5), (260, 6, 4), (516, 5, 3), (128, 3, 3), (256, 4, 3), (4, 70, 40), (2, 600, 3), (129, 5, 4), (61, 9, 7)])
+@pytest.mark.parametrize("kind", ["noise", "blobs"])
+def test_extraction_row_mask_paths(ctx, dims, kind):
+    """The fused kernel classifies 128 cells of a row per warp step from row bit masks.  Rows with partial / exactly full 128-point
+    chunks, TMA-eligible (nx % 4 == 0) and LDG rows, tiles so tall that a warp owns more than 32 steps, steps with more triangles
+    than ring slots (noise) and fields that are empty but for a few blobs (step early-out): counts and stage arrays bit-exact
+    against the oracle, meshes within 1e-5, and every code path of the product (TMA / LDG, with / without the stage arrays, the
+    fused band-raw mode) bit-identical to each other."""
+    nx, ny, nz = dims
+    rng = np.random.RandomState(5)
+    if kind == "noise":
+        k = rng.rand(nz, ny, nx).astype(np.float32)
+    else:
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        k = np.zeros((nz, ny, nx), np.float32)
+        for cx, cy, cz in ((0.1, 0.5, 0.5), (0.52, 0.3, 0.4), (0.97, 0.8, 0.6)):
+            d2 = (x - cx * nx) ** 2 + (y - cy * ny) ** 2 + (z - cz * nz) ** 2
+            k = np.maximum(k, np.exp(-d2 / 6.0).astype(np.float32))
+    lo_b, hi_b = cases.BAND_LO, 0.6
+    mask, kk = orc.normalise_four(k, lo_b, hi_b, ab=(0.0, 1.0))
+    mv = max_verts_for(dims)
+    ncell = (nx - 1) * (ny - 1) * (nz - 1)
+    o = orc.extract(orc.MODE_LATTICE_ONE, dims, (1, 1, 1), (0, 0, 0), cases.ISO_MASK, f0=mask, f1=kk, iso1=lo_b, iso2=hi_b, max_verts=mv)
+    iso = g.Isosurface(ctx)
+    meshes = []
+    for opts in (_capi.GCB_OPT_FILL_STAGE_ARRAYS, _capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_NO_TMA, 0, _capi.GCB_OPT_NO_TMA):
+        ctx.set_options(opts)
+        scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+        act, tot = iso.computeIsosurface_latticeone(dev(mask), mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), mv, dev(kk), lo_b, hi_b)
+        assert (act, tot) == (o["active"], o["total"]), "%s %s opts=%d" % (dims, kind, opts)
+        if opts & _capi.GCB_OPT_FILL_STAGE_ARRAYS:
+            compare_extractions(mine_result(scr, mesh, dims, act, tot), o, "row masks %s %s opts=%d" % (dims, kind, opts), exact_mesh=False)
+        else:
+            assert np.array_equal(scr.compVoxelArray[:act].cpu().numpy().astype(np.uint32), o["compVoxelArray"][:act])
+        meshes.append((mesh.pos[:tot].clone(), mesh.norm[:tot].clone()))
+    for p2, n2 in meshes[1:]:
+        assert_bits_equal(meshes[0][0], p2, "paths agree: pos")
+        assert_bits_equal(meshes[0][1], n2, "paths agree: norm")
+    # the fused band-raw mode on the raw field (range [0, 1] -> k = f): same mesh again, bit for bit
+    for opts in (0, _capi.GCB_OPT_NO_TMA):
+        ctx.set_options(opts)
+        mesh = g.MeshBuffers(mv)
+        act, tot = g.extract_band_raw(ctx, dev(k).reshape(-1), 0.0, 1.0, cases.ISO_MASK, lo_b, hi_b, dims, (1, 1, 1), (0, 0, 0), mesh.pos, mesh.norm, mv)
+        assert (act, tot) == (o["active"], o["total"])
+        assert_bits_equal(meshes[0][0], mesh.pos[:tot], "band-raw pos")
+        assert_bits_equal(meshes[0][1], mesh.norm[:tot], "band-raw norm")
+    ctx.set_options(_capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET)
+
+
 def test_max_verts_truncation(ctx):
     """Writes at index >= maxVerts-3 are dropped (MarchingCubes_kernel.cu:2181); totals still report the full count."""
     n = 32
