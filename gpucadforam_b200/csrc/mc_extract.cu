@@ -934,12 +934,16 @@ static int occupancy(size_t smem, bool tma) { return tma ? occupancy_one<MODE, t
 int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts) {
     if (a.nx < 2 || a.ny < 2 || a.nz < 2) { *active = 0; *verts = 0; return 0; }
     a.cx = a.nx - 1; a.cy = a.ny - 1; a.cz = a.nz - 1;
-    // tile height: ~4096 cells per tile, staged rows must fit in shared memory
+    // tile height: staged rows must fit in shared memory
     if (a.nx > 65535u) return fail_msg(c, "grid row too wide (nx > 65535)");
     a.ppr = (a.nx + 127u) / 128u;
     a.cpr = (a.cx + 127u) / 128u;
     a.cstride = 128u * a.cpr;
-    uint32_t R = 4096u / a.cx;
+    // ~4096 cells per tile; large grids in the three-CTA modes take twice that (measured on the 768x384x384 density: 8 rows per
+    // tile instead of 5 at the same occupancy, 1.29 -> 1.09 ms -- the per-tile latencies are what a sparse surface pays for)
+    uint32_t tile_cells = (a.mode != M_BAND_RAW && (unsigned long long)a.cx * a.cy * a.cz >= (1ull << 25)) ? 8192u : 4096u;
+    if (const char* e = getenv("GCB_MC_TILE_CELLS")) tile_cells = (uint32_t)atoi(e);  // A/B measurements
+    uint32_t R = tile_cells / a.cx;
     if (R < 1) R = 1;
     if (R > a.cy) R = a.cy;
     const bool ids = a.mode == M_LATTICE_ONE || a.mode == M_LATTICE;
