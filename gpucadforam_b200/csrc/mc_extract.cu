@@ -954,9 +954,15 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
         return stride * 4 * 2 + (ids ? stride * 2 : 0) + planes * 2 * (r + 1) * a.ppr * 16 + 16 + (size_t)r * a.cstride * (a.mode == M_REGION ? 2 : 1) + fixed_bytes;
     };
     // 228 KB shared memory per SM, 1 KB reserved per CTA: 56 KB keeps four CTAs on an SM (M_BAND_RAW's register budget; 6-row tiles
-    // for 512-wide rows), 75 KB three (the other modes)
+    // for 512-wide rows), 75 KB three (the other modes).  Rows of 2048 points leave one row per tile
+    // at 56 KB -- every staged row is then shared by a single cell row -- so very wide grids trade the fourth CTA for taller
+    // tiles (2048-wide slab: 1 row per tile at 56 KB 5.52 ms, 2 rows at 75 KB 5.05 ms; 1024-wide: 3 rows at 56 KB 2.49 ms, 5 rows
+    // at 75 KB 2.58 ms; equal at 512).
+    const uint32_t R0 = R;
     size_t cap = (a.mode == M_BAND_RAW ? 56 : 75) * 1024;
-    if (const char* e = getenv("GCB_MC_SMEM_CAP_KB")) cap = (size_t)atoi(e) * 1024;  // A/B measurements of tile height vs CTAs per SM
+    while (R > 1 && smem_for(R) > cap) --R;
+    if (a.mode == M_BAND_RAW && R < 3 && R < R0) { cap = 75 * 1024; R = R0; }
+    if (const char* e = getenv("GCB_MC_SMEM_CAP_KB")) { cap = (size_t)atoi(e) * 1024; R = R0; }  // A/B measurements of tile height vs CTAs per SM
     while (R > 1 && smem_for(R) > cap) --R;
     const size_t smem = smem_for(R);
     if (smem > 227 * 1024) return fail_msg(c, "grid row too wide for one shared-memory tile (nx too large)");
