@@ -773,7 +773,14 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
                 if (lane == 0 && (tv | ta)) { atomicAdd(A.totals, (unsigned long long)ta); atomicAdd(A.totals + 1, (unsigned long long)tv); }
             } else {
                 unsigned long long pa = 0, pv = 0;  // exclusive prefixes
-                if (tile > 0) {
+                // A tile without active cells has nothing to place: it publishes a zero aggregate and does not wait for its own
+                // prefix (sparse fields: most tiles, and the look-back wait was a quarter of their time).  Successors walk through
+                // such entries like through any aggregate; every 64th tile still resolves and publishes an inclusive prefix, which
+                // bounds the walk, and so does the last tile, which reports the totals.
+                const bool no_prefix = ta == 0u && !A.st_verts && (tile & 63u) != 0u && tile != A.num_tiles - 1;
+                if (no_prefix) {
+                    if (lane == 0) { st_relaxed(A.status_a + tile, kFlagAgg); st_relaxed(A.status_v + tile, kFlagAgg); }
+                } else if (tile > 0) {
                     if (lane == 0) { st_relaxed(A.status_a + tile, kFlagAgg | ta); st_relaxed(A.status_v + tile, kFlagAgg | tv); }
                     int64_t base = (int64_t)tile - 1;
                     for (;;) {
@@ -798,7 +805,7 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
                         base -= 32;
                     }
                 }
-                if (lane == 0) {
+                if (lane == 0 && !no_prefix) {
                     st_relaxed(A.status_a + tile, kFlagIncl | (pa + ta));
                     st_relaxed(A.status_v + tile, kFlagIncl | (pv + tv));
                     S.prefix[0] = pa; S.prefix[1] = pv;
