@@ -343,16 +343,15 @@ int gcb_unit_lattice_spectrum(gcb_ctx* ctx, const float* d_unit_cell, int Nxu, i
 }
 int gcb_GPU_buffer_normalise_buffer(gcb_ctx* ctx, float* d_vec1, float* d_vec2, int n) {
     CTX(ctx);
-    float a, b;
-    if (int r = k_minmax(C, d_vec1, (size_t)n, &a, &b)) return r;
-    SYNC_RET(k_normalise(C, d_vec1, d_vec2, (size_t)n, a, b));
+    // min/max stay in device memory between the reduction and the normalisation (one sync per call instead of two)
+    if (int r = k_minmax_device(C, d_vec1, (size_t)n)) return r;
+    SYNC_RET(k_normalise(C, d_vec1, d_vec2, (size_t)n, 0.f, 0.f, C->d_minmax));
 }
 int gcb_GPU_buffer_normalise_four(gcb_ctx* ctx, float* dataone, float* datatwo, float* datathree, size_t size, int Nx, int Ny, int Nz, float isoval_1,
                                   float isoval_2) {
     CTX(ctx);
-    float a, b;
-    if (int r = k_minmax(C, dataone, size, &a, &b)) return r;
-    SYNC_RET(k_normalise_four(C, dataone, datatwo, datathree, Nx, Ny, Nz, a, b, isoval_1, isoval_2));
+    if (int r = k_minmax_device(C, dataone, size)) return r;
+    SYNC_RET(k_normalise_four(C, dataone, datatwo, datathree, Nx, Ny, Nz, 0.f, 0.f, isoval_1, isoval_2, C->d_minmax));
 }
 int gcb_minmax(gcb_ctx* ctx, const float* d_in, size_t n, float* lo, float* hi) { CTX(ctx); return k_minmax(C, d_in, n, lo, hi); }
 

@@ -79,7 +79,7 @@ struct Ctx {
     unsigned long long launches = 0;
     int num_sms = 148;
     // extraction scratch
-    unsigned long long* d_status = nullptr;  // 2 * status_cap words
+    unsigned long long* d_status = nullptr;  // status_cap words: totals, tile counter, look-back state of both prefixes
     size_t status_cap = 0;
     uint32_t* d_tile_counter = nullptr;
     unsigned long long* d_totals = nullptr;  // 2 words
@@ -132,8 +132,9 @@ int k_cone_frustum(Ctx* c, float* out, float3 center, float3 ang, float tr, floa
 int k_pyramid_frustum(Ctx* c, float* out, float3 center, float3 ang, float xb, float xt, float yh, float zb, float zt, int nx, int ny, int nz, float dx, float dy, float dz);
 int k_minmax(Ctx* c, const float* in, size_t n, float* lo, float* hi);           // host results, reference semantics
 int k_minmax_device(Ctx* c, const float* in, size_t n);                          // leaves decoded result in c->d_minmax
-int k_normalise(Ctx* c, const float* in, float* out, size_t n, float a, float b);
-int k_normalise_four(Ctx* c, const float* in, float* mask, float* k, int nx, int ny, int nz, float a, float b, float iso1, float iso2);
+int k_normalise(Ctx* c, const float* in, float* out, size_t n, float a, float b, const float* d_ab = nullptr);
+int k_normalise_four(Ctx* c, const float* in, float* mask, float* k, int nx, int ny, int nz, float a, float b, float iso1, float iso2,
+                     const float* d_ab = nullptr);
 int k_refine(Ctx* c, const float* tex, int cx, int cy, int cz, float* out, int nx2, int ny2, int nz2, float dx, float dy, float dz);
 int k_grating(Ctx* c, const float* tex, int cx, int cy, int cz, float2* out, int nx2, int ny2, int nz2, float dx, float dy, float dz);
 int k_svl(Ctx* c, float* svl, const float2* grating, size_t n, int idx, const float2* coef);

@@ -918,9 +918,7 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
 // ---------------------------------------------------------------- host side
 template <int MODE, bool TMA>
 static cudaError_t launch_one(const McArgs& a, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(mc_fused_kernel<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    mc_fused_kernel<MODE, TMA><<<grid, kThreads, smem, st>>>(a);
+    mc_fused_kernel<MODE, TMA><<<grid, kThreads, smem, st>>>(a);  // cudaFuncAttributeMaxDynamicSharedMemorySize: set in occupancy_one()
     return cudaGetLastError();
 }
 template <int MODE>
@@ -988,31 +986,39 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     // TMA bulk copies need 16-byte aligned global addresses and sizes
     a.use_tma = !(c->options & GCB_OPT_NO_TMA) && a.f0 && (a.nx % 4 == 0) && (((uintptr_t)a.f0 & 15) == 0);
 
-    if (c->status_cap < a.num_tiles) {
+    // one scratch allocation, cleared by ONE memset per launch: [totals (2 words) | tile counter | pad | status_a | status_v]
+    const size_t need = 4 + 2 * (size_t)a.num_tiles;
+    if (c->status_cap < need) {
         if (c->d_status) cudaFree(c->d_status);
-        c->status_cap = (size_t)a.num_tiles + 1024;
-        GCB_CHECK(c, cudaMalloc(&c->d_status, c->status_cap * 2 * sizeof(unsigned long long)));
+        c->status_cap = need + 4096;
+        GCB_CHECK(c, cudaMalloc(&c->d_status, c->status_cap * sizeof(unsigned long long)));
     }
-    a.status_a = c->d_status;
-    a.status_v = c->d_status + c->status_cap;
-    a.tile_counter = c->d_tile_counter;
-    a.totals = c->d_totals;
-    if (!a.count_only) {
-        GCB_CHECK(c, cudaMemsetAsync(a.status_a, 0, (size_t)a.num_tiles * 8, c->stream));
-        GCB_CHECK(c, cudaMemsetAsync(a.status_v, 0, (size_t)a.num_tiles * 8, c->stream));
-    }
-    GCB_CHECK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(uint32_t), c->stream));
-    GCB_CHECK(c, cudaMemsetAsync(c->d_totals, 0, 2 * sizeof(unsigned long long), c->stream));
+    a.totals = c->d_status;
+    a.tile_counter = (uint32_t*)(c->d_status + 2);
+    a.status_a = c->d_status + 4;
+    a.status_v = c->d_status + 4 + a.num_tiles;
+    GCB_CHECK(c, cudaMemsetAsync(c->d_status, 0, (a.count_only ? 4 : need) * sizeof(unsigned long long), c->stream));
 
+    // occupancy query + shared-memory attribute once per (mode, stage path, tile size): both are host-side driver calls that a
+    // small grid would otherwise pay on every launch
+    // (the attribute belongs to the kernel function, not to a gcb context: the cache is per process and device)
+    if (a.mode < 0 || a.mode > M_REGION) return fail_msg(c, "bad mode");
+    struct OccEntry { size_t smem = 0; int occ = 0; };
+    static OccEntry occ_cache[16][6][2];
     int occ = 1;
-    switch (a.mode) {
-    case M_LATTICE_ONE: occ = occupancy<M_LATTICE_ONE>(smem, a.use_tma); break;
-    case M_LATTICE: occ = occupancy<M_LATTICE>(smem, a.use_tma); break;
-    case M_CSG: occ = occupancy<M_CSG>(smem, a.use_tma); break;
-    case M_TOPO: occ = occupancy<M_TOPO>(smem, a.use_tma); break;
-    case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem, a.use_tma); break;
-    case M_REGION: occ = occupancy<M_REGION>(smem, a.use_tma); break;
-    default: return fail_msg(c, "bad mode");
+    OccEntry& oc = occ_cache[c->device & 15][a.mode][a.use_tma ? 1 : 0];
+    if (oc.smem == smem && oc.occ > 0) occ = oc.occ;
+    else {
+        switch (a.mode) {
+        case M_LATTICE_ONE: occ = occupancy<M_LATTICE_ONE>(smem, a.use_tma); break;
+        case M_LATTICE: occ = occupancy<M_LATTICE>(smem, a.use_tma); break;
+        case M_CSG: occ = occupancy<M_CSG>(smem, a.use_tma); break;
+        case M_TOPO: occ = occupancy<M_TOPO>(smem, a.use_tma); break;
+        case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem, a.use_tma); break;
+        case M_REGION: occ = occupancy<M_REGION>(smem, a.use_tma); break;
+        default: return fail_msg(c, "bad mode");
+        }
+        oc.smem = smem; oc.occ = occ;
     }
     if (occ < 1) return fail_msg(c, "extraction kernel does not fit on an SM");
     // persistent grid: every CTA resident (required by the look-back's forward progress)
@@ -1032,7 +1038,7 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     if (e != cudaSuccess) return fail(c, "mc_fused_kernel launch", e);
     c->launches++;
     if (c->timing) { cudaEventRecord(c->ev[1], c->stream); c->extract_timed = true; }
-    GCB_CHECK(c, cudaMemcpyAsync(c->h_totals, c->d_totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    GCB_CHECK(c, cudaMemcpyAsync(c->h_totals, a.totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     GCB_CHECK(c, cudaStreamSynchronize(c->stream));
     *active = c->h_totals[0];
     *verts = c->h_totals[0] ? c->h_totals[1] : 0;  // early-out of Isosurface.cu:83-87
