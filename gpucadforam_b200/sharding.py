@@ -58,3 +58,32 @@ def gather_counts(dist, active, verts, device="cpu"):
         a += ac
         v += vc
     return per_rank, voff, aoff, (a, v)
+
+
+def slab_gridcenter(gridcenter, z0):
+    """gridcenter a rank passes to the legacy extraction entry points for a slab whose first point layer is global layer z0:
+    the reference computes positions as (gridPos - gridcenter) * voxelSize (MarchingCubes_kernel.cu:1888-1890), and
+    (z_local - (gc_z - z0)) equals (z_global - gc_z) exactly in fp32 (small integers / half-integers)."""
+    return (float(gridcenter[0]), float(gridcenter[1]), float(gridcenter[2]) - float(z0))
+
+
+def exchange_halo_planes(dist, fields, nzl):
+    """+z halo of STORED fields (density, grid_points, d_result ...): every local buffer holds `nzl` point layers,
+    layers 0..nzl-2 owned, layer nzl-1 = the first owned layer of the rank above (the top rank owns its last layer too).
+    `fields` is a list of (flat tensor, elements per point layer).  One batched send/recv per neighbour pair: NCCL point-to-point
+    (NVLink P2P on an NVSwitch box) for CUDA tensors, gloo for the CPU tests.  MC cells only look at +1
+    (MarchingCubes_kernel.cu:889-896), so nothing travels upwards."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ops, nbytes = [], 0
+    for (buf, plane) in fields:
+        if rank > 0:
+            ops.append(dist.P2POp(dist.isend, buf[:plane], rank - 1))
+        if rank < world - 1:
+            halo = buf[(nzl - 1) * plane: nzl * plane]
+            ops.append(dist.P2POp(dist.irecv, halo, rank + 1))
+            nbytes += halo.numel() * halo.element_size()
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return nbytes

@@ -622,6 +622,53 @@ def test_z_slab_concatenation_equals_single_pass(ctx, nslabs):
     assert torch.equal(torch.cat(comp_parts), comp[:a])
 
 
+@pytest.mark.parametrize("nslabs", [2, 3])
+@pytest.mark.parametrize("variant", ["_2", "_topo"])
+def test_stored_field_slabs_with_halo_plane_equal_single_pass(ctx, nslabs, variant):
+    """SURVEY.md 8e, stored fields (config 5 sharded): every slab holds its owned point layers of density / grid_points /
+    d_result plus the one +z halo layer copied from the slab above, and calls the LEGACY entry point with the slab's
+    gridcenter (sharding.slab_gridcenter).  Concatenated in slab order the meshes equal the single call byte for byte."""
+    from gpucadforam_b200 import sharding
+    T = cases.TOPO
+    fx, fy, fz = T["fdims"]
+    npts, plane = fx * fy * fz, fx * fy
+    dens = _upsample(ctx, T, cases.topo_coarse(T))
+    rng = np.random.RandomState(11)
+    host = np.zeros(npts, orc.GP_DTYPE)
+    host["t_x"] = np.where(rng.rand(npts) < 0.2, rng.rand(npts), 0).astype(np.float32)
+    host["t_y"] = np.where(rng.rand(npts) < 0.2, rng.rand(npts), 0).astype(np.float32)
+    host["val"][:200] = -1
+    vol_topo = gp_from_numpy(host)
+    result = dev(rng.rand(npts).astype(np.float32))
+    gc = (3.5, -1.25, 11.5)
+    iso = g.Isosurface(ctx)
+
+    def run(dims, center, d_topo, d_dens, d_res):
+        mv = max_verts_for(dims)
+        ncell = (dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1)
+        scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
+        fn = iso.computeIsosurface_2 if variant == "_2" else iso.computeIsosurface_topo
+        a, t = fn(mesh.pos, mesh.norm, T["iso"], scr, dims, T["d"], center, mv, d_topo, d_dens, 0.0, d_res)
+        return a, t, mesh.pos[:t].clone(), mesh.norm[:t].clone(), scr.compVoxelArray[:a].clone()
+
+    a, t, pos, norm, comp = run((fx, fy, fz), gc, vol_topo, dens, result)
+    assert t > 0
+    parts, ta, tt = [], 0, 0
+    for r in range(nslabs):
+        z0, z1 = sharding.slab_bounds(fz, nslabs, r)
+        nzl = z1 - z0 + 1
+        sl = slice(z0 * plane, (z1 + 1) * plane)                # owned layers + the halo layer of the slab above
+        a_r, t_r, p_r, n_r, c_r = run((fx, fy, nzl), sharding.slab_gridcenter(gc, z0), vol_topo[sl].contiguous(), dens[sl].contiguous(),
+                                      result[sl].contiguous())
+        parts.append((p_r, n_r, c_r + z0 * (fx - 1) * (fy - 1)))
+        ta += a_r
+        tt += t_r
+    assert (ta, tt) == (a, t)
+    assert_bits_equal(torch.cat([p[0] for p in parts]), pos, "stored-field slabs pos")
+    assert_bits_equal(torch.cat([p[1] for p in parts]), norm, "stored-field slabs norm")
+    assert torch.equal(torch.cat([p[2] for p in parts]), comp)
+
+
 def test_svl_field_slabs_equal_single_pass(ctx):
     cfg = cases.SVL
     phi, coef = cases.svl_inputs(cfg)

@@ -100,3 +100,69 @@ def test_control_slab_covers_sampled_planes():
                 for z in (z0, z1):
                     i = z // ratio
                     assert c0 <= i <= c1 and min(i + 1, czg - 1) <= c1
+
+
+# ---------------------------------------------------------------- stored fields: one-plane +z halo exchange (config 5 sharded)
+def _topo_inputs():
+    """config 5 in miniature with non-trivial stored state: density (refined), grid_points with crossing parameters, d_result."""
+    T = cases.TOPO
+    fx, fy, fz = T["fdims"]
+    npts = fx * fy * fz
+    dens = orc.refine(cases.topo_coarse(T), T["fdims"], T["d"]).reshape(-1)
+    rng = np.random.RandomState(5)
+    gp = np.zeros(npts, orc.GP_DTYPE)
+    gp["t_x"] = np.where(rng.rand(npts) < 0.2, rng.rand(npts), 0).astype(np.float32)
+    gp["t_z"] = np.where(rng.rand(npts) < 0.2, rng.rand(npts), 0).astype(np.float32)
+    gp["val"][:150] = -1
+    result = rng.rand(npts).astype(np.float32)
+    return T, dens, gp, result
+
+
+def _topo_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T, dens, gp, result = _topo_inputs()
+    fx, fy, fz = T["fdims"]
+    plane = fx * fy
+    z0, z1 = sharding.slab_bounds(fz, world, rank)
+    nzl = z1 - z0 + 1
+    owned = nzl if rank == world - 1 else nzl - 1            # the top rank owns its last point layer too
+
+    def local(a, width, np_dtype, poison):
+        """local buffer of nzl point layers: owned layers filled, the halo layer poisoned until the exchange fills it"""
+        flat = np.ascontiguousarray(a[z0 * plane:(z0 + owned) * plane]).view(np_dtype).reshape(-1)
+        buf = torch.from_numpy(np.full(nzl * plane * width, poison, np_dtype))
+        buf[:flat.size] = torch.from_numpy(flat)
+        return buf
+    l_dens = local(dens, 1, np.float32, np.nan)
+    l_res = local(result, 1, np.float32, np.nan)
+    l_gp = local(gp, 4, np.int32, 0x7fc00000)
+    nbytes = sharding.exchange_halo_planes(dist, [(l_dens, plane), (l_gp, plane * 4), (l_res, plane)], nzl)
+    assert nbytes == (0 if rank == world - 1 else plane * 24)
+    gc = sharding.slab_gridcenter((0.0, 0.0, 0.0), z0)
+    r = orc.extract(orc.MODE_TOPO, (fx, fy, nzl), T["d"], gc, T["iso"], f0=l_dens.numpy(), f1=l_res.numpy(), gp=l_gp.numpy().view(orc.GP_DTYPE).reshape(-1),
+                    iso1=0.0)
+    per_rank, voff, aoff, totals = sharding.gather_counts(dist, r["active"], r["total"])
+    np.savez(os.path.join(out, "topo%d.npz" % rank), pos=r["pos"][:r["total"]], norm=r["norm"][:r["total"]],
+             comp=r["compVoxelArray"].astype(np.int64) + z0 * (fx - 1) * (fy - 1), voff=voff[rank], totals=np.array(totals))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_stored_field_halo_exchange_reproduces_single_rank(tmp_path, world):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_topo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    T, dens, gp, result = _topo_inputs()
+    single = orc.extract(orc.MODE_TOPO, T["fdims"], T["d"], (0, 0, 0), T["iso"], f0=dens, f1=result, gp=gp, iso1=0.0)
+    parts = [np.load(os.path.join(str(tmp_path), "topo%d.npz" % r)) for r in range(world)]
+    t = single["total"]
+    assert t > 0 and all(len(p["pos"]) > 0 for p in parts)
+    assert tuple(parts[0]["totals"]) == (single["active"], t)
+    assert [int(p["voff"]) for p in parts] == list(np.cumsum([0] + [len(p["pos"]) for p in parts[:-1]]))
+    assert np.array_equal(np.concatenate([p["pos"] for p in parts]).view(np.uint32), single["pos"][:t].view(np.uint32))
+    assert np.array_equal(np.concatenate([p["norm"] for p in parts]).view(np.uint32), single["norm"][:t].view(np.uint32))
+    assert np.array_equal(np.concatenate([p["comp"] for p in parts]), single["compVoxelArray"].astype(np.int64))
