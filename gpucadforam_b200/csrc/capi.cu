@@ -267,6 +267,18 @@ int gcb_computeIsosurface_topo(gcb_ctx* ctx, void* pos, void* norm, float isoVal
                        activeVoxels, totalVerts, d_compVoxelArray, maxVerts, vol_topo, vol_two, isovalue1, d_result, disp, disp_two);
 }
 
+// End of a legacy call that returns nothing through host pointers: the reference wrappers end in cudaDeviceSynchronize
+// (e.g. MarchingCubes_kernel.cu:458, :1074); with GCB_OPT_ASYNC_FIELDS the call only enqueues on the context's stream (the next
+// call that reports counts or writes a file synchronises, and launch errors surface here through cudaGetLastError).
+static int field_call_end(Ctx* C) {
+    if (C->options & GCB_OPT_ASYNC_FIELDS) {
+        GCB_CHECK(C, cudaGetLastError());
+        return 0;
+    }
+    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
+    return 0;
+}
+
 int gcb_copy_parameter(gcb_ctx* ctx, unsigned int* voxel_verts, float isoValue, gcb_uint3 gridSize, gcb_uint3 gridSizeShift, gcb_uint3 gridSizeMask,
                        gcb_float3 voxelSize, unsigned int numVoxels, gcb_grid_points* vol_one, float* vol_two, float* vol_lattice, int fixed, int dynamic,
                        float iso1, float iso2, int obj_union, int obj_diff, int obj_intersect) {
@@ -275,22 +287,19 @@ int gcb_copy_parameter(gcb_ctx* ctx, unsigned int* voxel_verts, float isoValue, 
     int r = k_copy_parameter(C, (GridPoint*)vol_one, vol_two, vol_lattice, dynamic != 0, iso1, iso2, gridSize.x, gridSize.y, gridSize.z, isoValue,
                              obj_union != 0, obj_diff != 0, obj_intersect != 0);
     if (r) return r;
-    GCB_CHECK(C, cudaStreamSynchronize(C->stream));  // the reference wrapper ends in cudaDeviceSynchronize (:458)
-    return 0;
+    return field_call_end(C);  // the reference wrapper ends in cudaDeviceSynchronize (:458)
 }
 int gcb_patch_topo_field(gcb_ctx* ctx, float* d_vec1, int Nx, int Ny, int Nz, gcb_grid_points* vol_one) {
     CTX(ctx);
     if (int r = k_patch_topo_field(C, d_vec1, Nx, Ny, Nz, (const GridPoint*)vol_one)) return r;
-    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
-    return 0;
+    return field_call_end(C);
 }
 
 // ------------------------------------------------------------------ fields, legacy signatures
-#define SYNC_RET(expr)                                   \
-    do {                                                 \
-        if (int r_ = (expr)) return r_;                  \
-        GCB_CHECK(C, cudaStreamSynchronize(C->stream));  \
-        return 0;                                        \
+#define SYNC_RET(expr)                  \
+    do {                                \
+        if (int r_ = (expr)) return r_; \
+        return field_call_end(C);       \
     } while (0)
 
 int gcb_distance_from_line(gcb_ctx* ctx, float* d, gcb_float3 center, gcb_float3 axis, float radius_1, float thickness_radial, float thickness_axial, int Nx,
@@ -401,8 +410,7 @@ int gcb_updateTexture(gcb_ctx* ctx, gcb_pitched_ptr p) {
     prm.extent = make_cudaExtent((size_t)C->tex_x * sizeof(float), C->tex_y, C->tex_z);
     prm.kind = cudaMemcpyDeviceToDevice;
     GCB_CHECK(C, cudaMemcpy3DAsync(&prm, C->stream));
-    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
-    return 0;
+    return field_call_end(C);
 }
 int gcb_deleteTexture(gcb_ctx* ctx) {
     CTX(ctx);

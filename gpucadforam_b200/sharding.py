@@ -50,7 +50,7 @@ def gather_counts(dist, active, verts, device="cpu"):
         dist.all_gather(allc, mine)
     else:
         allc = [mine]
-    per_rank = [(int(c[0]), int(c[1])) for c in allc]
+    per_rank = [(int(a), int(v)) for (a, v) in torch.stack(allc).tolist()]  # one device-to-host read for all ranks
     voff, aoff, v, a = [], [], 0, 0
     for (ac, vc) in per_rank:
         aoff.append(a)

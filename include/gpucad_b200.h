@@ -53,7 +53,11 @@ enum {
     GCB_OPT_FILL_STAGE_ARRAYS = 1, /* also write d_voxelVerts/_Scan/d_voxelOccupied/_Scan (parity tests) */
     GCB_OPT_LEGACY_MEMSET = 2,     /* cudaMemset(pos/norm, 0, maxVerts BYTES) as Isosurface.cu:120-121 (default on) */
     GCB_OPT_NO_TMA = 4,            /* force the LDG stage-in path (debug / A-B measurement) */
-    GCB_OPT_OBJ_HOST = 8           /* gcb_file_write_obj: weld and format on one host thread (as the reference does) instead of on the GPU */
+    GCB_OPT_OBJ_HOST = 8,          /* gcb_file_write_obj: weld and format on one host thread (as the reference does) instead of on the GPU */
+    GCB_OPT_ASYNC_FIELDS = 16      /* legacy calls without host results (primitives, create_lattice, normalise, refine, grating, svl, copy_parameter,
+                                      texture upload ...) only enqueue on the context's stream instead of ending in a device synchronise as the
+                                      reference wrappers do (MarchingCubes_kernel.cu:458, :1074); calls that report counts still synchronise.  Off by
+                                      default: the default keeps the reference's blocking semantics */
 };
 int gcb_set_options(gcb_ctx* ctx, unsigned int flags);
 /* number of kernels this library launched on the context since creation / last reset */

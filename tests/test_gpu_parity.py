@@ -688,6 +688,55 @@ def test_svl_field_slabs_equal_single_pass(ctx):
         assert_bits_equal(out, whole[z0:z1 + 1].contiguous().view(-1), "svl slab z0=%d" % z0)
 
 
+def test_async_field_calls_equal_blocking_calls(ctx):
+    """GCB_OPT_ASYNC_FIELDS: legacy calls without host results only enqueue on the context's stream.  The config-1 and config-2
+    sequences (create_lattice -> normalise_four -> latticeone; primitives -> copy_parameter -> computeIsosurface) and the config-5
+    sequence (texture upload -> refine -> computeIsosurface_2) must give the same counts and mesh bytes as the blocking default."""
+    dflt = _capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET
+
+    def gyroid():
+        n = 40
+        _, m, k = _lattice_inputs(ctx, n, 0)
+        dims = (n, n, n)
+        mv = max_verts_for(dims)
+        scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+        a, t = g.Isosurface(ctx).computeIsosurface_latticeone(m, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), mv, k, cases.BAND_LO,
+                                                              cases.BAND_HI)
+        return a, t, mesh.pos[:t].clone(), mesh.norm[:t].clone()
+
+    def csg():
+        cfg = cases.CSG
+        nx, ny, nz = cfg["dims"]
+        vol_one, boundary = _csg_pipeline(ctx, False)
+        mv = max_verts_for(cfg["dims"])
+        scr, mesh = g.Scratch((nx - 1) * (ny - 1) * (nz - 1)), g.MeshBuffers(mv)
+        a, t, _ = g.Isosurface(ctx).computeIsosurface(mesh.pos, mesh.norm, 0.0, scr, cfg["dims"], cfg["d"], (0, 0, 0), mv, vol_one, boundary, None,
+                                                      obj_union=False, obj_diff=True)
+        return a, t, mesh.pos[:t].clone(), mesh.norm[:t].clone()
+
+    def topo():
+        T = cases.TOPO
+        fx, fy, fz = T["fdims"]
+        dens = _upsample(ctx, T, cases.topo_coarse(T))
+        mv = max_verts_for(T["fdims"])
+        scr, mesh = g.Scratch((fx - 1) * (fy - 1) * (fz - 1)), g.MeshBuffers(mv)
+        a, t = g.Isosurface(ctx).computeIsosurface_2(mesh.pos, mesh.norm, T["iso"], scr, T["fdims"], T["d"], (0, 0, 0), mv, gp_zeros(fx * fy * fz), dens, 0.0,
+                                                     torch.zeros(fx * fy * fz, device="cuda"))
+        return a, t, mesh.pos[:t].clone(), mesh.norm[:t].clone()
+
+    try:
+        for seq in (gyroid, csg, topo):
+            ctx.set_options(dflt)
+            a0, t0, p0, n0 = seq()
+            ctx.set_options(dflt | _capi.GCB_OPT_ASYNC_FIELDS)
+            a1, t1, p1, n1 = seq()
+            assert t0 > 0 and (a0, t0) == (a1, t1), seq.__name__
+            assert_bits_equal(p1, p0, "async %s pos" % seq.__name__)
+            assert_bits_equal(n1, n0, "async %s norm" % seq.__name__)
+    finally:
+        ctx.set_options(dflt)
+
+
 # ------------------------------------------------------------------ edge cases
 def test_empty_and_full_fields(ctx):
     n = 24

@@ -83,6 +83,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--coarse", default="384,192,192")
+    ap.add_argument("--blocking", action="store_true", help="every legacy call ends in a synchronise, as the reference wrappers do")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -99,7 +100,7 @@ def main():
                                                                                                                                            device="cuda")
     if use_dist:
         dist.broadcast(coarse, 0)
-    ctx = g.Context(local, options=0)
+    ctx = g.Context(local, options=0 if args.blocking else g._capi.GCB_OPT_ASYNC_FIELDS)
     z0, z1 = sharding.slab_bounds(fz, world, rank)
     pipe = SlabPipeline(ctx, coarse, cdims, fdims, d, z0, z1, top=(rank == world - 1))
 
@@ -123,7 +124,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     per_rank, voff, aoff, (ta, tv) = out
     line = {"config": 5, "workload": "cantilever density %dx%dx%d (coarse %dx%dx%d, 40 struts, sigma 1.5): refine + +z halo layer + computeIsosurface_2, iso 0.4"
-            % (fx, fy, fz, cx, cy, cz), "n_gpus": world, "scaling": "strong", "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms[0]),
+            % (fx, fy, fz, cx, cy, cz), "n_gpus": world, "scaling": "strong", "legacy_calls": "blocking" if args.blocking else "enqueue only (GCB_OPT_ASYNC_FIELDS)", "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms[0]),
             "voxels_per_s": fx * fy * fz / (float(ms[0]) * 1e-3), "triangles_per_s": tv / 3 / (float(ms[0]) * 1e-3), "active_voxels": ta,
             "triangles": tv // 3, "per_rank_active_verts": per_rank, "vertex_offsets": voff,
             "halo": {"bytes_per_rank_per_step": fx * fy * 24 if use_dist else 0, "transport": "NCCL send/recv (P2P over NVLink)" if use_dist else "none",

@@ -24,6 +24,7 @@ import ref_py as ref  # noqa: E402
 
 ISO_MASK, BAND_LO, BAND_HI = 0.25, 0.20, 0.30
 PEAK_GBS = 6456.2
+LEGACY_CALLS = "blocking (as the reference wrappers)"
 
 
 def timed(fn, steps, warmup):
@@ -53,6 +54,7 @@ def line(cfg, desc, points, ms_ours, ms_ref, act, tot, parity, alg_bytes, extra=
            "reference_kernels": {"ms": ms_ref, "voxels_per_s": points / (ms_ref * 1e-3)},
            "speedup_vs_reference_kernels": ms_ref / ms_ours, "parity_full_size": parity,
            "algorithmic_bytes": alg_bytes, "hbm_roofline_frac_whole_step": alg_bytes / (ms_ours * 1e-3) / 1e9 / PEAK_GBS}
+    out["legacy_calls"] = LEGACY_CALLS
     if extra:
         out.update(extra)
     print(json.dumps(out), flush=True)
@@ -187,11 +189,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--configs", default="1,2,5")
     ap.add_argument("--tmp", default="/tmp")
+    ap.add_argument("--async-fields", action="store_true", help="GCB_OPT_ASYNC_FIELDS: legacy field calls only enqueue (ours arm)")
     args = ap.parse_args()
     if not ref.available():
         print(json.dumps({"error": "oracle/_ref/libgpucad_ref.so not built"}))
         return 1
-    ctx = g.Context(0, options=0)
+    global LEGACY_CALLS
+    if args.async_fields:
+        LEGACY_CALLS = "ours: enqueue only (GCB_OPT_ASYNC_FIELDS); reference kernels: blocking"
+    ctx = g.Context(0, options=g._capi.GCB_OPT_ASYNC_FIELDS if args.async_fields else 0)
     for c in args.configs.split(","):
         {"1": lambda: config1(ctx, args), "2": lambda: config2(ctx, args, args.tmp), "5": lambda: config5(ctx, args)}[c.strip()]()
     return 0
