@@ -380,13 +380,13 @@ int gcb_svl(gcb_ctx* ctx, float* d_svl, void* d_grating, int NX, int NY, int NZ,
 }
 int gcb_topo_field(gcb_ctx* ctx, float* topo_field, float* isosurf, float volfrac, int NX, int NY, int NZ) {
     CTX(ctx);
-    SYNC_RET(k_topo_field(C, topo_field, isosurf, volfrac, (size_t)(unsigned)(NX * NY * NZ)));
+    SYNC_RET(k_topo_field(C, topo_field, isosurf, volfrac, (size_t)NX * NY * NZ));
 }
 int gcb_primitive_field(gcb_ctx* ctx, gcb_grid_points* primitive_field, float* primitive_active, float* isosurf, float isoval, int fixed, int active, int NX,
                         int NY, int NZ) {
     CTX(ctx);
     (void)isoval;
-    SYNC_RET(k_primitive_field(C, (const GridPoint*)primitive_field, primitive_active, isosurf, (size_t)(unsigned)(NX * NY * NZ), fixed != 0, active != 0));
+    SYNC_RET(k_primitive_field(C, (const GridPoint*)primitive_field, primitive_active, isosurf, (size_t)NX * NY * NZ, fixed != 0, active != 0));
 }
 
 int gcb_setupTexture(gcb_ctx* ctx, int dx, int dy, int dz) {
