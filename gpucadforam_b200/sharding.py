@@ -76,6 +76,8 @@ def exchange_halo_planes(dist, fields, nzl):
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return 0
     rank, world = dist.get_rank(), dist.get_world_size()
+    if nzl < 2:
+        raise ValueError("exchange_halo_planes: rank %d owns no point layer (nzl = %d): more ranks than even cell layers" % (rank, nzl))
     ops, nbytes = [], 0
     for (buf, plane) in fields:
         if rank > 0:

@@ -166,3 +166,20 @@ def test_stored_field_halo_exchange_reproduces_single_rank(tmp_path, world):
     assert np.array_equal(np.concatenate([p["pos"] for p in parts]).view(np.uint32), single["pos"][:t].view(np.uint32))
     assert np.array_equal(np.concatenate([p["norm"] for p in parts]).view(np.uint32), single["norm"][:t].view(np.uint32))
     assert np.array_equal(np.concatenate([p["comp"] for p in parts]), single["compVoxelArray"].astype(np.int64))
+
+
+def test_slab_gridcenter_shift_is_exact_in_fp32():
+    """(z_local - (gc_z - z0)) == (z_global - gc_z) bit for bit for the centres the reference uses: 0 (initMC_two, main.cu:2125-2139)
+    and half-integer grid centres, for every layer of a 2048-high grid and every even slab start."""
+    z = np.arange(0, 2048, dtype=np.float32)
+    for gc in (0.0, 1023.5, 383.5, -12.25, 191.0):
+        for z0 in (0, 2, 256, 1024, 1790, 2046):
+            shifted = np.float32(sharding.slab_gridcenter((0.0, 0.0, gc), z0)[2])
+            zl = z[z0:] - np.float32(z0)
+            assert np.array_equal((zl - shifted).view(np.uint32), (z[z0:] - np.float32(gc)).view(np.uint32))
+
+
+def test_halo_exchange_single_rank_is_a_no_op():
+    buf = torch.arange(12, dtype=torch.float32)
+    assert sharding.exchange_halo_planes(None, [(buf, 4)], 3) == 0
+    assert torch.equal(buf, torch.arange(12, dtype=torch.float32))
