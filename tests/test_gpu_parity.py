@@ -737,6 +737,57 @@ def test_async_field_calls_equal_blocking_calls(ctx):
         ctx.set_options(dflt)
 
 
+# ------------------------------------------------------------------ C++ host side
+def _run_headless(*args):
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpucadforam_b200", "gpucad_headless")
+    assert os.path.exists(exe), "gpucad_headless not built (make -C gpucadforam_b200/csrc headless; __graft_entry__.build() does it)"
+    out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"activeVoxels=(\d+) totalVerts=(\d+) triangles=(\d+)", out.stdout)
+    assert m, out.stdout
+    return int(m.group(1)), int(m.group(2)), int(m.group(3))
+
+
+def test_headless_cpp_harness_matches_python_driven_calls(ctx, tmp_path):
+    """The C++ host mirror (host/gpucad_host.hpp: the reference's class and method names over the C ABI) driven by
+    host/headless_main.cpp replays Multitopo's call sequences without GLFW / ImGui / Vulkan.  Same sequences through the ctypes
+    binding must give the same counts, and for config 2 the same `.obj` bytes."""
+    N = 64
+    n = N ** 3
+    dims = (N, N, N)
+    iso, lat, mod = g.Isosurface(ctx), g.Gratings(ctx), g.Modelling(ctx)
+    mv = max_verts_for(dims)
+    # config 1: create_lattice -> normalise_buffer (in place) -> normalise_four (k in place) -> latticeone   (main.cu:3717-3719, :4113-4119)
+    a1, t1, tri1 = _run_headless(1, N)
+    vol, mask = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(vol, N, N, N, n, 0)
+    lat.GPU_buffer_normalise_buffer(vol, vol, n)
+    lat.GPU_buffer_normalise_four(vol, mask, vol, n, N, N, N, 0.20, 0.30)
+    scr, mesh = g.Scratch((N - 1) ** 3), g.MeshBuffers(mv)
+    a, t = iso.computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, 0.25, scr, dims, (1, 1, 1), (0, 0, 0), mv, vol, 0.20, 0.30)
+    assert t > 0 and (a1, t1, tri1) == (a, t, t // 3)
+    # config 2: sphere U box - cylinder, then .obj   (main.cu:3304-3465, :4695-4778)
+    obj_cpp, obj_py = str(tmp_path / "cpp.obj"), str(tmp_path / "py.obj")
+    a2, t2, _ = _run_headless(2, N, obj_cpp)
+    s, d = N / 256.0, (0.5, 0.5, 0.5)
+    boundary, latf, vol_one = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), gp_zeros(n)
+    mod.sphere_with_center(boundary, (0, 0, 0), 40 * s, 2, N, N, N, *d, False)
+    iso.copy_parameter(0.0, dims, d, vol_one, boundary, latf)
+    mod.cuboid(boundary, (0, 0, 0), (0.3, 0.2, 0.1), 90 * s, 50 * s, 60 * s, N, N, N, *d)
+    iso.copy_parameter(0.0, dims, d, vol_one, boundary, latf)
+    mod.distance_from_line(boundary, (0, 0, 0), (0, 0, 1), 18 * s, 2, 200 * s, N, N, N, *d, False)
+    a, t, nf = iso.computeIsosurface(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv, vol_one, boundary, latf, obj_union=False, obj_diff=True)
+    assert t > 0 and (a2, t2) == (a, t) and nf == t // 3
+    g.File_output(ctx).file_write_obj(mesh.pos, t, obj_py)
+    assert open(obj_cpp, "rb").read() == open(obj_py, "rb").read()
+    # configs 3 (fused SVL lattice through the host-buffer entry point) and 5 (refine + patch_topo_field + computeIsosurface_2) run and produce a mesh
+    for cfg in (3, 5):
+        a_, t_, tri_ = _run_headless(cfg, N)
+        assert t_ > 0 and t_ == 3 * tri_ and a_ > 0
+
+
 # ------------------------------------------------------------------ edge cases
 def test_empty_and_full_fields(ctx):
     n = 24
