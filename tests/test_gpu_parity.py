@@ -741,8 +741,11 @@ def test_async_field_calls_equal_blocking_calls(ctx):
 def _run_headless(*args):
     import re
     import subprocess
-    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpucadforam_b200", "gpucad_headless")
-    assert os.path.exists(exe), "gpucad_headless not built (make -C gpucadforam_b200/csrc headless; __graft_entry__.build() does it)"
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpucadforam_b200")
+    exe = os.path.join(pkg, "gpucad_headless")
+    if not os.path.exists(exe):  # __graft_entry__.build() makes it; a box that received only the library builds it here (host code only)
+        subprocess.run(["make", "-C", os.path.join(pkg, "csrc"), "headless"], capture_output=True, timeout=600)
+    assert os.path.exists(exe), "gpucad_headless not built (make -C gpucadforam_b200/csrc headless)"
     out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     m = re.search(r"activeVoxels=(\d+) totalVerts=(\d+) triangles=(\d+)", out.stdout)
