@@ -45,20 +45,58 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~5 ms (the region of
+    the default run is 60 ms, too short for `nvidia-smi -lms`); falls back to one `nvidia-smi` query stream when NVML is missing."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons, self.source = [], None, set(), None
+
+    def _start_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        if visible and all(t.strip().isdigit() for t in visible.split(",")):
+            idx = int(visible.split(",")[self.index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+
+        def poll():
+            while not self.stop_flag:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for bit, name in bits:
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.005)
+        self.thread = threading.Thread(target=poll, daemon=True)
+        self.thread.start()
+        self.source = "nvml"
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.thread = None
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            self.source = "nvidia-smi"
         except OSError:
             self.proc = None
 
@@ -67,12 +105,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 6:
@@ -82,11 +124,11 @@ class ClockSampler:
                 mx = float(parts[1])
             except ValueError:
                 continue
-            for nme, v in zip(names, parts[2:6]):
+            for nme, v in zip(self.NAMES, parts[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def main():
