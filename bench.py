@@ -44,6 +44,28 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffers of the e2e leg
+    are allocated, so that every rank's host-to-device copies read memory of the GPU's own socket instead of crossing the
+    inter-socket link (eight ranks copy 4.2 GB per step).  Best effort: returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = index
+        if visible and all(t.strip().isdigit() for t in visible.split(",")):
+            idx = int(visible.split(",")[index])
+        before = os.sched_getaffinity(0)
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(idx))
+        after = os.sched_getaffinity(0)
+        if not after:
+            os.sched_setaffinity(0, before)
+            return None
+        return len(after)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~5 ms (the region of
     the default run is 60 ms, too short for `nvidia-smi -lms`); falls back to one `nvidia-smi` query stream when NVML is missing."""
@@ -157,6 +179,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if (world > 1 or os.environ.get("GCB_BENCH_AFFINITY")) and not os.environ.get("GCB_BENCH_NO_AFFINITY") else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -291,7 +314,8 @@ def main():
             "e2e": {"value": points / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(phi.numel() * 4 * world), "d2h_bytes_per_step": int((16 + 8) * world),
                     "note": "control grids copied from pinned host memory each step; counts and min/max read back; the mesh stays in device memory "
-                            "as in the reference (Vulkan-exported vertex buffers)"},
+                            "as in the reference (Vulkan-exported vertex buffers)",
+                    "host_cpus_bound_rank0": affinity},
             "gpu_launches": g_launch,
             "roofline": {"bound": "hbm", "kernel": "mc_fused_kernel<M_BAND_RAW, TMA>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES if (F, R, NH, world) == (512, 4, 62, 1) else None,
