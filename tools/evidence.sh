@@ -16,3 +16,8 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:mc_f
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:svl_field -s 4 -c 1 -f -o gpurun_out/${t}_field python bench.py --steps 2 --warmup 3 --profile > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mc_fused -s 4 -c 1 -f -o gpurun_out/${t}_topo python tools/topo_probe.py --steps 1 > /dev/null 2>&1
 ls -la gpurun_out | grep ${t}_
+# C++ host side and the enqueue-only legacy sequences
+for c in 1 2 3 5; do timeout 60 ./gpucadforam_b200/gpucad_headless $c 2>&1 | tail -1; done > gpurun_out/${t}_headless.txt
+(timeout 300 python tools/config_bench.py --async-fields 2>&1 | tail -3) > gpurun_out/${t}_configs_async.json
+timeout 200 python tools/config5_multi.py --check 2>/dev/null | tail -1 > gpurun_out/${t}_config5_n1.json
+# multi-GPU (separate calls, charged N x):  gpurun --gpus 8 -- 'bash tools/_scale.sh'   and   gpurun --gpus 8 -- 'bash tools/halo_run.sh TAG 8 only'
