@@ -339,6 +339,13 @@ def _coef_array(coef):
     return (C.c_float * len(flat))(*flat)
 
 
+def minmax(ctx, d_in, n=None):
+    """(min(0, min f), max(0, max f)) on the host, the reference reduction's semantics (Gratings.cu:1394-1495)."""
+    lo, hi = C.c_float(0), C.c_float(0)
+    ctx.check(lib().gcb_minmax(ctx._h, _ptr(d_in), int(d_in.numel() if n is None else n), C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
 def svl_field(ctx, d_svl, d_phi, coef, cdims, fdims, d, slab=(0, 0), cz0=0, accumulate=False, d_minmax=None):
     cx, cy, czl = cdims
     nx2, ny2, nz2l = fdims

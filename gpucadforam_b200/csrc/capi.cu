@@ -82,12 +82,15 @@ int gcb_create(gcb_ctx** out, int device, void* stream) {
               cudaMallocHost(&c->h_totals, 16) == cudaSuccess && cudaMalloc(&c->d_minmax, 16) == cudaSuccess &&
               cudaMallocHost(&c->h_minmax, 16) == cudaSuccess;
     for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
-    if (!ok) { delete c; return 3; }
+    if (!ok) { gcb_destroy(reinterpret_cast<gcb_ctx*>(c)); return 3; }  // releases whatever was allocated before the failure
     *out = reinterpret_cast<gcb_ctx*>(c);
     return 0;
 }
 int gcb_destroy(gcb_ctx* ctx) {
     CTX(ctx);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};  // leave the caller's current device as it was
     cudaSetDevice(C->device);
     cudaFree(C->d_status); cudaFree(C->d_tile_counter); cudaFree(C->d_totals); cudaFreeHost(C->h_totals);
     cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef);

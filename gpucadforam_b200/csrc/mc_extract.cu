@@ -30,6 +30,9 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 namespace gcb {
 
@@ -446,7 +449,10 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
     } else {
         n = cross3(sub3(v[1], v[0]), sub3(v[2], v[0]));
     }
-    const unsigned long long limit = (unsigned long long)((unsigned int)A.max_verts - 3u);  // uint wrap as :2181
+    // `index < maxVerts - 3` in unsigned arithmetic (:2181).  For maxVerts < 3 that expression wraps to ~4e9 in the reference and
+    // every triangle would be written past the end of the caller's buffers; this library writes nothing then (counts are still
+    // reported).  Capacities above 2^32 - 1 (fused entry points only) use the exact test `index + 3 <= maxVerts`.
+    const unsigned long long limit = A.max_verts < 3ull ? 0ull : (unsigned long long)((unsigned int)A.max_verts - 3u);
     const bool ok = (A.max_verts > 0xffffffffull) ? (vidx + 3 <= A.max_verts) : (vidx < limit);
     if (ok) {
 #pragma unroll
@@ -927,14 +933,16 @@ static cudaError_t launch_mode(const McArgs& a, int grid, size_t smem, cudaStrea
 }
 
 template <int MODE, bool TMA>
-static int occupancy_one(size_t smem) {
+static int occupancy_one(size_t smem, size_t attr_smem) {
     int n = 0;
-    cudaFuncSetAttribute(mc_fused_kernel<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaFuncSetAttribute(mc_fused_kernel<MODE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attr_smem) != cudaSuccess) return 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mc_fused_kernel<MODE, TMA>, kThreads, smem);
     return n;
 }
 template <int MODE>
-static int occupancy(size_t smem, bool tma) { return tma ? occupancy_one<MODE, true>(smem) : occupancy_one<MODE, false>(smem); }
+static int occupancy(size_t smem, size_t attr_smem, bool tma) {
+    return tma ? occupancy_one<MODE, true>(smem, attr_smem) : occupancy_one<MODE, false>(smem, attr_smem);
+}
 
 int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts) {
     if (a.nx < 2 || a.ny < 2 || a.nz < 2) { *active = 0; *verts = 0; return 0; }
@@ -999,26 +1007,33 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     a.status_v = c->d_status + 4 + a.num_tiles;
     GCB_CHECK(c, cudaMemsetAsync(c->d_status, 0, (a.count_only ? 4 : need) * sizeof(unsigned long long), c->stream));
 
-    // occupancy query + shared-memory attribute once per (mode, stage path, tile size): both are host-side driver calls that a
-    // small grid would otherwise pay on every launch
-    // (the attribute belongs to the kernel function, not to a gcb context: the cache is per process and device)
+    // occupancy query + shared-memory attribute once per (device, mode, stage path, tile size): both are host-side driver calls
+    // that a small grid would otherwise pay on every launch.  The attribute belongs to the kernel FUNCTION (per device), not to
+    // a gcb context, so the cache is process-wide, keyed by device, and guarded by a mutex: contexts on several host threads may
+    // launch concurrently.  The attribute only ever grows (a launch may request less dynamic shared memory than the function's
+    // maximum, never more), so a context that still uses a smaller tile is never invalidated by another one's larger tile.
     if (a.mode < 0 || a.mode > M_REGION) return fail_msg(c, "bad mode");
-    struct OccEntry { size_t smem = 0; int occ = 0; };
-    static OccEntry occ_cache[16][6][2];
+    struct OccEntry { size_t attr_smem = 0; size_t smem = 0; int occ = 0; };
+    static std::mutex occ_mutex;
+    static std::map<std::tuple<int, int, int>, OccEntry> occ_cache;
     int occ = 1;
-    OccEntry& oc = occ_cache[c->device & 15][a.mode][a.use_tma ? 1 : 0];
-    if (oc.smem == smem && oc.occ > 0) occ = oc.occ;
-    else {
-        switch (a.mode) {
-        case M_LATTICE_ONE: occ = occupancy<M_LATTICE_ONE>(smem, a.use_tma); break;
-        case M_LATTICE: occ = occupancy<M_LATTICE>(smem, a.use_tma); break;
-        case M_CSG: occ = occupancy<M_CSG>(smem, a.use_tma); break;
-        case M_TOPO: occ = occupancy<M_TOPO>(smem, a.use_tma); break;
-        case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem, a.use_tma); break;
-        case M_REGION: occ = occupancy<M_REGION>(smem, a.use_tma); break;
-        default: return fail_msg(c, "bad mode");
+    {
+        std::lock_guard<std::mutex> lock(occ_mutex);
+        OccEntry& oc = occ_cache[std::make_tuple(c->device, a.mode, a.use_tma ? 1 : 0)];
+        if (oc.smem == smem && oc.occ > 0 && oc.attr_smem >= smem) occ = oc.occ;
+        else {
+            const size_t attr = std::max(oc.attr_smem, smem);
+            switch (a.mode) {
+            case M_LATTICE_ONE: occ = occupancy<M_LATTICE_ONE>(smem, attr, a.use_tma); break;
+            case M_LATTICE: occ = occupancy<M_LATTICE>(smem, attr, a.use_tma); break;
+            case M_CSG: occ = occupancy<M_CSG>(smem, attr, a.use_tma); break;
+            case M_TOPO: occ = occupancy<M_TOPO>(smem, attr, a.use_tma); break;
+            case M_BAND_RAW: occ = occupancy<M_BAND_RAW>(smem, attr, a.use_tma); break;
+            case M_REGION: occ = occupancy<M_REGION>(smem, attr, a.use_tma); break;
+            default: return fail_msg(c, "bad mode");
+            }
+            oc.smem = smem; oc.occ = occ; oc.attr_smem = attr;
         }
-        oc.smem = smem; oc.occ = occ;
     }
     if (occ < 1) return fail_msg(c, "extraction kernel does not fit on an SM");
     // persistent grid: every CTA resident (required by the look-back's forward progress)

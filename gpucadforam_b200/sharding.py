@@ -26,6 +26,13 @@ def slab_bounds(gnz, world, rank, align=2):
     return cut(rank), cut(rank + 1)
 
 
+def validate_slabs(gnz, world, align=2):
+    """Raises (identically on every rank: pure function of its arguments) if the cut leaves some rank without a cell layer."""
+    empty = [r for r in range(world) if slab_bounds(gnz, world, r, align)[1] <= slab_bounds(gnz, world, r, align)[0]]
+    if empty:
+        raise ValueError("z-slab sharding: %d point layers over %d ranks (alignment %d) leaves ranks %s without a cell layer" % (gnz, world, align, empty))
+
+
 def control_slab(z0, z1, ratio, czg):
     """Control-grid planes [c0, c1] a fine slab holding point layers z0..z1 samples (trilinear: floor(z/ratio) and +1)."""
     c0 = z0 // ratio
@@ -76,8 +83,14 @@ def exchange_halo_planes(dist, fields, nzl):
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return 0
     rank, world = dist.get_rank(), dist.get_world_size()
-    if nzl < 2:
-        raise ValueError("exchange_halo_planes: rank %d owns no point layer (nzl = %d): more ranks than even cell layers" % (rank, nzl))
+    # An empty slab (more ranks than aligned cell layers) is a configuration error.  It is detected COLLECTIVELY -- one MIN
+    # all-reduce of the local layer count -- so that every rank raises before any point-to-point operation is posted; a rank that
+    # raised on its own would leave its neighbours waiting in batch_isend_irecv forever.
+    least = torch.tensor([int(nzl)], dtype=torch.int64, device=fields[0][0].device if fields else "cpu")
+    dist.all_reduce(least, op=dist.ReduceOp.MIN)
+    if int(least[0]) < 2:
+        raise ValueError("exchange_halo_planes: a rank owns no point layer (smallest slab holds %d layers, rank %d holds %d): "
+                         "more ranks than aligned cell layers" % (int(least[0]), rank, nzl))
     ops, nbytes = [], 0
     for (buf, plane) in fields:
         if rank > 0:

@@ -14,19 +14,28 @@ import torch
 HARMONICS = [(i, j, k) for k in range(-2, 3) for j in range(-2, 3) for i in range(-2, 3)][:62]
 
 
-def gyroid_coefficients(n=61):
-    """c_h of the gyroid unit cell truncated to 5x5x5 (main.cu:3578-3711 in spirit): FFT of the
-    reference's unit-cell expression (Fft_lattice.cu:28-34) sampled on n^3 points, divided by n^3."""
+def _unit_cell_coefficients(expr, n):
     ax = ((np.arange(n, dtype=np.float64) / (n - 1)) - 0.5) / 0.5
     a = (3.14 * ax).astype(np.float32).astype(np.float64)
     zz, yy, xx = np.meshgrid(a, a, a, indexing="ij")
-    f = np.cos(xx) * np.sin(yy) + np.cos(yy) * np.sin(zz) + np.cos(zz) * np.sin(xx)
+    f = expr(xx, yy, zz)
     spec = np.fft.fftn(f) / f.size
     out = []
     for (i, j, k) in HARMONICS:
         c = spec[k % n, j % n, i % n]
         out.append((float(np.float32(c.real)), float(np.float32(c.imag))))
     return out
+
+
+def gyroid_coefficients(n=61):
+    """c_h of the gyroid unit cell truncated to 5x5x5 (main.cu:3578-3711 in spirit): FFT of the
+    reference's unit-cell expression (Fft_lattice.cu:28-34) sampled on n^3 points, divided by n^3."""
+    return _unit_cell_coefficients(lambda x, y, z: np.cos(x) * np.sin(y) + np.cos(y) * np.sin(z) + np.cos(z) * np.sin(x), n)
+
+
+def schwarz_p_coefficients(n=61):
+    """c_h of the Schwarz-P unit cell, lattice type 1 of create_lattice (Fft_lattice.cu:37-40), same recipe as the gyroid set."""
+    return _unit_cell_coefficients(lambda x, y, z: np.cos(x) + np.cos(y) + np.cos(z), n)
 
 
 def phase_grids(cx, cy, cz, device="cpu", z0=0, cz_total=None, harmonics=None, periods=6.0, dtype=torch.float32):

@@ -51,7 +51,10 @@ int gcb_set_stream(gcb_ctx* ctx, void* stream);
 /* option flags */
 enum {
     GCB_OPT_FILL_STAGE_ARRAYS = 1, /* also write d_voxelVerts/_Scan/d_voxelOccupied/_Scan (parity tests) */
-    GCB_OPT_LEGACY_MEMSET = 2,     /* cudaMemset(pos/norm, 0, maxVerts BYTES) as Isosurface.cu:120-121 (default on) */
+    GCB_OPT_LEGACY_MEMSET = 2,     /* cudaMemset(pos/norm, 0, maxVerts BYTES) as Isosurface.cu:120-121 (default on).  One divergence:
+                                      the reference clears only after it knows activeVoxels > 0 and leaves both buffers untouched for
+                                      an empty surface; here the clear is enqueued before the fused kernel, so it also happens when
+                                      activeVoxels == 0 (consumers honour totalVerts either way) */
     GCB_OPT_NO_TMA = 4,            /* force the LDG stage-in path (debug / A-B measurement) */
     GCB_OPT_OBJ_HOST = 8,          /* gcb_file_write_obj: weld and format on one host thread (as the reference does) instead of on the GPU */
     GCB_OPT_ASYNC_FIELDS = 16      /* legacy calls without host results (primitives, create_lattice, normalise, refine, grating, svl, copy_parameter,
@@ -78,6 +81,12 @@ int gcb_destroyAllTextureObjects(gcb_ctx* ctx);
 void gcb_tables(unsigned int* tri, unsigned int* nverts);
 
 /* ------------------------------------------------------------------ extraction (legacy signatures) */
+/* Capacity rule shared by every extraction entry point: maxVerts is the capacity of pos / norm in VERTICES and a triangle is
+ * written iff its first vertex index satisfies `index < maxVerts - 3` (the reference's guard, MarchingCubes_kernel.cu:2181) --
+ * so a buffer that must hold all totalVerts vertices needs maxVerts >= totalVerts + 3, and with maxVerts == totalVerts the last
+ * triangle is dropped exactly as in the reference.  maxVerts < 3 writes nothing (the reference's unsigned `maxVerts - 3` wraps
+ * there and writes out of bounds; that is not reproduced).  gcb_extract_band_raw / gcb_svl_lattice* with maxVerts > 2^32 - 1
+ * use the exact test `index + 3 <= maxVerts`.  Counts (activeVoxels, totalVerts) are always the untruncated ones. */
 /* Isosurface::computeIsosurface  (src/Isosurface.h:28-33, Isosurface.cu:44-134) -- CSG / primitives */
 int gcb_computeIsosurface(gcb_ctx* ctx, float* vol, gcb_uint3 raster_grid, void* pos, void* norm, float isoValue,
     unsigned int numVoxels, unsigned int* d_voxelVerts, unsigned int* d_voxelVertsScan, unsigned int* d_voxelOccupied,

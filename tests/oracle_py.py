@@ -223,6 +223,29 @@ def copy_parameter(vol_one, vol_two, vol_lattice, dims, iso, dynamic=False, iso1
     return vol_one
 
 
+def primitive_field(prim, active, isosurf, fixed, dynamic):
+    """orc_primitive_field (Gratings.cu:1695-1725): returns the patched copy of isosurf."""
+    out = _f(isosurf).copy()
+    a = None if active is None else _f(active)
+    lib().orc_primitive_field(_p(prim), _p(a), _p(out), C.c_size_t(out.size), int(fixed), int(dynamic))
+    return out
+
+
+def topo_field(topo, isosurf, volfrac):
+    """orc_topo_field (Gratings.cu:1666-1681)."""
+    out = _f(isosurf).copy()
+    t = _f(topo)
+    lib().orc_topo_field(_p(t), _p(out), C.c_float(volfrac), C.c_size_t(out.size))
+    return out
+
+
+def patch_topo_field(d, dims, vol_one):
+    """orc_patch_topo_field (Isosurface.cu:674-707), index guard restated literally."""
+    out = _f(d).copy()
+    lib().orc_patch_topo_field(_p(out), dims[0], dims[1], dims[2], _p(vol_one))
+    return out
+
+
 def write_obj(pos, total_verts, filename):
     pos = _f(pos)
     return lib().orc_write_obj(_p(pos), C.c_uint32(total_verts), filename.encode())

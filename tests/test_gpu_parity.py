@@ -1231,3 +1231,131 @@ def test_region_metadata_written_past_max_verts(ctx):
     assert (a2, t2) == (act, tot)
     assert torch.equal(meta, meta2)
     assert torch.equal(mesh.pos[:small - 3], mesh2.pos[:small - 3]) and bool((mesh2.pos[small - 3:] == 0).all())
+
+
+# ------------------------------------------------------------------ mask helpers
+def _gp_random(n, seed, vals=(-1, 0, 1)):
+    rng = np.random.RandomState(seed)
+    gp = np.zeros(n, orc.GP_DTYPE)
+    gp["val"] = rng.choice(np.array(vals, np.int32), n)
+    gp["t_x"], gp["t_y"], gp["t_z"] = rng.rand(n), rng.rand(n), rng.rand(n)
+    return gp
+
+
+@pytest.mark.parametrize("which", ["fixed", "dynamic", "neither"])
+def test_primitive_field_three_way(ctx, which):
+    """Gratings::primitive_field (Gratings.cu:1695-1737): isosurf = FLT_MAX where primitive_fixed.val > -1 (fixed) or
+    primitive_active >= 0 (dynamic, checked only when fixed is false); untouched otherwise."""
+    dims = (32, 16, 24)  # 12288 points: a multiple of 1024 (the reference grid is ceil(n / 1024) blocks of 1024)
+    n = dims[0] * dims[1] * dims[2]
+    rng = np.random.RandomState(5)
+    gp = _gp_random(n, 6)
+    active = rng.uniform(-1, 1, n).astype(np.float32)
+    active[::7] = 0.0
+    active[3::11] = -0.0
+    iso0 = rng.uniform(-2, 2, n).astype(np.float32)
+    fixed, dynamic = which == "fixed", which == "dynamic"
+    d_gp, d_act = gp_from_numpy(gp), dev(active)
+    mine = dev(iso0)
+    g.Gratings(ctx).primitive_field(d_gp, d_act, mine, 0.0, fixed, dynamic, *dims)
+    o = orc.primitive_field(gp, active, iso0, fixed, dynamic)
+    assert np.array_equal(mine.cpu().numpy().view(np.uint32), o.view(np.uint32)), "primitive_field vs oracle"
+    if which != "neither":
+        assert int((mine == torch.finfo(torch.float32).max).sum()) > 0
+    else:
+        assert np.array_equal(mine.cpu().numpy().view(np.uint32), iso0.view(np.uint32))
+    if HAVE_REF:
+        theirs = dev(iso0)
+        ref.primitive_field(d_gp, d_act, theirs, fixed, dynamic, dims)
+        assert_bits_equal(mine, theirs, "primitive_field vs reference")
+
+
+def test_topo_field_three_way(ctx):
+    """Gratings::topo_field (Gratings.cu:1666-1692): isosurf = 0 where density < volfrac (strict)."""
+    dims = (32, 16, 24)
+    n = dims[0] * dims[1] * dims[2]
+    rng = np.random.RandomState(9)
+    topo = rng.uniform(0, 1, n).astype(np.float32)
+    topo[::5] = np.float32(0.4)   # equal to the threshold: kept
+    iso0 = rng.uniform(-2, 2, n).astype(np.float32)
+    mine = dev(iso0)
+    g.Gratings(ctx).topo_field(dev(topo), mine, 0.4, *dims)
+    o = orc.topo_field(topo, iso0, 0.4)
+    assert np.array_equal(mine.cpu().numpy().view(np.uint32), o.view(np.uint32)), "topo_field vs oracle"
+    assert np.array_equal(mine.cpu().numpy()[::5].view(np.uint32), iso0[::5].view(np.uint32))
+    if HAVE_REF:
+        theirs = dev(iso0)
+        ref.topo_field(dev(topo), theirs, 0.4, dims)
+        assert_bits_equal(mine, theirs, "topo_field vs reference")
+
+
+@pytest.mark.parametrize("dims", [(16, 8, 32), (32, 16, 8), (16, 16, 16), (8, 4, 64)], ids=["nz_gt_nx", "nx_gt_nz", "cube", "z_over_nx_ge_ny"])
+def test_patch_topo_field_three_way(ctx, dims):
+    """Isosurface::patch_topo_field (Isosurface.cu:674-722): d = 0 where vol_one.val == 1, behind the reference's index guard
+    (x = tx / (Nx Ny), y = x / Nx, z = x % Nx -- i.e. it tests the LAYER number against Nx, its quotient by Nx against Ny and its
+    remainder against Nz), which switches whole layers off when Nz > Nx.  Point counts are multiples of 1024 (the reference
+    kernel has no tx < n guard)."""
+    n = dims[0] * dims[1] * dims[2]
+    rng = np.random.RandomState(13)
+    gp = _gp_random(n, 14)
+    d0 = rng.uniform(0.1, 1.0, n).astype(np.float32)
+    mine = dev(d0)
+    d_gp = gp_from_numpy(gp)
+    g.Isosurface(ctx).patch_topo_field(mine, dims[0], dims[1], dims[2], d_gp)
+    o = orc.patch_topo_field(d0, dims, gp)
+    got = mine.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), o.view(np.uint32)), "patch_topo_field vs oracle"
+    # the guard, spelled independently: layer z is patched iff z < Nx and z // Nx < Ny and z % Nx < Nz
+    z = np.arange(n) // (dims[0] * dims[1])
+    live = (z < dims[0]) & (z // dims[0] < dims[1]) & (z % dims[0] < dims[2])
+    expect = np.where(live & (gp["val"] == 1), np.float32(0), d0)
+    assert np.array_equal(got, expect)
+    if dims[2] > dims[0]:
+        assert not live.all() and int(((gp["val"] == 1) & ~live).sum()) > 0   # the odd guard is actually exercised
+    if HAVE_REF:
+        theirs = dev(d0)
+        ref.patch_topo_field(theirs, dims, d_gp)
+        assert_bits_equal(mine, theirs, "patch_topo_field vs reference")
+
+
+# ------------------------------------------------------------------ computeIsosurface_lattice with mask ids {2, 0}
+def _two_band_mask(ctx, n):
+    """mask = 1 where k (gyroid) lies in [BAND_LO, BAND_HI], else 2 where k2 (second TPMS) lies in [0.45, 0.55], else 0 -- every
+    {1,0} edge then brackets a band level of k and every {2,0} edge a band level of k2, so vertexInterp3_new (:3269-3416) always
+    assigns t (the reference leaves it uninitialised otherwise)."""
+    _, m1, k1 = _lattice_inputs(ctx, n, 0)
+    f2 = torch.zeros(n * n * n, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(f2, n, n, n, n * n * n, 1)
+    lat = g.Gratings(ctx)
+    lat.GPU_buffer_normalise_buffer(f2, f2, f2.numel())
+    m2, k2 = torch.zeros_like(f2), torch.zeros_like(f2)
+    lat.GPU_buffer_normalise_four(f2, m2, k2, f2.numel(), n, n, n, 0.45, 0.55)
+    mask = torch.where(m1 == 1.0, torch.ones_like(m1), torch.where(m2 == 1.0, torch.full_like(m1, 2.0), torch.zeros_like(m1)))
+    return mask.contiguous(), k1, k2
+
+
+@pytest.mark.parametrize("n", [40, 64])
+def test_lattice_variant_second_band_ids_two_zero(ctx, n):
+    """generateTriangles_lattice_kernel_new with a mask that holds the value 2: edges with ids {2,0} take the second half of
+    vertexInterp3_new (MarchingCubes_kernel.cu:3347-3413; interp_band_two in mc_extract.cu) on vol_two with iso1 / iso2."""
+    mask, k1, k2 = _two_band_mask(ctx, n)
+    assert int((mask == 2.0).sum()) > 1000 and int((mask == 1.0).sum()) > 1000
+    dims, vox, cen = (n, n, n), (0.5, 0.5, 0.5), (3.0, -2.0, 1.0)
+    mv = max_verts_for(dims)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    act, tot = g.Isosurface(ctx).computeIsosurface_lattice(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, dims, vox, cen, mv, k1, k2, cases.BAND_LO,
+                                                           cases.BAND_HI, 0.45, 0.55)
+    mine = mine_result(scr, mesh, dims, act, tot)
+    o = orc.extract(orc.MODE_LATTICE, dims, vox, cen, cases.ISO_MASK, f0=mask.cpu().numpy(), f1=k1.cpu().numpy(), f2=k2.cpu().numpy(), iso1=cases.BAND_LO,
+                    iso2=cases.BAND_HI, iso1b=0.45, iso2b=0.55, max_verts=mv)
+    compare_extractions(mine, o, "lattice ids {2,0} vs oracle", exact_mesh=False)
+    # the {2,0} path is really taken: with vol_two zeroed the vertices on those edges move
+    scr0, mesh0 = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    a0, t0 = g.Isosurface(ctx).computeIsosurface_lattice(mask, mesh0.pos, mesh0.norm, cases.ISO_MASK, scr0, dims, vox, cen, mv, k1, torch.zeros_like(k2),
+                                                         cases.BAND_LO, cases.BAND_HI, 0.45, 0.55)
+    assert (a0, t0) == (act, tot) and not torch.equal(mesh0.pos[:tot], mesh.pos[:tot])
+    if HAVE_REF:
+        scr2, mesh2 = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+        a2, t2 = ref.isosurface_lattice(False, False, mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, vox, cen, scr2, mv, k1, k2, cases.BAND_LO,
+                                        cases.BAND_HI, 0.45, 0.55)
+        compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "lattice ids {2,0} vs reference", exact_mesh=True)

@@ -127,3 +127,43 @@ def test_unit_spectrum_matches_fft_and_is_hermitian():
     F2 = np.fft.fftn(f2.astype(np.float64)) / f2.size
     w2 = np.array([F2[k % 9, j % 14, i % 20] for k in (-1, 0, 1) for j in (-1, 0, 1) for i in (-1, 0, 1)])
     assert np.abs(g2 - w2).max() <= 1e-6 * np.abs(w2).max()
+
+
+def test_mask_helpers_known_answers():
+    """primitive_field / topo_field / patch_topo_field against hand-written expectations."""
+    n = 64
+    gp = np.zeros(n, orc.GP_DTYPE)
+    gp["val"] = np.tile(np.array([-1, 0, 1, -1], np.int32), n // 4)
+    iso = np.arange(n, dtype=np.float32) - 10
+    fmax = np.finfo(np.float32).max
+    o = orc.primitive_field(gp, None, iso, True, False)
+    assert np.array_equal(o, np.where(gp["val"] > -1, fmax, iso))
+    act = np.linspace(-1, 1, n).astype(np.float32)
+    act[5] = -0.0
+    o = orc.primitive_field(gp, act, iso, False, True)
+    assert np.array_equal(o, np.where(act >= 0, fmax, iso)) and o[5] == fmax   # -0.0 >= 0
+    o = orc.topo_field(act, iso, 0.25)
+    assert np.array_equal(o, np.where(act < np.float32(0.25), np.float32(0), iso))
+    # patch_topo_field: the reference guard looks at the layer number only (Isosurface.cu:684-692)
+    dims = (4, 2, 8)
+    n = dims[0] * dims[1] * dims[2]
+    gp = np.zeros(n, orc.GP_DTYPE)
+    gp["val"] = 1
+    d = np.ones(n, np.float32)
+    o = orc.patch_topo_field(d, dims, gp)
+    layer = np.arange(n) // (dims[0] * dims[1])
+    assert np.array_equal(o == 0, layer < dims[0])   # layers z >= Nx are never patched
+
+
+def test_lattice_ids_two_zero_use_the_second_field():
+    """vertexInterp3_new second half (MarchingCubes_kernel.cu:3347-3413): an edge joining mask ids {2,0} is interpolated on vol_two
+    with iso1 / iso2.  One cell column with a single inside corner plane gives closed-form vertices."""
+    dims = (2, 2, 2)
+    mask = np.zeros(dims[::-1], np.float32)
+    mask[1] = 2.0                     # z = 1 plane: id 2 (outside: 2 >= iso), z = 0 plane: id 0 (inside)
+    k1 = np.zeros_like(mask)
+    k2 = np.zeros_like(mask)
+    k2[1] = 0.8                       # crossing of iso1b = 0.6 at t = 0.75 along z
+    r = orc.extract(orc.MODE_LATTICE, dims, (1, 1, 1), (0, 0, 0), cases.ISO_MASK, f0=mask, f1=k1, f2=k2, iso1=0.2, iso2=0.3, iso1b=0.6, iso2b=0.9)
+    assert r["active"] == 1 and r["total"] == 6
+    assert np.allclose(r["pos"][:6, 2], 0.75)

@@ -183,3 +183,36 @@ def test_halo_exchange_single_rank_is_a_no_op():
     buf = torch.arange(12, dtype=torch.float32)
     assert sharding.exchange_halo_planes(None, [(buf, 4)], 3) == 0
     assert torch.equal(buf, torch.arange(12, dtype=torch.float32))
+
+
+def _empty_slab_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gnz = 5
+    z0, z1 = sharding.slab_bounds(gnz, world, rank)
+    nzl = (z1 - z0 + 1) if z1 > z0 else 1
+    buf = torch.zeros(max(nzl, 1) * 4)
+    try:
+        sharding.exchange_halo_planes(dist, [(buf, 4)], nzl)
+        verdict = "no error"
+    except ValueError as e:
+        verdict = "ValueError" if "owns no point layer" in str(e) else "other: %s" % e
+    open(os.path.join(out, "empty%d.txt" % rank), "w").write(verdict)
+    dist.destroy_process_group()
+
+
+def test_empty_slab_fails_on_every_rank_instead_of_hanging(tmp_path):
+    """5 point layers over 4 ranks leaves ranks without a cell layer: every rank must raise BEFORE any send/recv is posted
+    (a rank that raised alone would leave its neighbours blocked in batch_isend_irecv)."""
+    world = 4
+    assert sharding.slab_bounds(5, world, 0) == (0, 0)
+    with pytest.raises(ValueError):
+        sharding.validate_slabs(5, world)
+    sharding.validate_slabs(40, 3)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_empty_slab_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert [open(os.path.join(str(tmp_path), "empty%d.txt" % r)).read() for r in range(world)] == ["ValueError"] * world
