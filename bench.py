@@ -153,6 +153,186 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def workload_config(F, R, NH, gnz, world, strong):
+    """The `config` object of the JSON line: identical in both arms (the driver compares them)."""
+    c = F // R
+    return {"workload": "config 3: spatially varying gyroid lattice, %d harmonics, control grid %dx%dx%d -> fine %dx%dx%d, band [0.20,0.30]"
+                        % (NH, c, c, gnz // R, F, F, gnz),
+            "fine": [F, F, gnz], "control": [c, c, gnz // R], "ratio": R, "harmonics": NH, "parallelism": "z-slabs x%d" % world,
+            "scaling_mode": "strong" if strong else "weak",
+            "l2_policy": "inputs larger than L2: field, control grids and mesh are each far above 126 MB per rank and are streamed once per step"}
+
+
+class SvlLeg:
+    """One SVL-lattice workload (configs 3 / 4) on this rank's z-slab: set-up, device-timed steps, end-to-end steps."""
+
+    def __init__(self, env, F, R, NH, gnz, fast=False, spectrum="gyroid"):
+        torch, g, sharding, synth = env["torch"], env["g"], env["sharding"], env["synth"]
+        self.env, self.F, self.R, self.NH, self.gnz, self.fast = env, F, R, NH, gnz, fast
+        rank, world, dev = env["rank"], env["world"], env["dev"]
+        sharding.validate_slabs(gnz, world)
+        self.z0, self.z1 = sharding.slab_bounds(gnz, world, rank)
+        self.nzl = self.z1 - self.z0 + 1
+        self.d = (1.0 / R,) * 3
+        self.cxy, self.czg = F // R, gnz // R
+        self.c0, c1 = sharding.control_slab(self.z0, self.z1, R, self.czg)
+        self.czl = c1 - self.c0 + 1
+        self.coef = (synth.gyroid_coefficients() if spectrum == "gyroid" else synth.schwarz_p_coefficients())[:NH]
+        self.phi = synth.phase_grids(self.cxy, self.cxy, self.czl, device=dev, z0=self.c0, cz_total=self.czg, harmonics=synth.HARMONICS[:NH], periods=F / 40.0)
+        torch.cuda.synchronize()
+        self.ctx = env["ctx"]
+        self.opts = g._capi.GCB_OPT_FAST_FIELD if fast else 0
+        self.svl = torch.empty(F * F * self.nzl, device=dev)
+        self.mm = torch.zeros(2, device=dev)
+        self.ldims = (F, F, self.nzl)
+        self.ctx.set_options(self.opts)
+        a, b = self._field_and_minmax()
+        self.act, self.tot = g.extract_band_raw(self.ctx, self.svl, a, b, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), None, None, 0,
+                                                slab=(self.z0, gnz), count_only=True)
+        self.cap = self.tot + 3   # count-then-allocate (SURVEY.md 7 "Capacity"); +3: the reference's `index < maxVerts - 3` guard
+        self.mesh = g.MeshBuffers(self.cap, device=dev)
+        self.hphi = None
+
+    def _field_and_minmax(self):
+        g, sharding = self.env["g"], self.env["sharding"]
+        g.svl_field(self.ctx, self.svl, self.phi, self.coef, (self.cxy, self.cxy, self.czl), self.ldims, self.d, slab=(self.z0, self.gnz), cz0=self.c0, d_minmax=self.mm)
+        return sharding.allreduce_minmax(self.env["dist"], self.mm)   # one 2-float all-reduce (N > 1), then the values on the host
+
+    def step(self):
+        g = self.env["g"]
+        a, b = self._field_and_minmax()
+        return g.extract_band_raw(self.ctx, self.svl, a, b, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap,
+                                  slab=(self.z0, self.gnz))
+
+    def e2e_step(self):
+        g, sharding, torch = self.env["g"], self.env["sharding"], self.env["torch"]
+        if self.hphi is None:
+            self.hphi = torch.empty(self.phi.shape, dtype=torch.float32, pin_memory=True)
+            self.hphi.copy_(self.phi)
+            self.phi_scratch = torch.empty_like(self.phi)
+        cd = (self.cxy, self.cxy, self.czl)
+        if self.env["world"] == 1:
+            a_, t_, _ = g.svl_lattice_host(self.ctx, self.hphi, self.phi_scratch, self.svl, self.coef, cd, self.ldims, self.d, ISO_MASK, BAND_LO, BAND_HI, self.d,
+                                           (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap)
+            return a_, t_
+        g.svl_field_host(self.ctx, self.svl, self.hphi, self.phi_scratch, self.coef, cd, self.ldims, self.d, slab=(self.z0, self.gnz), cz0=self.c0, d_minmax=self.mm)
+        a_, b_ = sharding.allreduce_minmax(self.env["dist"], self.mm)
+        return g.extract_band_raw(self.ctx, self.svl, a_, b_, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap,
+                                  slab=(self.z0, self.gnz))
+
+    def run(self, steps, warmup, e2e=True, sampler=None):
+        """Device-timed steps (CUDA events on the current stream, barrier + synchronize on both sides), then the e2e steps.
+        Returns this rank's numbers; reduce() turns them into the whole-job line."""
+        torch, env = self.env["torch"], self.env
+        self.ctx.set_options(self.opts)
+        for _ in range(warmup):
+            res = self.step()
+        assert res == (self.act, self.tot), "count pass and mesh pass disagree"
+        self.ctx.enable_kernel_timing(True)
+        env["barrier"]()
+        if sampler is not None:
+            sampler.start()
+        self.ctx.reset_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ext_ms, fld_ms = [], []
+        env["barrier"]()
+        ev0.record()
+        for _ in range(steps):
+            self.step()
+            ext_ms.append(self.ctx.last_extract_kernel_ms())   # events already complete: the step ends with the counts on the host
+            fld_ms.append(self.ctx.last_field_kernel_ms())
+        ev1.record()
+        env["barrier"]()
+        launches = self.ctx.launch_count()
+        clocks = sampler.stop() if sampler is not None else None
+        ms = ev0.elapsed_time(ev1) / steps
+        self.ctx.enable_kernel_timing(False)
+        out = {"ms": ms, "ext_ms": sum(ext_ms) / len(ext_ms), "fld_ms": sum(fld_ms) / len(fld_ms), "launches": launches, "clocks": clocks, "e2e_ms": None}
+        if e2e:
+            for _ in range(2):
+                r2 = self.e2e_step()
+            assert r2 == (self.act, self.tot)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            env["barrier"]()
+            e0.record()
+            for _ in range(steps):
+                self.e2e_step()
+            e1.record()
+            env["barrier"]()
+            out["e2e_ms"] = e0.elapsed_time(e1) / steps
+        return out
+
+    def reduce(self, r):
+        """max over ranks of the times, global counts (all-gather + exclusive scan = global vertex offsets)."""
+        torch, env, sharding = self.env["torch"], self.env, self.env["sharding"]
+        dist, dev = env["dist"], env["dev"]
+        stats = torch.tensor([r["ms"], r["e2e_ms"] or 0.0, r["ext_ms"], r["fld_ms"]], device=dev, dtype=torch.float64)
+        per_rank, voff, aoff, (g_act, g_tot) = sharding.gather_counts(dist, self.act, self.tot, device=dev)
+        g_launch = r["launches"]
+        if env["world"] > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+            lt = torch.tensor([r["launches"]], device=dev, dtype=torch.int64)
+            dist.all_reduce(lt)
+            g_launch = int(lt[0])
+        ms, e2e_ms, ext_k, fld_k = [float(x) for x in stats.cpu()]
+        return {"ms": ms, "e2e_ms": e2e_ms if r["e2e_ms"] is not None else None, "ext_ms": ext_k, "fld_ms": fld_k, "launches": g_launch,
+                "g_act": g_act, "g_tot": g_tot, "per_rank_verts": [v for (_, v) in per_rank]}
+
+    def summary(self, red, peak):
+        """Compact record of a secondary leg (fast mode, ratio 2, config 4)."""
+        F, gnz = self.F, self.gnz
+        points = F * F * gnz
+        alg_ext = 4.0 * F * F * self.nzl + 32.0 * self.tot
+        out = {"grid": [F, F, gnz], "control": [self.cxy, self.cxy, self.czg], "ratio": self.R, "field_mode": "fast" if self.fast else "exact",
+               "ms_per_step": red["ms"], "value": points / (red["ms"] * 1e-3), "unit": "voxels/s", "triangles": red["g_tot"] // 3,
+               "triangles_per_s": (red["g_tot"] / 3) / (red["ms"] * 1e-3), "active_voxels": red["g_act"],
+               "field_kernel_ms": red["fld_ms"], "extract_kernel_ms": red["ext_ms"],
+               "extraction_hbm_frac": alg_ext / (red["ext_ms"] * 1e-3) / 1e9 / peak}
+        if red["e2e_ms"] is not None:
+            out["e2e"] = {"value": points / (red["e2e_ms"] * 1e-3), "unit": "voxels/s", "ms_per_step": red["e2e_ms"],
+                          "h2d_bytes_per_step": int(self.phi.numel() * 4 * self.env["world"]), "d2h_bytes_per_step": int((16 + 8) * self.env["world"])}
+        return out
+
+    def free(self):
+        torch = self.env["torch"]
+        for name in ("phi", "svl", "mesh", "hphi", "phi_scratch", "mm"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+
+def h2d_probe(env, nbytes=512 << 20, reps=4):
+    """Multi-rank runs: host-to-device bandwidth of one pinned buffer per rank, every rank copying at the same time and rank 0
+    alone -- names the limiter of the e2e leg (PCIe links shared behind a switch / host memory) by measurement."""
+    torch, dist, dev = env["torch"], env["dist"], env["dev"]
+    h = torch.empty(nbytes // 4, dtype=torch.float32, pin_memory=True)
+    h.zero_()
+    dbuf = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+
+    def gbs():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dbuf.copy_(h, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    dbuf.copy_(h)
+    env["barrier"]()
+    together = gbs()
+    env["barrier"]()
+    alone = gbs() if env["rank"] == 0 else 0.0
+    env["barrier"]()
+    t = torch.tensor([together, alone], device=dev, dtype=torch.float64)
+    allt = [torch.zeros_like(t) for _ in range(env["world"])]
+    dist.all_gather(allt, t)
+    rows = [[float(x) for x in a.cpu()] for a in allt]
+    return {"bytes": nbytes, "per_rank_gbs_all_ranks_copying": [round(r[0], 2) for r in rows], "rank0_gbs_alone": round(rows[0][1], 2),
+            "aggregate_gbs": round(sum(r[0] for r in rows), 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,8 +343,10 @@ def main():
     ap.add_argument("--ratio", type=int, default=4, help="fine/control upsampling ratio (2 = the app's own, 4 default, 8)")
     ap.add_argument("--harmonics", type=int, default=62)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile", action="store_true", help="timed steps only (no e2e leg, no CPU baseline): for runs under ncu")
+    ap.add_argument("--profile", action="store_true", help="timed steps only (no e2e leg, no extra legs, no CPU baseline): for runs under ncu")
+    ap.add_argument("--fast-field", action="store_true", help="headline leg in GCB_OPT_FAST_FIELD mode (default: exact, with the fast mode reported beside it)")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the global grid is fine^3 for every N (e.g. --fine 2048 --gpus 8 = BASELINE config 4)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (fast mode, ratio 2, configs 1/2/5, config 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -188,152 +370,114 @@ def main():
     import gpucadforam_b200 as g
     from gpucadforam_b200 import sharding, synth
 
-    F, R, NH = args.fine, args.ratio, args.harmonics
-    gnz = F if args.strong else F * world   # global point layers (weak scaling: one fine^3 block per rank)
-    z0, z1 = sharding.slab_bounds(gnz, world, rank)
-    nzl = z1 - z0 + 1
-    d = (1.0 / R,) * 3
-    cxy = F // R
-    czg = gnz // R
-    c0, c1 = sharding.control_slab(z0, z1, R, czg)
-    czl = c1 - c0 + 1
-    coef = synth.gyroid_coefficients()[:NH]
-    harm = synth.HARMONICS[:NH]
     dev = torch.device("cuda", local_rank)
-    phi = synth.phase_grids(cxy, cxy, czl, device=dev, z0=c0, cz_total=czg, harmonics=harm, periods=F / 40.0)
-    torch.cuda.synchronize()
-    ctx = g.Context(local_rank, options=0)
-    svl = torch.empty(F * F * nzl, device=dev)
-    mm = torch.zeros(2, device=dev)
-    voxel, center = d, (0.0, 0.0, 0.0)
-    ldims = (F, F, nzl)
-
-    def field_and_minmax():
-        g.svl_field(ctx, svl, phi, coef, (cxy, cxy, czl), ldims, d, slab=(z0, gnz), cz0=c0, d_minmax=mm)
-        return sharding.allreduce_minmax(dist, mm)   # one 2-float all-reduce (N > 1), then the values on the host
-
-    # set-up (untimed): count, then allocate the mesh exactly (count-then-allocate, SURVEY.md 7 "Capacity")
-    a, b = field_and_minmax()
-    act, tot = g.extract_band_raw(ctx, svl, a, b, ISO_MASK, BAND_LO, BAND_HI, ldims, voxel, center, None, None, 0, slab=(z0, gnz), count_only=True)
-    cap = tot + 3
-    mesh = g.MeshBuffers(cap, device=dev)
-
-    def step():
-        a, b = field_and_minmax()
-        return g.extract_band_raw(ctx, svl, a, b, ISO_MASK, BAND_LO, BAND_HI, ldims, voxel, center, mesh.pos, mesh.norm, cap, slab=(z0, gnz))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        res = step()
-    assert res == (act, tot), "count pass and mesh pass disagree"
-    ctx.enable_kernel_timing(True)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ctx.reset_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ext_ms, fld_ms = [], []
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-        ext_ms.append(ctx.last_extract_kernel_ms())   # events already complete: the step ends with the counts on the host
-        fld_ms.append(ctx.last_field_kernel_ms())
-    ev1.record()
-    barrier()
-    launches = ctx.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1) / args.steps
-    ctx.enable_kernel_timing(False)
+    env = {"torch": torch, "g": g, "sharding": sharding, "synth": synth, "dist": dist, "dev": dev, "rank": rank, "world": world, "barrier": barrier,
+           "ctx": g.Context(local_rank, options=0)}
+    ctx = env["ctx"]
+    F, R, NH = args.fine, args.ratio, args.harmonics
+    gnz = F if args.strong else F * world   # global point layers (weak scaling: one fine^3 block per rank)
+    peak, peak_src = peaks()
 
+    # ---- headline leg: BASELINE config 3, exact field (bit-identical to the reference kernels) unless --fast-field
+    leg = SvlLeg(env, F, R, NH, gnz, fast=args.fast_field)
+    raw = leg.run(args.steps, args.warmup, e2e=not args.profile, sampler=ClockSampler(local_rank) if rank == 0 else None)
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms, "extract_kernel_ms": sum(ext_ms) / len(ext_ms),
-                              "field_kernel_ms": sum(fld_ms) / len(fld_ms), "verts": tot, "launches": launches}))
+            print(json.dumps({"profile_run": True, "ms_per_step": raw["ms"], "extract_kernel_ms": raw["ext_ms"], "field_kernel_ms": raw["fld_ms"],
+                              "verts": leg.tot, "launches": raw["launches"], "field_mode": "fast" if args.fast_field else "exact"}))
         return
-    # ---- e2e: host control grids -> C-ABI host entry point (single GPU) / per-rank H2D + same step (multi GPU)
-    hphi = torch.empty(phi.shape, dtype=torch.float32, pin_memory=True)
-    hphi.copy_(phi)
-    phi_scratch = torch.empty_like(phi)
+    red = leg.reduce(raw)
+    clocks = raw["clocks"]
+    nzl, tot, phi_elems = leg.nzl, leg.tot, leg.phi.numel()
+    probe = h2d_probe(env) if world > 1 else None
+    leg.free()
 
-    def e2e_step():
-        if world == 1:
-            a_, t_, _ = g.svl_lattice_host(ctx, hphi, phi_scratch, svl, coef, (cxy, cxy, czl), ldims, d, ISO_MASK, BAND_LO, BAND_HI, voxel, center, mesh.pos,
-                                           mesh.norm, cap)
-            return a_, t_
-        g.svl_field_host(ctx, svl, hphi, phi_scratch, coef, (cxy, cxy, czl), ldims, d, slab=(z0, gnz), cz0=c0, d_minmax=mm)
-        a_, b_ = sharding.allreduce_minmax(dist, mm)
-        return g.extract_band_raw(ctx, svl, a_, b_, ISO_MASK, BAND_LO, BAND_HI, ldims, voxel, center, mesh.pos, mesh.norm, cap,
-                                  slab=(z0, gnz))
-
-    for _ in range(2):
-        r2 = e2e_step()
-    assert r2 == (act, tot)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
-
-    # max over ranks, global counts and offsets
-    stats = torch.tensor([ms, e2e_ms, sum(ext_ms) / len(ext_ms), sum(fld_ms) / len(fld_ms)], device=dev, dtype=torch.float64)
-    per_rank, voff, aoff, (g_act, g_tot) = sharding.gather_counts(dist, act, tot, device=dev)   # global vertex offsets = exclusive scan
-    g_launch = launches
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(lt)
-        g_launch = int(lt[0])
-    ms, e2e_ms, ext_k_ms, fld_k_ms = [float(x) for x in stats.cpu()]
+    extra = {}
+    if not args.no_extra:
+        # ---- fast field mode on the same workload (GCB_OPT_FAST_FIELD; tolerance stated in include/gpucad_b200.h)
+        if not args.fast_field:
+            fl = SvlLeg(env, F, R, NH, gnz, fast=True)
+            extra["fast_field"] = fl.summary(fl.reduce(fl.run(args.steps, args.warmup, e2e=True)), peak)
+            extra["fast_field"]["note"] = ("GCB_OPT_FAST_FIELD: |c_h| cos(phi_h + arg c_h) with MUFU.COS + packed-fp32 lerps; field within sum|c_h| (ulp(phi)/2 + 4e-6) "
+                                           "of the exact field, extraction bit-exact on that field (tests/test_gpu_parity.py::test_svl_field_fast_mode)")
+            fl.free()
+        ctx.set_options(0)
+        if world == 1 and (F, R) == (512, 4):
+            # ---- the reference app's own upsampling ratio 2 (control 256^3, 4.2 GB of control grids)
+            r2 = SvlLeg(env, F, 2, NH, gnz)
+            extra["ratio2"] = r2.summary(r2.reduce(r2.run(3, 3, e2e=True)), peak)
+            r2.free()
+            # ---- BASELINE configs 1, 2, 5 at full size through the legacy call sequences (and the fused entry points)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import config_bench
+            extra["configs"] = config_bench.run_ours(g, ctx, args.steps, args.warmup)
+            extra["configs"]["note"] = "this library only; the reference kernels' times for the same configs are in the --impl reference line"
+        if not args.strong and F == 512:
+            # ---- BASELINE config 4: 2048-wide grid, z-slab sharded.  The 2048^3 mesh alone is ~354 GB (3.7 G triangles x 96 B), so the
+            # full grid runs at N >= 4 (<= 106 GB per rank); N = 1 / 2 run the tallest 2048-wide stack of 513 point layers per rank
+            g4 = min(2048, 512 * world + 1)
+            try:
+                c4 = SvlLeg(env, 2048, 4, NH, g4)
+                s4 = c4.summary(c4.reduce(c4.run(2, 3, e2e=(world >= 4))), peak)
+                s4["complete_2048_cubed"] = bool(g4 == 2048)
+                s4["scaling"] = "strong"
+                s4["note"] = "BASELINE config 4 (2048^3 SVL lattice, z-slabs)" if g4 == 2048 else \
+                    "2048x2048x%d stack (%d point layers per rank): the full 2048^3 mesh (~354 GB) needs the HBM of >= 4 GPUs" % (g4, (g4 - 1) // world + 1)
+                extra["config4"] = s4
+                c4.free()
+            except Exception as e:  # noqa: BLE001  (an allocation failure here must not lose the headline line)
+                extra["config4"] = {"error": str(e)[:200]}
 
     if rank == 0:
         points = F * F * gnz
-        peak, peak_src = peaks()
-        alg_bytes = 4.0 * F * F * nzl + 32.0 * tot          # this rank's launch: 4 B/point read + 32 B/vertex written
-        achieved = alg_bytes / (ext_k_ms * 1e-3) / 1e9
+        ms, e2e_ms, ext_k_ms, fld_k_ms = red["ms"], red["e2e_ms"], red["ext_ms"], red["fld_ms"]
+        alg_ext = 4.0 * F * F * nzl + 32.0 * tot          # this rank's launch: 4 B/point read + 32 B/vertex written
+        alg_fld = 4.0 * F * F * nzl + 4.0 * phi_elems       # 4 B/point written + the control grids read once
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         sincos = float(F) * F * nzl * NH
+        ext_roof = {"bound": "hbm", "kernel": "mc_fused_kernel<M_BAND_RAW, TMA>", "achieved": alg_ext / (ext_k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": alg_ext / (ext_k_ms * 1e-3) / 1e9 / peak,
+                    "traffic": NCU_TRAFFIC_BYTES if (F, R, NH, world) == (512, 4, 62, 1) else None,
+                    "traffic_source": "profiles/r01_ncu_mc_fused.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch, this workload)",
+                    "kernel_ms": ext_k_ms, "share_of_step": ext_k_ms / ms, "algorithmic_bytes": alg_ext, "peak_source": peak_src}
+        # the field kernel has (almost) nothing to read: against the HBM roofline it is nowhere by construction; what bounds it is
+        # instruction issue / the FP32 pipes, reported as issue slots per (point, harmonic) next to the HBM figure the contract asks for
+        fld_name = "svl_field_fast_kernel" if args.fast_field else "svl_field_tile_kernel"
+        fld_roof = {"bound": "hbm", "kernel": fld_name, "achieved": alg_fld / (fld_k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": alg_fld / (fld_k_ms * 1e-3) / 1e9 / peak, "traffic": NCU_FIELD_TRAFFIC_BYTES if (F, R, NH, world) == (512, 4, 62, 1) else None,
+                    "traffic_source": "profiles/r01_ncu_svl_field.txt", "kernel_ms": fld_k_ms, "share_of_step": fld_k_ms / ms, "algorithmic_bytes": alg_fld,
+                    "peak_source": peak_src,
+                    "actual_limiter": {"bound": "instruction issue (FP32 FMA / FP64 / XU pipes; nothing to stream)",
+                                       "point_harmonics_per_s": sincos / (fld_k_ms * 1e-3),
+                                       "issue_slots_per_point_harmonic": 148 * 4 * 32 * sm_mhz * 1e6 * (fld_k_ms * 1e-3) / sincos,
+                                       "ncu": "profiles/r02_ncu_svl_field*.txt (issue-slot and pipe utilisation of this kernel)"}}
+        dominant, other = (fld_roof, ext_roof) if fld_k_ms >= ext_k_ms else (ext_roof, fld_roof)
         out = {
             "metric": "voxels/s (field + marching cubes, device-timed)", "value": points / (ms * 1e-3), "unit": "voxels/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config 3: spatially varying gyroid lattice, %d harmonics, control grid %dx%dx%d -> fine %dx%dx%d, band [0.20,0.30]"
-                                   % (NH, cxy, cxy, czg, F, F, gnz),
-                       "fine": [F, F, gnz], "control": [cxy, cxy, czg], "ratio": R, "parallelism": "z-slabs x%d" % world,
-                       "l2_policy": "inputs larger than L2: %.2f GB field + %.2f GB control grids + %.2f GB mesh per rank"
-                                    % (4e-9 * F * F * nzl, 4e-9 * phi.numel(), 32e-9 * tot)},
-            "triangles_per_s": (g_tot / 3) / (ms * 1e-3), "triangles": g_tot // 3, "active_voxels": g_act,
+            "config": workload_config(F, R, NH, gnz, world, args.strong),
+            "field_mode": "fast (GCB_OPT_FAST_FIELD)" if args.fast_field else "exact (field bit-identical to the reference kernels)",
+            "triangles_per_s": (red["g_tot"] / 3) / (ms * 1e-3), "triangles": red["g_tot"] // 3, "active_voxels": red["g_act"],
+            "per_rank_vertices": red["per_rank_verts"],
             "e2e": {"value": points / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(phi.numel() * 4 * world), "d2h_bytes_per_step": int((16 + 8) * world),
+                    "h2d_bytes_per_step": int(phi_elems * 4 * world), "d2h_bytes_per_step": int((16 + 8) * world),
                     "note": "control grids copied from pinned host memory each step; counts and min/max read back; the mesh stays in device memory "
                             "as in the reference (Vulkan-exported vertex buffers)",
                     "host_cpus_bound_rank0": affinity},
-            "gpu_launches": g_launch,
-            "roofline": {"bound": "hbm", "kernel": "mc_fused_kernel<M_BAND_RAW, TMA>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES if (F, R, NH, world) == (512, 4, 62, 1) else None,
-                         "traffic_source": "profiles/r01_ncu_mc_fused.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch, this workload)",
-                         "kernel_ms": ext_k_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
-            # the field kernel moves 4 B/point and is bound by instruction issue (exact texture model in fp64 + libdevice-identical
-            # sincosf): reported as issue slots per (point, harmonic), not against the HBM roofline
-            "field_kernel": {"kernel": "svl_field_tile_kernel", "bound": "instruction issue (fp64 lerps + sincosf polynomial)", "kernel_ms": fld_k_ms,
-                             "share_of_step": fld_k_ms / ms,
-                             "sincos_pairs_per_s": sincos / (fld_k_ms * 1e-3),
-                             "issue_slots_per_point_harmonic": 148 * 4 * 32 * sm_mhz * 1e6 * (fld_k_ms * 1e-3) / sincos,
-                             # against the HBM roofline it is nowhere: it writes 4 B/point and reads the control grids once
-                             "hbm": {"algorithmic_bytes": 4.0 * F * F * nzl + 4.0 * phi.numel(),
-                                     "achieved_gbs": (4.0 * F * F * nzl + 4.0 * phi.numel()) / (fld_k_ms * 1e-3) / 1e9,
-                                     "frac": (4.0 * F * F * nzl + 4.0 * phi.numel()) / (fld_k_ms * 1e-3) / 1e9 / peak},
-                             "ncu": "profiles/r01_ncu_svl_field.txt: issue slots 66 % busy, FMA / ALU / FP64 / XU pipes 26-27 % each"},
+            "gpu_launches": red["launches"],
+            "roofline": dominant, "roofline_other_kernel": other,
             "clocks": clocks,
         }
+        if probe:
+            out["e2e"]["h2d_probe"] = probe
+        out.update(extra)
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(NH)
         print(json.dumps(out))
@@ -343,6 +487,8 @@ def main():
 
 # measured once with `ncu --set full` on the default workload (profiles/r01_ncu_mc_fused.txt): 0.540 GB read + 5.468 GB written
 NCU_TRAFFIC_BYTES = 539927808 + 5467993000
+# profiles/r01_ncu_svl_field.txt: 0.52 GB read (control grids once) + 0.50 GB written (the field)
+NCU_FIELD_TRAFFIC_BYTES = 521009664 + 500735744
 
 
 def cpu_baseline(nh, budget_s=12.0):
@@ -371,17 +517,20 @@ def cpu_baseline(nh, budget_s=12.0):
 
 
 def reference_arm(args, torch, rank, world, local_rank):
-    """The reference's own implementation of the path.  Rank 0 only."""
+    """The reference's own implementation of the path: its unmodified CUDA kernels (oracle/_ref) on one GPU.  Rank 0 only; at
+    N > 1 it times ONE fine^3 block -- one rank's share of the weak-scaling workload -- and reports that block's voxels/s."""
     if rank != 0:
         return
     import ref_py as ref
     F, R, NH = args.fine, args.ratio, args.harmonics
-    base = {"impl": "reference", "metric": "voxels/s (field + marching cubes, device-timed)", "unit": "voxels/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    gnz = F if args.strong else F * world
+    base = {"impl": "reference", "metric": "voxels/s (field + marching cubes, device-timed)", "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(F, R, NH, gnz, world, args.strong)}
     if not (ref.available() and torch.cuda.is_available()):
         cb = cpu_baseline(NH)
+        cb["sample"] = "bounded CPU sample of the workload (no GPU / reference library here): " + cb["sample"]
         base.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
-                    config={"workload": "config 3 (bounded CPU sample): " + cb["sample"]},
                     e2e={"value": cb["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
         print(json.dumps(base))
         return
@@ -435,13 +584,20 @@ def reference_arm(args, torch, rank, world, local_rank):
     val = F ** 3 / (ms * 1e-3)
     launches_per_step = NH * 4 + 3 + 7  # 62 x (copytotexture, memcpy3D, grating, svl) + normalise (3) + classify, 2 scans(x2 kernels), compact, generate
     base.update(value=val, ms_per_step=ms, triangles_per_s=tot / 3 / (ms * 1e-3), triangles=tot // 3, active_voxels=act, clocks=clocks,
-                config={"workload": "config 3: spatially varying gyroid lattice, %d harmonics, control grid %d^3 -> fine %d^3, band [0.20,0.30]"
-                                    % (NH, c, F), "fine": [F, F, F], "control": [c, c, c], "ratio": R,
-                        "note": "reference CUDA kernels (unmodified sources, sm_100a) via oracle/_ref; classify launched with a corrected 2-D grid: %s"
-                                % bool(fix)},
+                reference_note="reference CUDA kernels (unmodified sources, sm_100a) via oracle/_ref, device-resident inputs; classify launched with a "
+                               "corrected 2-D grid: %s" % bool(fix),
                 cpu_baseline={"value": val, "unit": "voxels/s", "cores": 0, "kind": "reference",
-                              "sample": "full workload on 1 B200 with the reference's own CUDA kernels (the reference has no CPU implementation)"},
+                              "sample": "one %d^3 block (%s) on 1 B200 with the reference's own CUDA kernels -- the reference has no CPU implementation"
+                                        % (F, "the whole workload" if gnz == F else "1/%d of the workload: one rank's share" % world)},
                 e2e={"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=launches_per_step * args.steps)
+    if not args.no_extra and world == 1 and (F, R) == (512, 4):
+        # the reference kernels on BASELINE configs 1, 2, 5 (the product arm reports its own times for the same configs)
+        del svl, ga, mask, k, zeros, scr, mesh, phi
+        ref.delete_texture()
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import config_bench
+        base["configs"] = config_bench.run_reference(g, ref, args.steps, max(args.warmup, 3))
     print(json.dumps(base))
 
 

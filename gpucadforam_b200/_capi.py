@@ -104,6 +104,7 @@ GCB_OPT_LEGACY_MEMSET = 2
 GCB_OPT_NO_TMA = 4
 GCB_OPT_OBJ_HOST = 8
 GCB_OPT_ASYNC_FIELDS = 16
+GCB_OPT_FAST_FIELD = 32
 
 
 def load(path=LIB_PATH):

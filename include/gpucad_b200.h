@@ -57,6 +57,12 @@ enum {
                                       activeVoxels == 0 (consumers honour totalVerts either way) */
     GCB_OPT_NO_TMA = 4,            /* force the LDG stage-in path (debug / A-B measurement) */
     GCB_OPT_OBJ_HOST = 8,          /* gcb_file_write_obj: weld and format on one host thread (as the reference does) instead of on the GPU */
+    GCB_OPT_FAST_FIELD = 32,       /* gcb_svl_field / gcb_svl_lattice*: evaluate the SVL sum as |c_h| cos(phi_h + arg c_h) with the hardware
+                                      cosine and packed-fp32 trilinear blends instead of the bit-exact texture model + libdevice sincosf.
+                                      The field then agrees with the default mode to ~1e-6 of its range (bound: sum_h |c_h| (ulp(phi_h)/2 +
+                                      4e-6), the first term being the rounding the reference itself applies to the interpolated phase); the
+                                      extraction is unchanged, i.e. bit-exact on that field.  Power-of-two upsampling ratios only (others
+                                      fall back to the exact kernels); valid for |phi| < 2^24.  Off by default */
     GCB_OPT_ASYNC_FIELDS = 16      /* legacy calls without host results (primitives, create_lattice, normalise, refine, grating, svl, copy_parameter,
                                       texture upload ...) only enqueue on the context's stream instead of ending in a device synchronise as the
                                       reference wrappers do (MarchingCubes_kernel.cu:458, :1074); calls that report counts still synchronise.  Off by

@@ -1359,3 +1359,127 @@ def test_lattice_variant_second_band_ids_two_zero(ctx, n):
         a2, t2 = ref.isosurface_lattice(False, False, mask, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, vox, cen, scr2, mv, k1, k2, cases.BAND_LO,
                                         cases.BAND_HI, 0.45, 0.55)
         compare_extractions(mine, mine_result(scr2, mesh2, dims, a2, t2), "lattice ids {2,0} vs reference", exact_mesh=True)
+
+
+# ------------------------------------------------------------------ fast field mode (GCB_OPT_FAST_FIELD)
+@pytest.fixture(scope="module")
+def fctx():
+    c = g.Context(0, options=_capi.GCB_OPT_FILL_STAGE_ARRAYS | _capi.GCB_OPT_LEGACY_MEMSET | _capi.GCB_OPT_FAST_FIELD)
+    yield c
+    c.close()
+
+
+def _fast_case(name):
+    from gpucadforam_b200 import synth
+    if name == "bench_like":   # the bench workload in miniature: 62 harmonics, ratio 4, |phi| up to ~60 rad
+        F, R = 128, 4
+        c = F // R
+        return dict(cdims=(c, c, c), fdims=(F, F, F), d=(0.25,) * 3), synth.phase_grids(c, c, c, periods=F / 40.0).numpy(), synth.gyroid_coefficients()
+    if name == "large_phase":  # |phi| ~ 230 rad as at 512^3: the reference's own rounding of phi (ulp 1.5e-5) dominates the difference
+        cfg = dict(cdims=(16, 16, 16), fdims=(64, 64, 64), d=(0.25,) * 3)
+        nh = 8
+        phi = synth.phase_grids(16, 16, 16, periods=2.0, harmonics=synth.HARMONICS[:nh]).numpy()
+        phi = (phi + np.float32(231.7) * np.array([1, -1, 1, 1, -1, 1, -1, 1], np.float32)[:, None, None, None]).astype(np.float32)
+        coef = [(c[0] + 0.1, c[1] - 0.05) for c in synth.gyroid_coefficients()[:nh]]
+        return cfg, phi, coef
+    cfg = getattr(cases, name)
+    phi, coef = cases.svl_inputs(cfg)
+    return cfg, phi, coef
+
+
+@pytest.mark.parametrize("name", ["SVL", "SVL4", "bench_like", "large_phase"])
+def test_svl_field_fast_mode(ctx, fctx, name):
+    """GCB_OPT_FAST_FIELD: |c| cos(phi + arg c) with MUFU.COS and packed-fp32 lerps.  Floating-point row: the field is within
+    sum_h |c_h| (ulp(phi_h)/2 + 4e-6) of the exact (reference-identical) field -- tolerance stated in gpucad_b200.h -- and within
+    1.5e-6 sum |c_h| of the numpy restatement of the same algorithm (tests/fast_field_model.py; the rest is MUFU.COS vs cos).
+    Everything downstream is exact: min/max as the reference reduction defines them, and the mesh extracted from THAT field is
+    bit-identical to the reference kernels / equal to the oracle (north_star: topology bit-exact given the same fp32 field)."""
+    from fast_field_model import bound, fast_field
+    cfg, phi, coef = _fast_case(name)
+    fx, fy, fz = cfg["fdims"]
+    dims = cfg["fdims"]
+    ratio = int(round(1.0 / cfg["d"][0]))
+    dphi = dev(phi)
+    exact, fast, mm = torch.zeros(fx * fy * fz, device="cuda"), torch.zeros(fx * fy * fz, device="cuda"), torch.zeros(2, device="cuda")
+    g.svl_field(ctx, exact, dphi, coef, cfg["cdims"], dims, cfg["d"])
+    g.svl_field(fctx, fast, dphi, coef, cfg["cdims"], dims, cfg["d"], d_minmax=mm)
+    err = float((fast.double() - exact.double()).abs().max())
+    b = bound(phi, coef)
+    sumc = float(sum(np.hypot(c[0], c[1]) for c in coef))
+    print("fast field %s: max |fast - exact| = %.3g (bound %.3g, range [%.3f, %.3f])" % (name, err, b, float(exact.min()), float(exact.max())))
+    assert err > 0.0, "fast mode did not run (fields identical)"
+    assert err <= b
+    model = fast_field(phi, coef, dims, ratio).reshape(-1)
+    merr = float(np.abs(fast.cpu().numpy().astype(np.float64) - model).max())
+    print("fast field %s: max |gpu - numpy model| = %.3g" % (name, merr))
+    assert merr <= 1.5e-6 * sumc + 1e-7
+    lo, hi = orc.minmax(fast.cpu().numpy())
+    assert (float(mm[0]), float(mm[1])) == (lo, hi)
+    # extraction on the fast field
+    mv = max_verts_for(dims)
+    mesh = g.MeshBuffers(mv)
+    comp = torch.zeros((fx - 1) * (fy - 1) * (fz - 1), dtype=torch.int32, device="cuda")
+    a1, t1 = g.extract_band_raw(fctx, fast, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, cfg["d"], (0, 0, 0), mesh.pos, mesh.norm, mv, comp=comp)
+    assert t1 > 0
+    if fx * fy * fz <= 64 ** 3:
+        mask, k = orc.normalise_four(fast.cpu().numpy().reshape(fz, fy, fx), cases.BAND_LO, cases.BAND_HI)
+        o = orc.extract(orc.MODE_LATTICE_ONE, dims, cfg["d"], (0, 0, 0), cases.ISO_MASK, f0=mask, f1=k, iso1=cases.BAND_LO, iso2=cases.BAND_HI, max_verts=mv)
+        assert (a1, t1) == (o["active"], o["total"])
+        assert np.array_equal(comp[:a1].cpu().numpy().astype(np.uint32), o["compVoxelArray"])
+        scale = max(1.0, float(np.abs(o["pos"][:t1, :3]).max()))
+        assert np.allclose(mesh.pos[:t1].cpu().numpy(), o["pos"][:t1], rtol=0, atol=1e-5 * scale)
+    if HAVE_REF:
+        mask2, k2 = torch.zeros_like(fast), torch.zeros_like(fast)
+        ref.normalise_four(fast, mask2, k2, dims, cases.BAND_LO, cases.BAND_HI)
+        scr2, mesh2 = g.Scratch((fx - 1) * (fy - 1) * (fz - 1)), g.MeshBuffers(mv)
+        a2, t2 = ref.isosurface_lattice(True, False, mask2, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, cfg["d"], (0, 0, 0), scr2, mv, k2, None, cases.BAND_LO,
+                                        cases.BAND_HI)
+        assert (a1, t1) == (a2, t2)
+        assert torch.equal(comp[:a1], scr2.compVoxelArray[:a1])
+        assert_bits_equal(mesh.pos[:t1], mesh2.pos[:t1], "fast field, extraction vs reference kernels: pos")
+        assert_bits_equal(mesh.norm[:t1], mesh2.norm[:t1], "fast field, extraction vs reference kernels: norm")
+    # the mesh of the fast field is the mesh of the exact field up to cells whose corner values sit within the tolerance of a band level
+    mesh_e = g.MeshBuffers(mv)
+    loe, hie = orc.minmax(exact.cpu().numpy())
+    ae, te = g.extract_band_raw(ctx, exact, loe, hie, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, cfg["d"], (0, 0, 0), mesh_e.pos, mesh_e.norm, mv)
+    print("fast field %s: triangles %d (exact field %d)" % (name, t1 // 3, te // 3))
+    assert abs(t1 - te) <= max(30, 2e-3 * te)
+
+
+def test_svl_field_fast_mode_slabs_and_host_path_equal_single_pass(fctx):
+    """The per-cell phase reduction makes the fast field a function of the global grid only: z-slabs starting on even and odd
+    global layers, and the slab-pipelined host-input entry point, reproduce the single-pass field bit for bit."""
+    cfg = cases.SVL4
+    phi, coef = cases.svl_inputs(cfg)
+    fx, fy, fz = cfg["fdims"]
+    dphi = dev(phi)
+    whole = torch.zeros(fx * fy * fz, device="cuda")
+    g.svl_field(fctx, whole, dphi, coef, cfg["cdims"], cfg["fdims"], cfg["d"])
+    w3 = whole.view(fz, fy, fx)
+    R = 4
+    for (z0, z1) in ((0, 8), (8, 14), (14, 21), (21, 31)):   # cell layers; starts: 0, 8 (0 mod 4), 14 (2 mod 4), 21 (odd)
+        nzl = z1 - z0 + 1
+        c0 = z0 // R
+        c1 = min((z1 // R) + 1, cfg["cdims"][2] - 1)
+        sub = dphi[:, c0:c1 + 1].contiguous()
+        out = torch.zeros(fx * fy * nzl, device="cuda")
+        g.svl_field(fctx, out, sub, coef, (cfg["cdims"][0], cfg["cdims"][1], c1 - c0 + 1), (fx, fy, nzl), cfg["d"], slab=(z0, fz), cz0=c0)
+        assert_bits_equal(out, w3[z0:z1 + 1].contiguous().view(-1), "fast svl slab z0=%d" % z0)
+    hphi = torch.from_numpy(phi).pin_memory()
+    f2, mmd, scratch_phi = torch.zeros_like(whole), torch.zeros(2, device="cuda"), torch.zeros_like(dphi)
+    g.svl_field_host(fctx, f2, hphi, scratch_phi, coef, cfg["cdims"], cfg["fdims"], cfg["d"], d_minmax=mmd)
+    assert_bits_equal(f2, whole, "fast svl_field_host")
+    assert (float(mmd[0]), float(mmd[1])) == orc.minmax(whole.cpu().numpy())
+
+
+def test_fast_field_option_leaves_other_ratios_on_the_exact_kernels(ctx, fctx):
+    """Non power-of-two upsampling ratios have no fast kernel: the option is ignored there and the field stays bit-identical."""
+    from gpucadforam_b200 import synth
+    cdims, fdims, d = (8, 8, 8), (24, 24, 24), (1.0 / 3.0,) * 3
+    nh = 5
+    phi = synth.phase_grids(8, 8, 8, periods=3.0, harmonics=synth.HARMONICS[:nh]).numpy()
+    coef = [(c[0] + 0.1, c[1] - 0.05) for c in synth.gyroid_coefficients()[:nh]]
+    a, b = torch.zeros(24 ** 3, device="cuda"), torch.zeros(24 ** 3, device="cuda")
+    g.svl_field(ctx, a, dev(phi), coef, cdims, fdims, d)
+    g.svl_field(fctx, b, dev(phi), coef, cdims, fdims, d)
+    assert_bits_equal(a, b, "ratio 3: fast option ignored")

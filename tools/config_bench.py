@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
-"""BASELINE configs 1, 2 and 5 at full size on one B200: this library (legacy-signature C ABI) next to the reference's own
-CUDA kernels (oracle/_ref), same inputs, CUDA-event timing, and a full-size parity check of the results (counts and whole
-vertex / normal buffers bit for bit).  Config 3 is bench.py's default line, config 4 its --gpus 8 --strong line.
+"""BASELINE configs 1, 2 and 5 at full size on one B200.  Two arms, kept apart so that bench.py's product arm never loads the
+reference library: `ours_*` drive this library through the legacy-signature C ABI (the reference's own call sequences) and,
+where one exists, through the fused entry point; `ref_*` drive the reference's own CUDA kernels (oracle/_ref) on the same inputs.
+bench.py imports both (`ours` in the default arm, `ref` under --impl reference); run as a script it does both on one GPU, adds
+the full-size parity check (counts and whole vertex / normal buffers bit for bit) and prints one JSON line per config.
 
     python tools/config_bench.py [--steps 5] [--warmup 3] > profiles/rNN_configs.json
 """
@@ -15,16 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-import gpucadforam_b200 as g  # noqa: E402
-from gpucadforam_b200 import synth  # noqa: E402
-import ref_py as ref  # noqa: E402
-
 ISO_MASK, BAND_LO, BAND_HI = 0.25, 0.20, 0.30
-PEAK_GBS = 6456.2
-LEGACY_CALLS = "blocking (as the reference wrappers)"
+
+C1 = dict(n=128, workload="config 1: gyroid TPMS unit lattice 128^3, band [0.20,0.30] (create_lattice, 2 normalises, latticeone)")
+C2 = dict(n=256, d=(0.5, 0.5, 0.5), workload="config 2: CSG sphere U box - cylinder on a 256^3 fine grid (3 primitives, 2 retains, computeIsosurface obj_diff)",
+          sph=dict(center=(0.0, 0.0, 0.0), radius=40.0, thickness=2.0),
+          cub=dict(center=(1.0, 0.5, -0.5), angles=(0.3, 0.2, 0.1), xw=90.0, yw=50.0, zw=60.0),
+          cyl=dict(center=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), radius=18.0, tr=2.0, ta=200.0))
+C5 = dict(cdims=(384, 192, 192), fdims=(768, 384, 384), d=(0.5, 0.5, 0.5), iso=0.4,
+          workload="config 5: cantilever density 768x384x384 (coarse 384x192x192, 40 struts, sigma 1.5): refine + computeIsosurface_2, iso 0.4")
 
 
 def timed(fn, steps, warmup):
@@ -48,33 +51,44 @@ def same(a, b, nbytes):
     return bool(torch.equal(a.view(torch.uint8).reshape(-1)[:nbytes], b.view(torch.uint8).reshape(-1)[:nbytes]))
 
 
-def line(cfg, desc, points, ms_ours, ms_ref, act, tot, parity, alg_bytes, extra=None):
-    out = {"config": cfg, "workload": desc, "points": points, "active_voxels": act, "triangles": tot // 3,
-           "ours": {"ms": ms_ours, "voxels_per_s": points / (ms_ours * 1e-3), "triangles_per_s": tot / 3 / (ms_ours * 1e-3)},
-           "reference_kernels": {"ms": ms_ref, "voxels_per_s": points / (ms_ref * 1e-3)},
-           "speedup_vs_reference_kernels": ms_ref / ms_ours, "parity_full_size": parity,
-           "algorithmic_bytes": alg_bytes, "hbm_roofline_frac_whole_step": alg_bytes / (ms_ours * 1e-3) / 1e9 / PEAK_GBS}
-    out["legacy_calls"] = LEGACY_CALLS
-    if extra:
-        out.update(extra)
-    print(json.dumps(out), flush=True)
+def _res(ms, points, act, tot, **extra):
+    out = {"ms": ms, "voxels_per_s": points / (ms * 1e-3), "triangles_per_s": tot / 3 / (ms * 1e-3), "triangles": tot // 3, "active_voxels": act}
+    out.update(extra)
+    return out
 
 
-def config1(ctx, args):
-    """Gyroid TPMS unit lattice 128^3: create_lattice -> normalise_buffer -> normalise_four -> latticeone (main.cu:4080-4137)."""
-    n = 128
+# ------------------------------------------------------------------ config 1
+def ours_config1(g, ctx, steps, warmup, keep=None):
+    """main.cu:4080-4137: create_lattice -> GPU_buffer_normalise_buffer -> GPU_buffer_normalise_four -> computeIsosurface_latticeone."""
+    n = C1["n"]
     dims, npts, ncell = (n, n, n), n ** 3, (n - 1) ** 3
     mv = max(4 * npts, 300000)
     lat, iso = g.Gratings(ctx), g.Isosurface(ctx)
     f, mask, k = (torch.zeros(npts, device="cuda") for _ in range(3))
     scr, mesh = g.Scratch(ncell), g.MeshBuffers(mv)
 
-    def ours():
+    def legacy():
         g.Fft_lattice(ctx).create_lattice(f, n, n, n, npts, 0)
         lat.GPU_buffer_normalise_buffer(f, f, npts)
         lat.GPU_buffer_normalise_four(f, mask, k, npts, n, n, n, BAND_LO, BAND_HI)
         return iso.computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, ISO_MASK, scr, dims, (1, 1, 1), (0, 0, 0), mv, k, BAND_LO, BAND_HI)
 
+    ms, (act, tot) = timed(legacy, steps, warmup)
+    out = {"workload": C1["workload"], "points": npts, "legacy_calls": _res(ms, npts, act, tot, calls=4)}
+    if hasattr(g, "tpms_lattice"):
+        mesh_f = g.MeshBuffers(mv)
+        ms_f, (a2, t2) = timed(lambda: g.tpms_lattice(ctx, f, 0, dims, ISO_MASK, BAND_LO, BAND_HI, (1, 1, 1), (0, 0, 0), mesh_f.pos, mesh_f.norm, mv)[:2], steps, warmup)
+        out["fused_call"] = _res(ms_f, npts, a2, t2, calls=1, same_mesh_as_legacy=bool((a2, t2) == (act, tot) and same(mesh.pos, mesh_f.pos, tot * 16)
+                                                                                     and same(mesh.norm, mesh_f.norm, tot * 16)))
+    if keep is not None:
+        keep.update(k=k, mesh=mesh, counts=(act, tot))
+    return out
+
+
+def ref_config1(g, ref, steps, warmup, keep=None):
+    n = C1["n"]
+    dims, npts, ncell = (n, n, n), n ** 3, (n - 1) ** 3
+    mv = max(4 * npts, 300000)
     f2, mask2, k2 = (torch.zeros(npts, device="cuda") for _ in range(3))
     scr2, mesh2 = g.Scratch(ncell), g.MeshBuffers(mv)
 
@@ -84,103 +98,173 @@ def config1(ctx, args):
         ref.normalise_four(f2, mask2, k2, dims, BAND_LO, BAND_HI)
         return ref.isosurface_lattice(True, False, mask2, mesh2.pos, mesh2.norm, ISO_MASK, dims, (1, 1, 1), (0, 0, 0), scr2, mv, k2, None, BAND_LO, BAND_HI)
 
-    ms_o, (act, tot) = timed(ours, args.steps, args.warmup)
-    ms_r, (a2, t2) = timed(theirs, args.steps, args.warmup)
-    parity = {"counts": (act, tot) == (a2, t2), "field_bits": same(k, k2, npts * 4), "pos_bits": same(mesh.pos, mesh2.pos, tot * 16),
-              "norm_bits": same(mesh.norm, mesh2.norm, tot * 16)}
-    # stored-field formulation the reference imposes: field written once, read by two normalise passes, mask + k written and read
-    line(1, "gyroid TPMS unit lattice 128^3, band [0.20,0.30], legacy call sequence (5 calls)", npts, ms_o, ms_r, act, tot, parity,
-         4.0 * npts * 6 + 32.0 * tot)
+    ms, (act, tot) = timed(theirs, steps, warmup)
+    if keep is not None:
+        keep.update(k=k2, mesh=mesh2, counts=(act, tot))
+    return {"workload": C1["workload"], "points": npts, "reference_kernels": _res(ms, npts, act, tot)}
 
 
-def config2(ctx, args, tmpdir):
-    """CSG sphere U box - cylinder on a 256^3 fine grid (dx2 = 0.5) + .obj export (main.cu:3304-3465, :4695-4778)."""
-    n = 256
-    dims, d, npts, ncell = (n, n, n), (0.5, 0.5, 0.5), n ** 3, (n - 1) ** 3
+# ------------------------------------------------------------------ config 2
+def ours_config2(g, ctx, steps, warmup, keep=None):
+    """main.cu:3304-3465: sphere -> retain(union); cuboid -> retain(union); cylinder with obj_diff -> mesh."""
+    n, d = C2["n"], C2["d"]
+    dims, npts, ncell = (n, n, n), n ** 3, (n - 1) ** 3
     mv = max(4 * npts, 300000)
     m, iso = g.Modelling(ctx), g.Isosurface(ctx)
-    sph = dict(center=(0.0, 0.0, 0.0), radius=40.0, thickness=2.0)
-    cub = dict(center=(1.0, 0.5, -0.5), angles=(0.3, 0.2, 0.1), xw=90.0, yw=50.0, zw=60.0)
-    cyl = dict(center=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), radius=18.0, tr=2.0, ta=200.0)
+    sph, cub, cyl = C2["sph"], C2["cub"], C2["cyl"]
     zeros = torch.zeros(npts, device="cuda")
+    v1, b1, s1, m1 = gp_zeros(npts), torch.zeros(npts, device="cuda"), g.Scratch(ncell), g.MeshBuffers(mv)
 
-    def run(use_ref, vol_one, boundary, scr, mesh):
-        vol_one.zero_()
-        if use_ref:
-            ref.sphere(boundary, sph["center"], sph["radius"], sph["thickness"], dims, d, False)
-            ref.copy_parameter(vol_one, boundary, zeros, dims, d, 0.0, obj_union=True)
-            ref.cuboid(boundary, cub["center"], cub["angles"], cub["xw"], cub["yw"], cub["zw"], dims, d)
-            ref.copy_parameter(vol_one, boundary, zeros, dims, d, 0.0, obj_union=True)
-            ref.distance_from_line(boundary, cyl["center"], cyl["axis"], cyl["radius"], cyl["tr"], cyl["ta"], dims, d, False)
-            return ref.isosurface_csg(False, mesh.pos, mesh.norm, 0.0, dims, d, (0, 0, 0), scr, mv, vol_one, boundary, zeros, obj_union=False, obj_diff=True)
-        m.sphere_with_center(boundary, sph["center"], sph["radius"], sph["thickness"], n, n, n, *d, False)
-        iso.copy_parameter(0.0, dims, d, vol_one, boundary, zeros, obj_union=True)
-        m.cuboid(boundary, cub["center"], cub["angles"], cub["xw"], cub["yw"], cub["zw"], n, n, n, *d)
-        iso.copy_parameter(0.0, dims, d, vol_one, boundary, zeros, obj_union=True)
-        m.distance_from_line(boundary, cyl["center"], cyl["axis"], cyl["radius"], cyl["tr"], cyl["ta"], n, n, n, *d, False)
-        act, tot, _ = iso.computeIsosurface(mesh.pos, mesh.norm, 0.0, scr, dims, d, (0, 0, 0), mv, vol_one, boundary, zeros, obj_union=False, obj_diff=True)
+    def legacy():
+        v1.zero_()
+        m.sphere_with_center(b1, sph["center"], sph["radius"], sph["thickness"], n, n, n, *d, False)
+        iso.copy_parameter(0.0, dims, d, v1, b1, zeros, obj_union=True)
+        m.cuboid(b1, cub["center"], cub["angles"], cub["xw"], cub["yw"], cub["zw"], n, n, n, *d)
+        iso.copy_parameter(0.0, dims, d, v1, b1, zeros, obj_union=True)
+        m.distance_from_line(b1, cyl["center"], cyl["axis"], cyl["radius"], cyl["tr"], cyl["ta"], n, n, n, *d, False)
+        act, tot, _ = iso.computeIsosurface(m1.pos, m1.norm, 0.0, s1, dims, d, (0, 0, 0), mv, v1, b1, zeros, obj_union=False, obj_diff=True)
         return act, tot
 
-    v1, b1, s1, m1 = gp_zeros(npts), torch.zeros(npts, device="cuda"), g.Scratch(ncell), g.MeshBuffers(mv)
+    ms, (act, tot) = timed(legacy, steps, warmup)
+    out = {"workload": C2["workload"], "points": npts, "legacy_calls": _res(ms, npts, act, tot, calls=6)}
+    if hasattr(g, "csg_retain_primitive"):
+        v3, b3, m3 = gp_zeros(npts), torch.zeros(npts, device="cuda"), g.MeshBuffers(mv)
+
+        def fused():
+            v3.zero_()
+            g.csg_retain_primitive(ctx, "sphere", v3, b3, dims, d, 0.0, center=sph["center"], radius=sph["radius"], thickness=sph["thickness"])
+            g.csg_retain_primitive(ctx, "cuboid", v3, b3, dims, d, 0.0, center=cub["center"], angles=cub["angles"], xw=cub["xw"], yw=cub["yw"], zw=cub["zw"])
+            m.distance_from_line(b3, cyl["center"], cyl["axis"], cyl["radius"], cyl["tr"], cyl["ta"], n, n, n, *d, False)
+            act, tot, _ = iso.computeIsosurface(m3.pos, m3.norm, 0.0, s1, dims, d, (0, 0, 0), mv, v3, b3, zeros, obj_union=False, obj_diff=True)
+            return act, tot
+        ms_f, (a2, t2) = timed(fused, steps, warmup)
+        out["fused_call"] = _res(ms_f, npts, a2, t2, calls=4, same_mesh_as_legacy=bool((a2, t2) == (act, tot) and torch.equal(v1, v3)
+                                                                                     and same(m1.pos, m3.pos, tot * 16) and same(m1.norm, m3.norm, tot * 16)))
+    if keep is not None:
+        keep.update(gp=v1, mesh=m1, counts=(act, tot))
+    return out
+
+
+def ref_config2(g, ref, steps, warmup, keep=None):
+    n, d = C2["n"], C2["d"]
+    dims, npts, ncell = (n, n, n), n ** 3, (n - 1) ** 3
+    mv = max(4 * npts, 300000)
+    sph, cub, cyl = C2["sph"], C2["cub"], C2["cyl"]
+    zeros = torch.zeros(npts, device="cuda")
     v2, b2, s2, m2 = gp_zeros(npts), torch.zeros(npts, device="cuda"), g.Scratch(ncell), g.MeshBuffers(mv)
-    ms_o, (act, tot) = timed(lambda: run(False, v1, b1, s1, m1), args.steps, args.warmup)
-    ms_r, (a2, t2) = timed(lambda: run(True, v2, b2, s2, m2), args.steps, args.warmup)
-    parity = {"counts": (act, tot) == (a2, t2), "grid_points_bits": same(v1, v2, npts * 16), "pos_bits": same(m1.pos, m2.pos, tot * 16),
-              "norm_bits": same(m1.norm, m2.norm, tot * 16)}
-    # .obj export: ours (hash weld) vs the reference writer (std::map weld), wall clock, same bytes
-    p1, p2 = os.path.join(tmpdir, "ours.obj"), os.path.join(tmpdir, "ref.obj")
-    t0 = time.time(); g.File_output(ctx).file_write_obj(m1.pos, tot, p1); t_obj_o = time.time() - t0
-    t0 = time.time(); ref.write_obj(m2.pos, t2, p2); t_obj_r = time.time() - t0
-    parity["obj_bytes"] = open(p1, "rb").read() == open(p2, "rb").read()
-    # 3 primitive fields written (4 B), 2 retains (grid_points 16 R + 16 W, field 4 R + 3 neighbours cached), extraction 24 B/pt
-    line(2, "CSG sphere U box - cylinder, 256^3 fine grid: 3 primitives, 2 retains, computeIsosurface (obj_diff)", npts, ms_o, ms_r, act, tot, parity,
-         npts * (3 * 4.0 + 2 * 36.0 + 24.0) + 32.0 * tot,
-         {"obj_export": {"ours_s": t_obj_o, "reference_writer_s": t_obj_r, "bytes": os.path.getsize(p1), "note": "host-side weld + text, wall clock, 1 thread each"}})
+
+    def theirs():
+        v2.zero_()
+        ref.sphere(b2, sph["center"], sph["radius"], sph["thickness"], dims, d, False)
+        ref.copy_parameter(v2, b2, zeros, dims, d, 0.0, obj_union=True)
+        ref.cuboid(b2, cub["center"], cub["angles"], cub["xw"], cub["yw"], cub["zw"], dims, d)
+        ref.copy_parameter(v2, b2, zeros, dims, d, 0.0, obj_union=True)
+        ref.distance_from_line(b2, cyl["center"], cyl["axis"], cyl["radius"], cyl["tr"], cyl["ta"], dims, d, False)
+        return ref.isosurface_csg(False, m2.pos, m2.norm, 0.0, dims, d, (0, 0, 0), s2, mv, v2, b2, zeros, obj_union=False, obj_diff=True)
+
+    ms, (act, tot) = timed(theirs, steps, warmup)
+    if keep is not None:
+        keep.update(gp=v2, mesh=m2, counts=(act, tot))
+    return {"workload": C2["workload"], "points": npts, "reference_kernels": _res(ms, npts, act, tot)}
 
 
-def config5(ctx, args):
-    """Synthetic cantilever density 768x384x384: refine (2x upsample) + computeIsosurface_2 semantics, iso = 0.4 (main.cu:3060-3109)."""
-    cdims, fdims, d = (384, 192, 192), (768, 384, 384), (0.5, 0.5, 0.5)
+# ------------------------------------------------------------------ config 5
+def _config5_density():
+    from gpucadforam_b200 import synth
+    cx, cy, cz = C5["cdims"]
+    return synth.cantilever_density(cx, cy, cz, struts=40, sigma=1.5, device="cuda").contiguous().reshape(-1)
+
+
+def ours_config5(g, ctx, steps, warmup, keep=None):
+    """main.cu:3060-3109: refine (2x upsample of the coarse density) + computeIsosurface_2 semantics, iso = VolumeFraction 0.4."""
+    cdims, fdims, d = C5["cdims"], C5["fdims"], C5["d"]
     cx, cy, cz = cdims
     fx, fy, fz = fdims
     npts, ncell = fx * fy * fz, (fx - 1) * (fy - 1) * (fz - 1)
-    coarse = synth.cantilever_density(cx, cy, cz, struts=40, sigma=1.5, device="cuda").contiguous().reshape(-1)
+    coarse = _config5_density()
     vol_topo = gp_zeros(npts)
     result = torch.zeros(npts, device="cuda")
     lat, iso = g.Gratings(ctx), g.Isosurface(ctx)
     lat.setupTexture(cx, cy, cz)
     pitched_buf = torch.zeros(cx * cy * cz, device="cuda")
     pp = lat.pitched(pitched_buf, cx, cy)
-    dens, dens2 = torch.zeros(npts, device="cuda"), torch.zeros(npts, device="cuda")
-    # count first, then allocate the mesh exactly (the reference preallocates 4 vertices per point)
-    lat.copytotexture(coarse, pp, cx, cy, cz); lat.updateTexture(pp); lat.refine(dens, fx, fy, fz, *d)
-    scr = g.Scratch(ncell)
-    probe = g.MeshBuffers(3)
-    act0, tot0 = iso.computeIsosurface_2(probe.pos, probe.norm, 0.4, scr, fdims, d, (0, 0, 0), 3, vol_topo, dens, 0.0, result)
-    mv = tot0 + 3
-    mesh, mesh2, scr2 = g.MeshBuffers(mv), g.MeshBuffers(mv), g.Scratch(ncell)
+    dens = torch.zeros(npts, device="cuda")
+    lat.copytotexture(coarse, pp, cx, cy, cz)
+    lat.updateTexture(pp)
+    lat.refine(dens, fx, fy, fz, *d)
+    scr, probe = g.Scratch(ncell), g.MeshBuffers(3)
+    _, tot0 = iso.computeIsosurface_2(probe.pos, probe.norm, C5["iso"], scr, fdims, d, (0, 0, 0), 3, vol_topo, dens, 0.0, result)
+    mv = tot0 + 3   # count first, then allocate the mesh exactly (the reference preallocates 4 vertices per point)
+    mesh = g.MeshBuffers(mv)
 
-    def ours():
+    def legacy():
         lat.copytotexture(coarse, pp, cx, cy, cz)
         lat.updateTexture(pp)
         lat.refine(dens, fx, fy, fz, *d)
-        return iso.computeIsosurface_2(mesh.pos, mesh.norm, 0.4, scr, fdims, d, (0, 0, 0), mv, vol_topo, dens, 0.0, result)
+        return iso.computeIsosurface_2(mesh.pos, mesh.norm, C5["iso"], scr, fdims, d, (0, 0, 0), mv, vol_topo, dens, 0.0, result)
 
+    ms, (act, tot) = timed(legacy, steps, warmup)
+    out = {"workload": C5["workload"], "points": npts, "legacy_calls": _res(ms, npts, act, tot, calls=4)}
+    if hasattr(g, "density_surface"):
+        mesh_f = g.MeshBuffers(mv)
+        ms_f, (a2, t2) = timed(lambda: g.density_surface(ctx, coarse, cdims, dens, fdims, d, C5["iso"], d, (0, 0, 0), mesh_f.pos, mesh_f.norm, mv), steps, warmup)
+        out["fused_call"] = _res(ms_f, npts, a2, t2, calls=1, same_mesh_as_legacy=bool((a2, t2) == (act, tot) and same(mesh.pos, mesh_f.pos, tot * 16)
+                                                                                     and same(mesh.norm, mesh_f.norm, tot * 16)))
+    lat.deleteTexture()
+    if keep is not None:
+        keep.update(dens=dens, mesh=mesh, counts=(act, tot), mv=mv)
+    return out
+
+
+def ref_config5(g, ref, steps, warmup, keep=None, mv=None):
+    cdims, fdims, d = C5["cdims"], C5["fdims"], C5["d"]
+    cx, cy, cz = cdims
+    fx, fy, fz = fdims
+    npts, ncell = fx * fy * fz, (fx - 1) * (fy - 1) * (fz - 1)
+    coarse = _config5_density()
+    vol_topo = gp_zeros(npts)
+    result = torch.zeros(npts, device="cuda")
+    dens2 = torch.zeros(npts, device="cuda")
+    scr2 = g.Scratch(ncell)
     ref.setup_texture(cx, cy, cz)
+    ref.upload_texture(coarse, cx, cy, cz)
+    ref.refine(dens2, fdims, d)
+    if mv is None:
+        probe = g.MeshBuffers(3)
+        _, tot0 = ref.isosurface_topo(False, probe.pos, probe.norm, C5["iso"], fdims, d, (0, 0, 0), scr2, 3, vol_topo, dens2, 0.0, result, vol_one=vol_topo, d_solid=dens2)
+        mv = tot0 + 3
+    mesh2 = g.MeshBuffers(mv)
 
     def theirs():
         ref.upload_texture(coarse, cx, cy, cz)
         ref.refine(dens2, fdims, d)
-        return ref.isosurface_topo(False, mesh2.pos, mesh2.norm, 0.4, fdims, d, (0, 0, 0), scr2, mv, vol_topo, dens2, 0.0, result, vol_one=vol_topo, d_solid=dens2)
+        return ref.isosurface_topo(False, mesh2.pos, mesh2.norm, C5["iso"], fdims, d, (0, 0, 0), scr2, mv, vol_topo, dens2, 0.0, result, vol_one=vol_topo, d_solid=dens2)
 
-    ms_o, (act, tot) = timed(ours, args.steps, args.warmup)
-    ms_r, (a2, t2) = timed(theirs, args.steps, args.warmup)
+    ms, (act, tot) = timed(theirs, steps, warmup)
     ref.delete_texture()
-    parity = {"counts": (act, tot) == (a2, t2), "density_bits": same(dens, dens2, npts * 4), "pos_bits": same(mesh.pos, mesh2.pos, tot * 16),
-              "norm_bits": same(mesh.norm, mesh2.norm, tot * 16)}
-    # refine writes 4 B/pt; extraction reads density 4 + grid_points 16 + d_result 4 (only at active cells) per point
-    line(5, "cantilever density 768x384x384 (coarse 384x192x192, 40 struts, sigma 1.5): refine + computeIsosurface_2, iso 0.4", npts, ms_o, ms_r, act, tot,
-         parity, npts * (4.0 + 20.0) + 32.0 * tot)
+    if keep is not None:
+        keep.update(dens=dens2, mesh=mesh2, counts=(act, tot))
+    return {"workload": C5["workload"], "points": npts, "reference_kernels": _res(ms, npts, act, tot)}
+
+
+OURS = {"1": ours_config1, "2": ours_config2, "5": ours_config5}
+REFS = {"1": ref_config1, "2": ref_config2, "5": ref_config5}
+
+
+def run_ours(g, ctx, steps, warmup, which=("1", "2", "5")):
+    out = {}
+    for c in which:
+        out[c] = OURS[c](g, ctx, steps, warmup)
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_reference(g, ref, steps, warmup, which=("1", "2", "5")):
+    out = {}
+    for c in which:
+        out[c] = REFS[c](g, ref, steps, warmup)
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -191,15 +275,37 @@ def main():
     ap.add_argument("--tmp", default="/tmp")
     ap.add_argument("--async-fields", action="store_true", help="GCB_OPT_ASYNC_FIELDS: legacy field calls only enqueue (ours arm)")
     args = ap.parse_args()
+    import gpucadforam_b200 as g
+    import ref_py as ref
     if not ref.available():
         print(json.dumps({"error": "oracle/_ref/libgpucad_ref.so not built"}))
         return 1
-    global LEGACY_CALLS
-    if args.async_fields:
-        LEGACY_CALLS = "ours: enqueue only (GCB_OPT_ASYNC_FIELDS); reference kernels: blocking"
     ctx = g.Context(0, options=g._capi.GCB_OPT_ASYNC_FIELDS if args.async_fields else 0)
-    for c in args.configs.split(","):
-        {"1": lambda: config1(ctx, args), "2": lambda: config2(ctx, args, args.tmp), "5": lambda: config5(ctx, args)}[c.strip()]()
+    for c in [x.strip() for x in args.configs.split(",")]:
+        ko, kr = {}, {}
+        o = OURS[c](g, ctx, args.steps, args.warmup, keep=ko)
+        r = REFS[c](g, ref, args.steps, args.warmup, keep=kr, **({"mv": ko["mv"]} if c == "5" else {}))
+        tot = ko["counts"][1]
+        parity = {"counts": ko["counts"] == kr["counts"], "pos_bits": same(ko["mesh"].pos, kr["mesh"].pos, tot * 16),
+                  "norm_bits": same(ko["mesh"].norm, kr["mesh"].norm, tot * 16)}
+        for key in ("k", "gp", "dens"):
+            if key in ko:
+                parity[key + "_bits"] = bool(torch.equal(ko[key].view(torch.uint8), kr[key].view(torch.uint8)))
+        line = {"config": int(c)}
+        line.update(o)
+        line.update(reference_kernels=r["reference_kernels"], parity_full_size=parity,
+                    speedup_legacy_calls=r["reference_kernels"]["ms"] / o["legacy_calls"]["ms"],
+                    legacy_calls_mode="enqueue only (GCB_OPT_ASYNC_FIELDS)" if args.async_fields else "blocking (as the reference wrappers)")
+        if "fused_call" in o:
+            line["speedup_fused_call"] = r["reference_kernels"]["ms"] / o["fused_call"]["ms"]
+        if c == "2":
+            p1, p2 = os.path.join(args.tmp, "ours.obj"), os.path.join(args.tmp, "ref.obj")
+            t0 = time.time(); g.File_output(ctx).file_write_obj(ko["mesh"].pos, tot, p1); t_o = time.time() - t0
+            t0 = time.time(); ref.write_obj(kr["mesh"].pos, tot, p2); t_r = time.time() - t0
+            line["obj_export"] = {"ours_s": t_o, "reference_writer_s": t_r, "bytes": os.path.getsize(p1), "same_bytes": open(p1, "rb").read() == open(p2, "rb").read()}
+        print(json.dumps(line), flush=True)
+        del ko, kr
+        torch.cuda.empty_cache()
     return 0
 
 
