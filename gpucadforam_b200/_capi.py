@@ -77,6 +77,9 @@ SIGNATURES = {
     "gcb_create_lattice": (I, [P, P, U, U, U, U, U]),
     "gcb_GPU_buffer_normalise_buffer": (I, [P, P, P, I]),
     "gcb_GPU_buffer_normalise_four": (I, [P, P, P, P, C.c_size_t, I, I, I, F, F]),
+    "gcb_GPU_buffer_normalise_three": (I, [P, P, P, C.c_size_t, F, F]),
+    "gcb_period_data": (I, [P, P, I, I, I, F, F, F, F, F, F, C.c_char]),
+    "gcb_angle_data": (I, [P, P, I, I, I, F, F, F, F, F, F, C.c_char]),
     "gcb_grating": (I, [P, P, I, I, I, F, F, F]),
     "gcb_refine": (I, [P, P, I, I, I, F, F, F]),
     "gcb_svl": (I, [P, P, P, I, I, I, I, P]),

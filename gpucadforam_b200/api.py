@@ -257,6 +257,15 @@ class Gratings:
     def GPU_buffer_normalise_four(self, dataone, datatwo, datathree, size, Nx, Ny, Nz, isoval_1, isoval_2):
         self.ctx.check(lib().gcb_GPU_buffer_normalise_four(self.ctx._h, _ptr(dataone), _ptr(datatwo), _ptr(datathree), size, Nx, Ny, Nz, isoval_1, isoval_2))
 
+    def GPU_buffer_normalise_three(self, dataone, datatwo, size, a1, b1):
+        self.ctx.check(lib().gcb_GPU_buffer_normalise_three(self.ctx._h, _ptr(dataone), _ptr(datatwo), size, a1, b1))
+
+    def period_data(self, d_period, NX, NY, NZ, dx, dy, dz, mean_x, mean_y, mean_z, axis="z"):
+        self.ctx.check(lib().gcb_period_data(self.ctx._h, _ptr(d_period), NX, NY, NZ, dx, dy, dz, mean_x, mean_y, mean_z, axis.encode()))
+
+    def angle_data(self, d_theta, NX, NY, NZ, dx, dy, dz, mean_x, mean_y, mean_z, axis="z"):
+        self.ctx.check(lib().gcb_angle_data(self.ctx._h, _ptr(d_theta), NX, NY, NZ, dx, dy, dz, mean_x, mean_y, mean_z, axis.encode()))
+
     def grating(self, dvol, NX2, NY2, NZ2, dx2, dy2, dz2):
         self.ctx.check(lib().gcb_grating(self.ctx._h, _ptr(dvol), NX2, NY2, NZ2, dx2, dy2, dz2))
 

@@ -365,6 +365,19 @@ int gcb_GPU_buffer_normalise_four(gcb_ctx* ctx, float* dataone, float* datatwo, 
     if (int r = k_minmax_device(C, dataone, size)) return r;
     SYNC_RET(k_normalise_four(C, dataone, datatwo, datathree, Nx, Ny, Nz, 0.f, 0.f, isoval_1, isoval_2, C->d_minmax));
 }
+int gcb_GPU_buffer_normalise_three(gcb_ctx* ctx, float* dataone, float* datatwo, size_t size, float a1, float b1) {
+    CTX(ctx);
+    if (int r = k_minmax_device(C, dataone, size)) return r;
+    SYNC_RET(k_normalise_three(C, dataone, datatwo, size, a1, b1, C->d_minmax));
+}
+int gcb_period_data(gcb_ctx* ctx, float* d_period, int NX, int NY, int NZ, float dx, float dy, float dz, float mean_x, float mean_y, float mean_z, char axis) {
+    CTX(ctx);
+    SYNC_RET(k_period_angle(C, d_period, NX, NY, NZ, dx, dy, dz, mean_x, mean_y, mean_z, (int)axis, false));
+}
+int gcb_angle_data(gcb_ctx* ctx, float* d_theta, int NX, int NY, int NZ, float dx, float dy, float dz, float mean_x, float mean_y, float mean_z, char axis) {
+    CTX(ctx);
+    SYNC_RET(k_period_angle(C, d_theta, NX, NY, NZ, dx, dy, dz, mean_x, mean_y, mean_z, (int)axis, true));
+}
 int gcb_minmax(gcb_ctx* ctx, const float* d_in, size_t n, float* lo, float* hi) { CTX(ctx); return k_minmax(C, d_in, n, lo, hi); }
 
 int gcb_grating(gcb_ctx* ctx, void* dvol, int NX2, int NY2, int NZ2, float dx2, float dy2, float dz2) {

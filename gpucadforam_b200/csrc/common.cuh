@@ -147,6 +147,8 @@ int k_copy_parameter(Ctx* c, GridPoint* vol_one, const float* vol_two, const flo
 int k_primitive_field(Ctx* c, const GridPoint* prim, const float* active, float* isosurf, size_t n, bool fixed, bool dynamic);
 int k_topo_field(Ctx* c, const float* topo, float* isosurf, float volfrac, size_t n);
 int k_patch_topo_field(Ctx* c, float* d, int nx, int ny, int nz, const GridPoint* vol_one);
+int k_period_angle(Ctx* c, float* out, int nx, int ny, int nz, float dx, float dy, float dz, float mx, float my, float mz, int axis, bool angle);
+int k_normalise_three(Ctx* c, const float* in, float* out, size_t n, float a1, float b1, const float* d_ab);
 int k_copy_to_pitched(Ctx* c, const float* src, gcb_pitched_ptr dst, int nx, int ny, int nz);
 
 // ---- linear point index -> (x, y, z).  The reference kernels do this with 64-bit / and % per point (up to four ~70-instruction

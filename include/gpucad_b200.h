@@ -181,6 +181,14 @@ int gcb_create_lattice(gcb_ctx* ctx, float* d_latticevol, unsigned int NX, unsig
 int gcb_GPU_buffer_normalise_buffer(gcb_ctx* ctx, float* d_vec1, float* d_vec2, int n);               /* Gratings.cu:1500-1537 */
 int gcb_GPU_buffer_normalise_four(gcb_ctx* ctx, float* dataone, float* datatwo, float* datathree, size_t size, int Nx, int Ny,
     int Nz, float isoval_1, float isoval_2);                                                            /* Gratings.cu:1579-1617 */
+/* Gratings::GPU_buffer_normalise_three (Gratings.h:48, Gratings.cu:1539-1572; kernel device_bufferthree :1071-1087):
+ * datatwo = a1 + b1 * (dataone - min) / (max - min), min / max with the reduction's clamp through zero. */
+int gcb_GPU_buffer_normalise_three(gcb_ctx* ctx, float* dataone, float* datatwo, size_t size, float a1, float b1);
+/* Gratings::period_data / angle_data (Gratings.h:31-35, Gratings.cu:1357-1392; kernels :775-853): the spatially varying period
+ * (distance from the shifted axis, before GPU_buffer_normalise_three maps it to [a1, a1 + b1]) and rotation fields of the SVL
+ * phase solve, Multitopo::spatial_lattice_run main.cu:3927-3931.  axis: 'x', 'y' or 'z'. */
+int gcb_period_data(gcb_ctx* ctx, float* d_period, int NX, int NY, int NZ, float dx, float dy, float dz, float mean_x, float mean_y, float mean_z, char axis);
+int gcb_angle_data(gcb_ctx* ctx, float* d_theta, int NX, int NY, int NZ, float dx, float dy, float dz, float mean_x, float mean_y, float mean_z, char axis);
 int gcb_grating(gcb_ctx* ctx, void* dvol /*float2*/, int NX2, int NY2, int NZ2, float dx2, float dy2, float dz2); /* :976-982 */
 int gcb_refine(gcb_ctx* ctx, float* dvol, int NX2, int NY2, int NZ2, float dx, float dy, float dz);   /* :984-990 */
 int gcb_svl(gcb_ctx* ctx, float* d_svl, void* d_grating /*float2*/, int NX, int NY, int NZ, int indxx, void* data_fft /*float2*/); /* :992-998 */

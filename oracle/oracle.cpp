@@ -979,6 +979,38 @@ void orc_patch_topo_field(float* d, int nx, int ny, int nz, const orc_grid_point
     }
 }
 
+/* set_period_kernel (Gratings.cu:818-853): distance from the axis through (mean - 1/d) in the plane normal to `axis`.  The
+ * reference build contracts `x + 1`, x = (xx - mean_x) * dx, into one fma (read from its SASS); powf(v, 2) is the library pow. */
+void orc_period_data(float* out, int nx, int ny, int nz, float dx, float dy, float dz, float mx, float my, float mz, int axis) {
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)nx * ny * nz; ++i) {
+        const int xx = (int)(i % nx), yy = (int)((i % ((int64_t)nx * ny)) / nx), zz = (int)(i / ((int64_t)nx * ny));
+        const float x1 = fmaf((float)xx - mx, dx, 1.0f), y1 = fmaf((float)yy - my, dy, 1.0f), z1 = fmaf((float)zz - mz, dz, 1.0f);
+        float p;
+        if (axis == 'z') p = sqrtf(powf(x1, 2) + powf(y1, 2));
+        else if (axis == 'y') p = sqrtf(powf(x1, 2) + powf(z1, 2));
+        else p = sqrtf(powf(z1, 2) + powf(y1, 2));
+        out[i] = p;
+    }
+}
+/* set_theta_kernel (Gratings.cu:775-815): atan2f(y + 1, x + 1) for every axis but 'y' */
+void orc_angle_data(float* out, int nx, int ny, int nz, float dx, float dy, float dz, float mx, float my, float mz, int axis) {
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)nx * ny * nz; ++i) {
+        const int xx = (int)(i % nx), yy = (int)((i % ((int64_t)nx * ny)) / nx), zz = (int)(i / ((int64_t)nx * ny));
+        const float x1 = fmaf((float)xx - mx, dx, 1.0f), y1 = fmaf((float)yy - my, dy, 1.0f), z1 = fmaf((float)zz - mz, dz, 1.0f);
+        out[i] = (axis == 'y') ? atan2f(z1, x1) : atan2f(y1, x1);
+    }
+}
+/* GPU_buffer_normalise_three (Gratings.cu:1539-1572): out = a1 + b1 * (in - min) / (max - min) with the reduction's {0, 0} seed;
+ * `a1 + b1 * k` is one fma in the reference build */
+void orc_normalise_three(const float* in, float* out, size_t n, float a1, float b1) {
+    float lo, hi;
+    orc_minmax(in, n, &lo, &hi);
+#pragma omp parallel for
+    for (int64_t i = 0; i < (int64_t)n; ++i) out[i] = fmaf((in[i] - lo) / (hi - lo), b1, a1);
+}
+
 /* File_output::file_write_obj: File_output.cu:5-81 */
 int orc_write_obj(const float* pos, uint32_t total_verts, const char* filename) {
     std::ofstream out(filename, std::ios::out);

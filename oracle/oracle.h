@@ -134,6 +134,12 @@ void orc_primitive_field(const orc_grid_point* prim, const float* active, float*
 void orc_topo_field(const float* topo, float* isosurf, float volfrac, size_t n);
 void orc_patch_topo_field(float* d, int nx, int ny, int nz, const orc_grid_point* vol_one);
 
+/* period / angle fields of the SVL phase solve: set_period_kernel / set_theta_kernel (Gratings.cu:775-853) and
+ * GPU_buffer_normalise_three = min/max reduction + device_bufferthree (Gratings.cu:1071-1087, :1539-1572) */
+void orc_period_data(float* out, int nx, int ny, int nz, float dx, float dy, float dz, float mx, float my, float mz, int axis);
+void orc_angle_data(float* out, int nx, int ny, int nz, float dx, float dy, float dz, float mx, float my, float mz, int axis);
+void orc_normalise_three(const float* in, float* out, size_t n, float a1, float b1);
+
 /* .obj writer (File_output::file_write_obj); pos is float4[total_verts] on the host */
 int orc_write_obj(const float* pos, uint32_t total_verts, const char* filename);
 

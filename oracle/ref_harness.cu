@@ -339,6 +339,10 @@ int ref_period_data(float* d_period, int nx, int ny, int nz, float dx, float dy,
     g_lat->period_data(d_period, nx, ny, nz, dx, dy, dz, mx, my, mz, (char)axis);
     return last_error("period_data");
 }
+int ref_angle_data(float* d_theta, int nx, int ny, int nz, float dx, float dy, float dz, float mx, float my, float mz, int axis) {
+    g_lat->angle_data(d_theta, nx, ny, nz, dx, dy, dz, mx, my, mz, (char)axis);
+    return last_error("angle_data");
+}
 int ref_normalise_three(float* d_in, float* d_out, size_t size, float a1, float b1) {
     g_lat->GPU_buffer_normalise_three(d_in, d_out, size, a1, b1);
     return last_error("normalise_three");

@@ -37,9 +37,9 @@ def fast_field(phi, coef, fdims, ratio):
         def red(zi, yi):
             p = g[zi][:, yi][:, :, ix]
             pn = g[zi][:, yi][:, :, ix1]
-            pr = (fq * (-hi)).astype(np.float64) + p.astype(np.float64)   # fma: one rounding
-            pr = pr.astype(F)
-            pr = ((fq * (-lo)).astype(np.float64) + pr.astype(np.float64)).astype(F)
+            pr = (fq.astype(np.float64) * (-float(hi)) + p.astype(np.float64)).astype(F)   # fma: exact product, one rounding
+            pr = (fq.astype(np.float64) * (-float(lo)) + pr.astype(np.float64)).astype(F)
+            pr = (pr + th).astype(F)                                      # theta is folded into the staged value
             dxv = (pn - p).astype(F)
             return (wx[None, None, :].astype(np.float64) * dxv.astype(np.float64) + pr.astype(np.float64)).astype(F)   # x-lerp, fma
         L00, L01, L10, L11 = red(izc, iy), red(izc, iy1), red(iz1, iy), red(iz1, iy1)
@@ -49,8 +49,7 @@ def fast_field(phi, coef, fdims, ratio):
         m1 = (wyb.astype(np.float64) * D1.astype(np.float64) + L10.astype(np.float64)).astype(F)
         E = (m1 - m0).astype(F)
         v = (wzb.astype(np.float64) * E.astype(np.float64) + m0.astype(np.float64)).astype(F)
-        r = (v + th).astype(F)
-        c = np.cos(r.astype(np.float64)).astype(F)
+        c = np.cos(v.astype(np.float64)).astype(F)
         out = (c.astype(np.float64) * float(am) + out.astype(np.float64)).astype(F)
     return out
 

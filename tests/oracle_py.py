@@ -246,6 +246,23 @@ def patch_topo_field(d, dims, vol_one):
     return out
 
 
+def period_data(dims, d, mean, axis="z", angle=False):
+    """orc_period_data / orc_angle_data (Gratings.cu:775-853) -> [nz, ny, nx] float32."""
+    nx, ny, nz = dims
+    out = np.zeros((nz, ny, nx), np.float32)
+    fn = lib().orc_angle_data if angle else lib().orc_period_data
+    fn(_p(out), nx, ny, nz, C.c_float(d[0]), C.c_float(d[1]), C.c_float(d[2]), C.c_float(mean[0]), C.c_float(mean[1]), C.c_float(mean[2]), ord(axis))
+    return out
+
+
+def normalise_three(f, a1, b1):
+    """orc_normalise_three (Gratings.cu:1539-1572)."""
+    f = _f(f)
+    out = np.zeros_like(f)
+    lib().orc_normalise_three(_p(f), _p(out), C.c_size_t(f.size), C.c_float(a1), C.c_float(b1))
+    return out
+
+
 def write_obj(pos, total_verts, filename):
     pos = _f(pos)
     return lib().orc_write_obj(_p(pos), C.c_uint32(total_verts), filename.encode())

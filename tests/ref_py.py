@@ -190,6 +190,10 @@ def period_data(d_period, dims, d, mean, axis="z"):
     _ok(lib().ref_period_data(_p(d_period), dims[0], dims[1], dims[2], F(d[0]), F(d[1]), F(d[2]), F(mean[0]), F(mean[1]), F(mean[2]), ord(axis)))
 
 
+def angle_data(d_theta, dims, d, mean, axis="z"):
+    _ok(lib().ref_angle_data(_p(d_theta), dims[0], dims[1], dims[2], F(d[0]), F(d[1]), F(d[2]), F(mean[0]), F(mean[1]), F(mean[2]), ord(axis)))
+
+
 def normalise_three(d_in, d_out, size, a1, b1):
     _ok(lib().ref_normalise_three(_p(d_in), _p(d_out), C.c_size_t(size), F(a1), F(b1)))
 

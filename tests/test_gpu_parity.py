@@ -1483,3 +1483,55 @@ def test_fast_field_option_leaves_other_ratios_on_the_exact_kernels(ctx, fctx):
     g.svl_field(ctx, a, dev(phi), coef, cdims, fdims, d)
     g.svl_field(fctx, b, dev(phi), coef, cdims, fdims, d)
     assert_bits_equal(a, b, "ratio 3: fast option ignored")
+
+
+# ------------------------------------------------------------------ period / angle fields (producers of finding_phi's d_period)
+@pytest.mark.parametrize("axis", ["z", "y", "x"])
+@pytest.mark.parametrize("dims,d,mean", [((32, 16, 24), (1.0, 1.0, 1.0), (16.0, 8.0, 12.0)), ((16, 16, 8), (0.5, 0.25, 1.5), (0.0, 0.0, 0.0))],
+                         ids=["round_lattice_means", "zero_means"])
+def test_period_and_angle_data_three_way(ctx, axis, dims, d, mean):
+    """Gratings::period_data / angle_data (Gratings.cu:1357-1392, kernels :775-853) as Multitopo::spatial_lattice_run calls them
+    (main.cu:3927-3929): bit-identical to the reference kernels (same fma contraction of `x + 1`, same inlined powf / atan2f), within
+    2 ulp of the oracle (glibc powf / atan2f).  Point counts are multiples of 1024."""
+    n = dims[0] * dims[1] * dims[2]
+    lat = g.Gratings(ctx)
+    per, ang = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lat.period_data(per, *dims, *d, *mean, axis)
+    lat.angle_data(ang, *dims, *d, *mean, axis)
+    op = orc.period_data(dims, d, mean, axis).reshape(-1)
+    oa = orc.period_data(dims, d, mean, axis, angle=True).reshape(-1)
+    assert ulp_diff(per, dev(op)) <= 2
+    assert np.allclose(ang.cpu().numpy(), oa, rtol=0, atol=1e-6)
+    if HAVE_REF:
+        per2, ang2 = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        ref.period_data(per2, dims, d, mean, axis)
+        ref.angle_data(ang2, dims, d, mean, axis)
+        assert_bits_equal(per, per2, "period_data vs reference")
+        assert_bits_equal(ang, ang2, "angle_data vs reference")
+
+
+def test_normalise_three_and_period_to_phase_chain(ctx):
+    """GPU_buffer_normalise_three (Gratings.cu:1539-1572) on the period field, then finding_phi on the result: the chain
+    period_data -> normalise_three -> finding_phi of spatial_lattice_run (main.cu:3929-3959) through the C ABI, bit for bit."""
+    dims, d = (32, 16, 24), (1.0, 1.0, 1.0)
+    n = dims[0] * dims[1] * dims[2]
+    mean = (dims[0] / 2.0, dims[1] / 2.0, dims[2] / 2.0)
+    a1, b1 = float(dims[0] // 10), float(dims[0] // 4)   # NumX/10, NumX/4 in integer arithmetic (main.cu:3931)
+    lat = g.Gratings(ctx)
+    per = torch.zeros(n, device="cuda")
+    lat.period_data(per, *dims, *d, *mean, "z")
+    raw = per.clone()
+    lat.GPU_buffer_normalise_three(per, per, n, a1, b1)      # in place, as the reference calls it
+    o = orc.normalise_three(raw.cpu().numpy(), a1, b1)
+    assert ulp_diff(per, dev(o)) <= 1
+    assert abs(float(per.min()) - a1) < 1e-5 and abs(float(per.max()) - (a1 + b1)) < 1e-4
+    phi = torch.zeros(n, device="cuda")
+    g.finding_phi(ctx, phi, per, dims, (1, -2, 1), d)
+    if HAVE_REF:
+        per2 = torch.zeros(n, device="cuda")
+        ref.period_data(per2, dims, d, mean, "z")
+        ref.normalise_three(per2, per2, n, a1, b1)
+        assert_bits_equal(per, per2, "normalise_three vs reference")
+        phi2 = torch.zeros(n, device="cuda")
+        ref.finding_phi(phi2, per2, dims, (1, -2, 1), d)
+        assert_bits_equal(phi, phi2, "finding_phi on the normalised period field")

@@ -167,3 +167,17 @@ def test_lattice_ids_two_zero_use_the_second_field():
     r = orc.extract(orc.MODE_LATTICE, dims, (1, 1, 1), (0, 0, 0), cases.ISO_MASK, f0=mask, f1=k1, f2=k2, iso1=0.2, iso2=0.3, iso1b=0.6, iso2b=0.9)
     assert r["active"] == 1 and r["total"] == 6
     assert np.allclose(r["pos"][:6, 2], 0.75)
+
+
+def test_period_and_normalise_three_known_answers():
+    """period_data = distance from the shifted axis; GPU_buffer_normalise_three maps it onto [a1, a1 + b1] (main.cu:3929-3931)."""
+    dims, d, mean = (16, 12, 8), (1.0, 1.0, 1.0), (8.0, 6.0, 4.0)
+    p = orc.period_data(dims, d, mean, "z")
+    z, y, x = np.meshgrid(np.arange(8), np.arange(12), np.arange(16), indexing="ij")
+    want = np.sqrt((x - 8.0 + 1.0) ** 2 + (y - 6.0 + 1.0) ** 2)
+    assert np.allclose(p, want, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(p[0], p[5])                       # 'z': no dependence on z
+    n3 = orc.normalise_three(p, 1.0, 4.0)                   # NumX/10, NumX/4 in integer arithmetic for NumX = 16
+    assert abs(float(n3.min()) - 1.0) < 1e-6 and abs(float(n3.max()) - 5.0) < 1e-6
+    th = orc.period_data(dims, d, mean, "z", angle=True)
+    assert np.allclose(th, np.arctan2(y - 6.0 + 1.0, x - 8.0 + 1.0), atol=1e-6)
