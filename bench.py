@@ -196,29 +196,56 @@ class SvlLeg:
     def _field_and_minmax(self):
         g, sharding = self.env["g"], self.env["sharding"]
         g.svl_field(self.ctx, self.svl, self.phi, self.coef, (self.cxy, self.cxy, self.czl), self.ldims, self.d, slab=(self.z0, self.gnz), cz0=self.c0, d_minmax=self.mm)
-        return sharding.allreduce_minmax(self.env["dist"], self.mm)   # one 2-float all-reduce (N > 1), then the values on the host
+        return sharding.allreduce_minmax(self.env["dist"], self.mm)   # set-up only: the values on the host
 
     def step(self):
-        g = self.env["g"]
-        a, b = self._field_and_minmax()
-        return g.extract_band_raw(self.ctx, self.svl, a, b, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap,
-                                  slab=(self.z0, self.gnz))
+        """field -> min/max (stays on the device; N > 1: one 2-float NCCL all-reduce) -> extraction reading the range in place -> counts"""
+        g, sharding = self.env["g"], self.env["sharding"]
+        g.svl_field(self.ctx, self.svl, self.phi, self.coef, (self.cxy, self.cxy, self.czl), self.ldims, self.d, slab=(self.z0, self.gnz), cz0=self.c0, d_minmax=self.mm)
+        ab = sharding.allreduce_minmax_device(self.env["dist"], self.mm)
+        return g.extract_band_raw_dev(self.ctx, self.svl, ab, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap,
+                                      slab=(self.z0, self.gnz))
 
-    def e2e_step(self):
-        g, sharding, torch = self.env["g"], self.env["sharding"], self.env["torch"]
+    def _host_buffers(self):
+        torch = self.env["torch"]
         if self.hphi is None:
             self.hphi = torch.empty(self.phi.shape, dtype=torch.float32, pin_memory=True)
             self.hphi.copy_(self.phi)
             self.phi_scratch = torch.empty_like(self.phi)
-        cd = (self.cxy, self.cxy, self.czl)
+        return (self.cxy, self.cxy, self.czl)
+
+    def e2e_step(self):
+        """one blocking call with HOST control grids (H2D inside), counts read back"""
+        g, sharding = self.env["g"], self.env["sharding"]
+        cd = self._host_buffers()
         if self.env["world"] == 1:
             a_, t_, _ = g.svl_lattice_host(self.ctx, self.hphi, self.phi_scratch, self.svl, self.coef, cd, self.ldims, self.d, ISO_MASK, BAND_LO, BAND_HI, self.d,
                                            (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap)
             return a_, t_
         g.svl_field_host(self.ctx, self.svl, self.hphi, self.phi_scratch, self.coef, cd, self.ldims, self.d, slab=(self.z0, self.gnz), cz0=self.c0, d_minmax=self.mm)
-        a_, b_ = sharding.allreduce_minmax(self.env["dist"], self.mm)
-        return g.extract_band_raw(self.ctx, self.svl, a_, b_, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap,
-                                  slab=(self.z0, self.gnz))
+        ab = sharding.allreduce_minmax_device(self.env["dist"], self.mm)
+        return g.extract_band_raw_dev(self.ctx, self.svl, ab, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap,
+                                      slab=(self.z0, self.gnz))
+
+    def e2e_pipelined(self, steps):
+        """`steps` jobs through the two-deep job pipeline (gcb_svl_lattice_host_submit / _wait): every job copies its control grids from
+        pinned host memory and has its counts read back; job i+1's copies overlap job i's kernels.  Single GPU.  Returns the results."""
+        g, torch = self.env["g"], self.env["torch"]
+        cd = self._host_buffers()
+        if not hasattr(self, "phi_scratch2") or self.phi_scratch2 is None:
+            self.phi_scratch2 = torch.empty_like(self.phi)
+        scr = [self.phi_scratch, self.phi_scratch2]
+
+        def submit(i):
+            g.svl_lattice_host_submit(self.ctx, i % 2, self.hphi, scr[i % 2], self.svl, self.coef, cd, self.ldims, self.d, ISO_MASK, BAND_LO, BAND_HI, self.d,
+                                      (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap)
+        res = []
+        submit(0)
+        for i in range(1, steps):
+            submit(i)
+            res.append(g.svl_lattice_host_wait(self.ctx, (i - 1) % 2)[:2])
+        res.append(g.svl_lattice_host_wait(self.ctx, (steps - 1) % 2)[:2])
+        return res
 
     def run(self, steps, warmup, e2e=True, sampler=None):
         """Device-timed steps (CUDA events on the current stream, barrier + synchronize on both sides), then the e2e steps.
@@ -259,7 +286,15 @@ class SvlLeg:
                 self.e2e_step()
             e1.record()
             env["barrier"]()
-            out["e2e_ms"] = e0.elapsed_time(e1) / steps
+            out["e2e_ms"] = out["e2e_blocking_ms"] = e0.elapsed_time(e1) / steps
+            if env["world"] == 1:
+                assert all(r == (self.act, self.tot) for r in self.e2e_pipelined(3))
+                env["barrier"]()
+                e0.record()
+                self.e2e_pipelined(steps)
+                e1.record()
+                env["barrier"]()
+                out["e2e_ms"] = e0.elapsed_time(e1) / steps
         return out
 
     def reduce(self, r):
@@ -275,7 +310,8 @@ class SvlLeg:
             dist.all_reduce(lt)
             g_launch = int(lt[0])
         ms, e2e_ms, ext_k, fld_k = [float(x) for x in stats.cpu()]
-        return {"ms": ms, "e2e_ms": e2e_ms if r["e2e_ms"] is not None else None, "ext_ms": ext_k, "fld_ms": fld_k, "launches": g_launch,
+        return {"ms": ms, "e2e_ms": e2e_ms if r["e2e_ms"] is not None else None, "e2e_blocking_ms": r.get("e2e_blocking_ms"), "ext_ms": ext_k, "fld_ms": fld_k,
+                "launches": g_launch,
                 "g_act": g_act, "g_tot": g_tot, "per_rank_verts": [v for (_, v) in per_rank]}
 
     def summary(self, red, peak):
@@ -289,13 +325,13 @@ class SvlLeg:
                "field_kernel_ms": red["fld_ms"], "extract_kernel_ms": red["ext_ms"],
                "extraction_hbm_frac": alg_ext / (red["ext_ms"] * 1e-3) / 1e9 / peak}
         if red["e2e_ms"] is not None:
-            out["e2e"] = {"value": points / (red["e2e_ms"] * 1e-3), "unit": "voxels/s", "ms_per_step": red["e2e_ms"],
+            out["e2e"] = {"value": points / (red["e2e_ms"] * 1e-3), "unit": "voxels/s", "ms_per_step": red["e2e_ms"], "blocking_call_ms": red["e2e_blocking_ms"],
                           "h2d_bytes_per_step": int(self.phi.numel() * 4 * self.env["world"]), "d2h_bytes_per_step": int((16 + 8) * self.env["world"])}
         return out
 
     def free(self):
         torch = self.env["torch"]
-        for name in ("phi", "svl", "mesh", "hphi", "phi_scratch", "mm"):
+        for name in ("phi", "svl", "mesh", "hphi", "phi_scratch", "phi_scratch2", "mm"):
             if hasattr(self, name):
                 setattr(self, name, None)
         torch.cuda.synchronize()
@@ -468,6 +504,11 @@ def main():
             "per_rank_vertices": red["per_rank_verts"],
             "e2e": {"value": points / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(phi_elems * 4 * world), "d2h_bytes_per_step": int((16 + 8) * world),
+                    "mode": ("two-deep job pipeline (gcb_svl_lattice_host_submit / _wait): every step copies its control grids from pinned host memory and "
+                             "reads its counts back; step i+1's copies overlap step i's kernels") if world == 1 else
+                            "one blocking sequence per step and rank (host control grids -> field -> NCCL min/max on the device -> extraction -> counts)",
+                    "blocking_call": {"ms_per_step": red["e2e_blocking_ms"], "value": points / (red["e2e_blocking_ms"] * 1e-3),
+                                      "note": "gcb_svl_lattice_host, one call per step, nothing overlapped across steps"},
                     "note": "control grids copied from pinned host memory each step; counts and min/max read back; the mesh stays in device memory "
                             "as in the reference (Vulkan-exported vertex buffers)",
                     "host_cpus_bound_rank0": affinity},

@@ -98,6 +98,9 @@ SIGNATURES = {
     "gcb_svl_field_host": (I, [P, P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, P]),
     "gcb_minmax": (I, [P, P, C.c_size_t, PF, PF]),
     "gcb_extract_band_raw": (I, [P, P, F, F, F, F, F, Uint3, Slab, Float3, Float3, P, P, ULL, P, I, PULL, PULL]),
+    "gcb_extract_band_raw_dev": (I, [P, P, P, F, F, F, Uint3, Slab, Float3, Float3, P, P, ULL, P, I, PULL, PULL]),
+    "gcb_svl_lattice_host_submit": (I, [P, I, P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL]),
+    "gcb_svl_lattice_host_wait": (I, [P, I, PULL, PULL, PF]),
     "gcb_svl_lattice": (I, [P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),
     "gcb_svl_lattice_host": (I, [P, P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),
 }

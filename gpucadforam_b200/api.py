@@ -380,6 +380,33 @@ def extract_band_raw(ctx, d_field, a, b, isoValue, isovalue1, isovalue2, gridSiz
     return act.value, tot.value
 
 
+def extract_band_raw_dev(ctx, d_field, d_minmax, isoValue, isovalue1, isovalue2, gridSizeLocal, voxelSize, gridcenter, pos, norm, maxVerts, slab=(0, 0),
+                         comp=None, count_only=False):
+    """extract_band_raw with the normalisation range {min, max} read from device memory (2-float CUDA tensor)."""
+    act, tot = C.c_ulonglong(0), C.c_ulonglong(0)
+    ctx.check(lib().gcb_extract_band_raw_dev(ctx._h, _ptr(d_field), _ptr(d_minmax), isoValue, isovalue1, isovalue2, _u3(gridSizeLocal),
+                                             Slab(slab[0], slab[1] or gridSizeLocal[2]), _f3(voxelSize), _f3(gridcenter), _ptr(pos), _ptr(norm), maxVerts,
+                                             _ptr(comp), int(count_only), C.byref(act), C.byref(tot)))
+    return act.value, tot.value
+
+
+def svl_lattice_host_submit(ctx, slot, h_phi, d_phi_scratch, d_svl_scratch, coef, cdims, fdims, d, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos,
+                            norm, maxVerts):
+    """Enqueue one host-input job in pipeline slot 0 / 1 (gcb_svl_lattice_host_submit); returns immediately."""
+    assert not h_phi.is_cuda and h_phi.is_contiguous()
+    ctx.check(lib().gcb_svl_lattice_host_submit(ctx._h, int(slot), C.c_void_p(h_phi.data_ptr()), _ptr(d_phi_scratch), _ptr(d_svl_scratch), len(coef),
+                                                _coef_array(coef), cdims[0], cdims[1], cdims[2], fdims[0], fdims[1], fdims[2], d[0], d[1], d[2], isoValue,
+                                                isovalue1, isovalue2, _f3(voxelSize), _f3(gridcenter), _ptr(pos), _ptr(norm), maxVerts))
+
+
+def svl_lattice_host_wait(ctx, slot):
+    """Block until the job in `slot` is complete: (activeVoxels, totalVerts, (min, max))."""
+    act, tot = C.c_ulonglong(0), C.c_ulonglong(0)
+    mm = (C.c_float * 2)()
+    ctx.check(lib().gcb_svl_lattice_host_wait(ctx._h, int(slot), C.byref(act), C.byref(tot), mm))
+    return act.value, tot.value, (mm[0], mm[1])
+
+
 def svl_lattice(ctx, d_svl_scratch, d_phi, coef, cdims, fdims, d, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos, norm, maxVerts):
     act, tot = C.c_ulonglong(0), C.c_ulonglong(0)
     mm = (C.c_float * 2)()

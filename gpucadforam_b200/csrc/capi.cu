@@ -98,6 +98,13 @@ int gcb_destroy(gcb_ctx* ctx) {
     if (C->copy_stream) { cudaStreamDestroy(C->copy_stream); for (int i = 0; i < Ctx::kBatches; ++i) cudaEventDestroy(C->copy_ev[i]); }
     if (C->aux_stream) { cudaStreamDestroy(C->aux_stream); cudaEventDestroy(C->aux_ev[0]); cudaEventDestroy(C->aux_ev[1]); }
     for (int i = 0; i < 4; ++i) if (C->ev[i]) cudaEventDestroy(C->ev[i]);
+    for (auto& sl : C->slot) {
+        if (sl.h_totals) cudaFreeHost(sl.h_totals);
+        if (sl.h_minmax) cudaFreeHost(sl.h_minmax);
+        if (sl.d_minmax) cudaFree(sl.d_minmax);
+        if (sl.field_done) cudaEventDestroy(sl.field_done);
+        if (sl.job_done) cudaEventDestroy(sl.job_done);
+    }
     delete C;
     return 0;
 }
@@ -489,16 +496,17 @@ int gcb_svl_field(gcb_ctx* ctx, float* d_svl, const float* d_phi, int nh, const 
     return 0;
 }
 
-int gcb_extract_band_raw(gcb_ctx* ctx, const float* d_field, float a, float b, float isoValue, float isovalue1, float isovalue2, gcb_uint3 gridSizeLocal,
-                         gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
-                         unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels, unsigned long long* totalVerts) {
-    CTX(ctx);
+static int extract_band_raw_impl(Ctx* C, const float* d_field, float a, float b, const float* d_ab, float isoValue, float isovalue1, float isovalue2,
+                                 gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
+                                 unsigned long long maxVerts, unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels,
+                                 unsigned long long* totalVerts, unsigned long long* h_totals_async) {
     if (!d_field) return fail_msg(C, "extract_band_raw: null field");
     McArgs A;
     base_args(A, M_BAND_RAW, gridSizeLocal, voxelSize, gridcenter, isoValue);
     A.iso1 = isovalue1; A.iso2 = isovalue2;
     A.f0 = d_field;
     A.na = a; A.nb = b;
+    A.d_ab = d_ab;
     A.gz0 = slab.z0;
     A.gnz = slab.gnz ? slab.gnz : gridSizeLocal.z;
     A.pos = (float4*)pos; A.norm = (float4*)norm;
@@ -506,10 +514,27 @@ int gcb_extract_band_raw(gcb_ctx* ctx, const float* d_field, float a, float b, f
     A.comp = d_compVoxelArray;
     A.count_only = count_only;
     unsigned long long act = 0, verts = 0;
-    if (int r = launch_extract(C, A, &act, &verts)) return r;
+    if (int r = launch_extract(C, A, &act, &verts, h_totals_async)) return r;
+    if (h_totals_async) return 0;
     if (activeVoxels) *activeVoxels = act;
     if (totalVerts) *totalVerts = count_only ? C->h_totals[1] : verts;
     return 0;
+}
+int gcb_extract_band_raw(gcb_ctx* ctx, const float* d_field, float a, float b, float isoValue, float isovalue1, float isovalue2, gcb_uint3 gridSizeLocal,
+                         gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
+                         unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels, unsigned long long* totalVerts) {
+    CTX(ctx);
+    return extract_band_raw_impl(C, d_field, a, b, nullptr, isoValue, isovalue1, isovalue2, gridSizeLocal, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+                                 d_compVoxelArray, count_only, activeVoxels, totalVerts, nullptr);
+}
+int gcb_extract_band_raw_dev(gcb_ctx* ctx, const float* d_field, const float* d_minmax, float isoValue, float isovalue1, float isovalue2,
+                             gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
+                             unsigned long long maxVerts, unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels,
+                             unsigned long long* totalVerts) {
+    CTX(ctx);
+    if (!d_minmax) return fail_msg(C, "extract_band_raw_dev: null min/max pointer");
+    return extract_band_raw_impl(C, d_field, 0.f, 0.f, d_minmax, isoValue, isovalue1, isovalue2, gridSizeLocal, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+                                 d_compVoxelArray, count_only, activeVoxels, totalVerts, nullptr);
 }
 
 int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz, int NX2, int NY2, int NZ2,
@@ -517,19 +542,24 @@ int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int 
                     void* norm, unsigned long long maxVerts, unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out) {
     CTX(ctx);
     gcb_slab slab{0u, (unsigned)NZ2};
+    // field -> min/max stays in device memory -> extraction reads it there: ONE synchronisation, at the end, for the counts
     if (int r = gcb_svl_field(ctx, d_svl_scratch, d_phi, nh, coef_host, cx, cy, cz, 0, NX2, NY2, NZ2, slab, dx, dy, dz, 0, C->d_minmax)) return r;
-    GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
-    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
-    const float a = C->h_minmax[0], b = C->h_minmax[1];
-    if (minmax_out) { minmax_out[0] = a; minmax_out[1] = b; }
+    if (minmax_out) GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
     gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
-    return gcb_extract_band_raw(ctx, d_svl_scratch, a, b, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts, nullptr, 0,
-                                activeVoxels, totalVerts);
+    if (int r = extract_band_raw_impl(C, d_svl_scratch, 0.f, 0.f, C->d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+                                      nullptr, 0, activeVoxels, totalVerts, nullptr))
+        return r;
+    if (minmax_out) { minmax_out[0] = C->h_minmax[0]; minmax_out[1] = C->h_minmax[1]; }
+    return 0;
 }
 
-int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_phi_scratch, int nh, const float* coef_host, int cx, int cy, int cz_local,
-                       int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_minmax) {
-    CTX(ctx);
+// d_mm: device scratch of the reduction (2 words, decoded in place to {min, max} floats), null = no reduction; d_minmax_out: where
+// the caller wants the decoded pair (may equal d_mm or be null); scratch_free: event after which d_phi_scratch may be overwritten
+// (null: everything queued on the compute stream so far)
+static int svl_field_host_impl(gcb_ctx* ctx, Ctx* C, float* d_svl, const float* h_phi, float* d_phi_scratch, int nh, const float* coef_host, int cx, int cy,
+                               int cz_local, int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_mm,
+                               float* d_minmax_out, cudaEvent_t scratch_free) {
+    float* const d_minmax = d_mm;
     // Upload / compute overlap by z-slabs of the FINE grid: a slab of fine layers needs only the control planes that bracket
     // it, for all harmonics -- one strided copy (nh rows of `planes * cy * cx` floats) on a copy stream -- and is then evaluated
     // for all harmonics in one launch, so every tile pays its staging prologue once and the running sum never round-trips
@@ -544,7 +574,7 @@ int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_
         GCB_CHECK(C, cudaEventCreateWithFlags(&C->aux_ev[0], cudaEventDisableTiming));
         GCB_CHECK(C, cudaEventCreateWithFlags(&C->aux_ev[1], cudaEventDisableTiming));
     }
-    if (nh <= 0 || NZ2_local <= 0) return gcb_svl_field(ctx, d_svl, d_phi_scratch, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, NZ2_local, slab, dx, dy, dz, 0, d_minmax);
+    if (nh <= 0 || NZ2_local <= 0) return gcb_svl_field(ctx, d_svl, d_phi_scratch, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, NZ2_local, slab, dx, dy, dz, 0, d_minmax_out);
     const size_t plane = (size_t)cx * cy, per = plane * cz_local;
     // slab thicknesses (fine layers, multiples of 8): 8, 8, 16, then ~1/14 of the grid each
     int f_start[Ctx::kBatches + 1];
@@ -563,9 +593,13 @@ int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_
         }
         f_start[nb] = NZ2_local;
     }
-    // order the copy stream after everything already queued on the compute stream (the scratch may still be in use)
-    GCB_CHECK(C, cudaEventRecord(C->copy_ev[0], C->stream));
-    GCB_CHECK(C, cudaStreamWaitEvent(C->copy_stream, C->copy_ev[0], 0));
+    // order the copy stream after the last reader of the scratch: an event of the caller's (job pipeline), else everything
+    // already queued on the compute stream
+    if (scratch_free) GCB_CHECK(C, cudaStreamWaitEvent(C->copy_stream, scratch_free, 0));
+    else {
+        GCB_CHECK(C, cudaEventRecord(C->copy_ev[0], C->stream));
+        GCB_CHECK(C, cudaStreamWaitEvent(C->copy_stream, C->copy_ev[0], 0));
+    }
     int copied = 0;  // local control planes [0, copied) are already queued
     for (int b = 0; b < nb; ++b) {
         // control planes bracketing fine layers [f_start[b], f_start[b+1]) (+1 plane of slack against rounding in generic ratios)
@@ -581,7 +615,7 @@ int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_
         }
         GCB_CHECK(C, cudaEventRecord(C->copy_ev[b], C->copy_stream));
     }
-    if (d_minmax) if (int r = k_minmax_init(C, C->d_minmax)) return r;
+    if (d_minmax) if (int r = k_minmax_init(C, d_mm)) return r;
     if (C->timing) cudaEventRecord(C->ev[2], C->stream);
     static const bool trace = getenv("GCB_TRACE") != nullptr;  // debugging aid: per-slab timeline on stderr
     cudaEvent_t tev[Ctx::kBatches + 1];
@@ -597,7 +631,7 @@ int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_
         const int f0 = f_start[b], f1 = f_start[b + 1];
         C->stream = st;
         const int r = k_svl_field(C, d_svl + (size_t)f0 * NX2 * NY2, d_phi_scratch, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, f1 - f0, slab.z0 + (unsigned)f0, dx,
-                                  dy, dz, 0, d_minmax ? C->d_minmax : nullptr);
+                                  dy, dz, 0, d_mm);
         C->stream = main_stream;
         if (r) return r;
         if (trace) cudaEventRecord(tev[b + 1], st);
@@ -610,8 +644,14 @@ int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_
         for (int b = 0; b <= nb; ++b) cudaEventDestroy(tev[b]);
     }
     if (C->timing) { cudaEventRecord(C->ev[3], C->stream); C->field_timed = true; }
-    if (d_minmax) if (int r = k_minmax_decode(C, C->d_minmax, d_minmax)) return r;
+    if (d_mm) if (int r = k_minmax_decode(C, d_mm, d_minmax_out ? d_minmax_out : d_mm)) return r;
     return 0;
+}
+int gcb_svl_field_host(gcb_ctx* ctx, float* d_svl, const float* h_phi, float* d_phi_scratch, int nh, const float* coef_host, int cx, int cy, int cz_local,
+                       int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_minmax) {
+    CTX(ctx);
+    return svl_field_host_impl(ctx, C, d_svl, h_phi, d_phi_scratch, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, NZ2_local, slab, dx, dy, dz,
+                               d_minmax ? C->d_minmax : nullptr, d_minmax, nullptr);
 }
 
 int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host, int cx, int cy, int cz,
@@ -620,14 +660,63 @@ int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch,
                          unsigned long long* totalVerts, float* minmax_out) {
     CTX(ctx);
     gcb_slab slab{0u, (unsigned)NZ2};
-    if (int r = gcb_svl_field_host(ctx, d_svl_scratch, h_phi, d_phi_scratch, nh, coef_host, cx, cy, cz, 0, NX2, NY2, NZ2, slab, dx, dy, dz, C->d_minmax)) return r;
-    GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
-    GCB_CHECK(C, cudaStreamSynchronize(C->stream));
-    const float a = C->h_minmax[0], bmax = C->h_minmax[1];
-    if (minmax_out) { minmax_out[0] = a; minmax_out[1] = bmax; }
+    if (int r = svl_field_host_impl(ctx, C, d_svl_scratch, h_phi, d_phi_scratch, nh, coef_host, cx, cy, cz, 0, NX2, NY2, NZ2, slab, dx, dy, dz, C->d_minmax, C->d_minmax,
+                                    nullptr))
+        return r;
+    if (minmax_out) GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
     gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
-    return gcb_extract_band_raw(ctx, d_svl_scratch, a, bmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts, nullptr, 0,
-                                activeVoxels, totalVerts);
+    if (int r = extract_band_raw_impl(C, d_svl_scratch, 0.f, 0.f, C->d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+                                      nullptr, 0, activeVoxels, totalVerts, nullptr))
+        return r;
+    if (minmax_out) { minmax_out[0] = C->h_minmax[0]; minmax_out[1] = C->h_minmax[1]; }
+    return 0;
+}
+
+// ------------------------------------------------------------------ two-deep job pipeline of the host-input path
+static int slot_init(Ctx* C, Ctx::Slot& s) {
+    if (s.h_totals) return 0;
+    GCB_CHECK(C, cudaMallocHost(&s.h_totals, 16));
+    GCB_CHECK(C, cudaMallocHost(&s.h_minmax, 16));
+    GCB_CHECK(C, cudaMalloc(&s.d_minmax, 16));
+    GCB_CHECK(C, cudaEventCreateWithFlags(&s.field_done, cudaEventDisableTiming));
+    GCB_CHECK(C, cudaEventCreateWithFlags(&s.job_done, cudaEventDisableTiming));
+    return 0;
+}
+int gcb_svl_lattice_host_submit(gcb_ctx* ctx, int slot, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host, int cx,
+                                int cy, int cz, int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2,
+                                gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts) {
+    CTX(ctx);
+    if (slot < 0 || slot > 1) return fail_msg(C, "svl_lattice_host_submit: slot must be 0 or 1");
+    Ctx::Slot& S = C->slot[slot];
+    if (S.busy) return fail_msg(C, "svl_lattice_host_submit: slot still holds an unfinished job (call gcb_svl_lattice_host_wait first)");
+    if (int r = slot_init(C, S)) return r;
+    gcb_slab slab{0u, (unsigned)NZ2};
+    // the control grids of this job are copied while the previous job (other slot, other scratch) computes: the copy stream only
+    // waits for the last field kernel that read THIS slot's scratch
+    if (int r = svl_field_host_impl(ctx, C, d_svl_scratch, h_phi, d_phi_scratch, nh, coef_host, cx, cy, cz, 0, NX2, NY2, NZ2, slab, dx, dy, dz, S.d_minmax, S.d_minmax,
+                                    S.field_done))
+        return r;
+    GCB_CHECK(C, cudaEventRecord(S.field_done, C->stream));
+    GCB_CHECK(C, cudaMemcpyAsync(S.h_minmax, S.d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
+    gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
+    if (int r = extract_band_raw_impl(C, d_svl_scratch, 0.f, 0.f, S.d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+                                      nullptr, 0, nullptr, nullptr, S.h_totals))
+        return r;
+    GCB_CHECK(C, cudaEventRecord(S.job_done, C->stream));
+    S.busy = true;
+    return 0;
+}
+int gcb_svl_lattice_host_wait(gcb_ctx* ctx, int slot, unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out) {
+    CTX(ctx);
+    if (slot < 0 || slot > 1) return fail_msg(C, "svl_lattice_host_wait: slot must be 0 or 1");
+    Ctx::Slot& S = C->slot[slot];
+    if (!S.busy) return fail_msg(C, "svl_lattice_host_wait: no job in this slot");
+    GCB_CHECK(C, cudaEventSynchronize(S.job_done));
+    S.busy = false;
+    if (activeVoxels) *activeVoxels = S.h_totals[0];
+    if (totalVerts) *totalVerts = S.h_totals[0] ? S.h_totals[1] : 0;
+    if (minmax_out) { minmax_out[0] = S.h_minmax[0]; minmax_out[1] = S.h_minmax[1]; }
+    return 0;
 }
 
 } // extern "C"

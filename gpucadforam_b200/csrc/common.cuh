@@ -50,6 +50,7 @@ struct McArgs {
     TriangleMetadata* meta;  // region + show_region: one record per triangle
     const float4* disp;    // topo displaced positions
     float na, nb;          // M_BAND_RAW: k = (f - na) / (nb - na)
+    const float* d_ab;     // M_BAND_RAW: {na, nb} in device memory (overrides na / nb when non-null)
     uint32_t gz0, gnz;     // global z offset of local point layer 0, global number of point layers
     float4* pos;
     float4* norm;
@@ -104,6 +105,16 @@ struct Ctx {
     cudaStream_t aux_stream = nullptr;   // second compute stream of the slab-overlapped host path (tail of slab k overlaps head of k+1)
     cudaEvent_t aux_ev[2] = {};
     cudaEvent_t copy_ev[kBatches] = {};
+    // two-deep job pipeline of the host-input entry point (gcb_svl_lattice_host_submit / _wait): per slot the pinned result
+    // words, the device min/max pair of the job's field, and an event marking the end of the job's last reader of the
+    // caller's control-grid scratch
+    struct Slot {
+        unsigned long long* h_totals = nullptr;  // pinned: {active, vertices}
+        float* h_minmax = nullptr;               // pinned: {min, max}
+        float* d_minmax = nullptr;               // device: 2 words raw (ordered-int) + 2 floats decoded
+        cudaEvent_t field_done = nullptr, job_done = nullptr;
+        bool busy = false;
+    } slot[2];
 };
 
 int fail(Ctx* c, const char* what, cudaError_t e);
@@ -115,7 +126,8 @@ int fail_msg(Ctx* c, const std::string& msg);
     } while (0)
 
 // ---- launchers implemented in the .cu files ----
-int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts);
+// h_totals_async != null: enqueue only (kernel + D2H of {active, vertices} into that pinned slot), no synchronisation
+int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts, unsigned long long* h_totals_async = nullptr);
 void host_tables(unsigned int* tri, unsigned int* nverts);
 int upload_tables_legacy(Ctx* c);
 

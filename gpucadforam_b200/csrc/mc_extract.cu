@@ -244,7 +244,7 @@ __device__ __forceinline__ float t_analysis(float iso, float f0, float f1, float
 // bit for every n whose remainder cannot underflow; tiny/zero numerators, tiny/huge quotients and inf/nan take the IEEE
 // division.  Checked exhaustively (all 2^32 numerators for 118 divisors incl. all-ones mantissas): tools/div_check.cu,
 // profiles/r01_div_check.txt.
-struct UniformDiv { float d, y; bool ok; };
+struct UniformDiv { float d, y; bool ok; float a; };  // a: the offset subtracted before the division (M_BAND_RAW: the field minimum)
 __device__ __forceinline__ UniformDiv make_uniform_div(float d) {
     UniformDiv u;
     u.d = d;
@@ -285,7 +285,7 @@ __device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& n
         val = raw;  // k `vol_one`
     } else if (MODE == M_BAND_RAW) {
         // device_bufferfour (Gratings.cu:1089-1134) fused; domain faces use GLOBAL coordinates
-        float k = div_by_uniform(__fsub_rn(raw, A.na), nd);
+        float k = div_by_uniform(__fsub_rn(raw, nd.a), nd);
         float m;
         if (row_face || x == 0 || x == A.nx - 1) { m = 0.0f; k = 0.0f; }
         else m = ((k >= A.iso1) && (k <= A.iso2)) ? 1.0f : 0.0f;
@@ -532,7 +532,12 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
 
     uint32_t parity = 0;
     const uint32_t slice_pts = A.nx * A.ny;
-    const UniformDiv nd = make_uniform_div(__fsub_rn(A.nb, A.na));  // M_BAND_RAW normalisation range
+    // M_BAND_RAW normalisation range {min, max}: kernel arguments, or read from device memory where the field kernel's reduction
+    // left it (no host round trip between field and extraction)
+    float na = A.na, nb = A.nb;
+    if (MODE == M_BAND_RAW && A.d_ab) { na = __ldg(A.d_ab); nb = __ldg(A.d_ab + 1); }
+    UniformDiv nd = make_uniform_div(__fsub_rn(nb, na));
+    nd.a = na;
     const uint32_t ppr = A.ppr, cpr = A.cpr;
     const uint32_t plane_words = 2u * R1 * ppr * 4u;  // words per bit plane
     constexpr bool tma = TMA;
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
                 if (x < A.nx) {
                     const float4 v4 = *reinterpret_cast<const float4*>(sv + x);
                     if (MODE == M_BAND_RAW) {
-                        float nn[4] = {__fsub_rn(v4.x, A.na), __fsub_rn(v4.y, A.na), __fsub_rn(v4.z, A.na), __fsub_rn(v4.w, A.na)}, kk[4];
+                        float nn[4] = {__fsub_rn(v4.x, na), __fsub_rn(v4.y, na), __fsub_rn(v4.z, na), __fsub_rn(v4.w, na)}, kk[4];
                         bool fast = nd.ok;
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {  // div_by_uniform, the four range checks folded into one branch
@@ -944,8 +949,12 @@ static int occupancy(size_t smem, size_t attr_smem, bool tma) {
     return tma ? occupancy_one<MODE, true>(smem, attr_smem) : occupancy_one<MODE, false>(smem, attr_smem);
 }
 
-int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts) {
-    if (a.nx < 2 || a.ny < 2 || a.nz < 2) { *active = 0; *verts = 0; return 0; }
+int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts, unsigned long long* h_totals_async) {
+    if (a.nx < 2 || a.ny < 2 || a.nz < 2) {
+        if (h_totals_async) { h_totals_async[0] = 0; h_totals_async[1] = 0; }
+        else { *active = 0; *verts = 0; }
+        return 0;
+    }
     a.cx = a.nx - 1; a.cy = a.ny - 1; a.cz = a.nz - 1;
     // tile height: staged rows must fit in shared memory
     if (a.nx > 65535u) return fail_msg(c, "grid row too wide (nx > 65535)");
@@ -1053,7 +1062,9 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
     if (e != cudaSuccess) return fail(c, "mc_fused_kernel launch", e);
     c->launches++;
     if (c->timing) { cudaEventRecord(c->ev[1], c->stream); c->extract_timed = true; }
-    GCB_CHECK(c, cudaMemcpyAsync(c->h_totals, a.totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long* dst = h_totals_async ? h_totals_async : c->h_totals;
+    GCB_CHECK(c, cudaMemcpyAsync(dst, a.totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    if (h_totals_async) return 0;  // enqueue only: the caller synchronises and reads {active, vertices} from its pinned slot
     GCB_CHECK(c, cudaStreamSynchronize(c->stream));
     *active = c->h_totals[0];
     *verts = c->h_totals[0] ? c->h_totals[1] : 0;  // early-out of Isosurface.cu:83-87

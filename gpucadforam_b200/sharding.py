@@ -49,6 +49,16 @@ def allreduce_minmax(dist, mm):
     return -float(t[0]), float(t[1])
 
 
+def allreduce_minmax_device(dist, mm):
+    """Same reduction, result left on the device: a 2-element tensor {min, max} the extraction kernel reads in place
+    (gcb_extract_band_raw_dev), so that no host synchronisation sits between the field and the extraction."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return mm
+    t = torch.stack([-mm[0], mm[1]])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return torch.stack([-t[0], t[1]])
+
+
 def gather_counts(dist, active, verts, device="cpu"):
     """All-gather of per-rank {active, verts}; returns (per-rank list, exclusive vertex offsets, exclusive active offsets, totals)."""
     mine = torch.tensor([int(active), int(verts)], dtype=torch.int64, device=device)

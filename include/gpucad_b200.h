@@ -269,6 +269,13 @@ int gcb_extract_band_raw(gcb_ctx* ctx, const float* d_field, float a, float b, f
     unsigned long long maxVerts, unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels,
     unsigned long long* totalVerts);
 
+/* Same, with the normalisation range read from DEVICE memory (d_minmax: {min, max}, e.g. the pair gcb_svl_field left there, or the
+ * result of an NCCL all-reduce over ranks): no host round trip between the field and the extraction. */
+int gcb_extract_band_raw_dev(gcb_ctx* ctx, const float* d_field, const float* d_minmax, float isoValue, float isovalue1, float isovalue2,
+    gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
+    unsigned long long maxVerts, unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels,
+    unsigned long long* totalVerts);
+
 /* Whole config-3/4 pipeline on one rank, device-resident inputs: gcb_svl_field -> (a,b given by
  * caller or computed locally when use_local_minmax != 0) -> gcb_extract_band_raw. */
 int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int nh, const float* coef_host, int cx, int cy, int cz,
@@ -283,6 +290,18 @@ int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch,
     int cx, int cy, int cz, int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1,
     float isovalue2, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
     unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out);
+
+/* Two-deep job pipeline of gcb_svl_lattice_host: _submit only enqueues (H2D copies on the library's copy stream, field,
+ * reduction, extraction and the read-back of the counts on the context's stream) and returns; _wait blocks until that slot's job
+ * is complete and hands back its counts.  With jobs alternating between slot 0 and slot 1, the control grids of job i+1 cross
+ * PCIe while job i computes.  Each slot needs its OWN d_phi_scratch (it is written while the other slot's job reads its own);
+ * d_svl_scratch and pos / norm may be shared between the slots (their uses are ordered on the context's stream -- a shared mesh
+ * buffer holds the mesh of the LAST submitted job).  h_phi must stay valid and unchanged until _wait returns.  Results equal
+ * the blocking call's bit for bit. */
+int gcb_svl_lattice_host_submit(gcb_ctx* ctx, int slot, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host,
+    int cx, int cy, int cz, int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2,
+    gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts);
+int gcb_svl_lattice_host_wait(gcb_ctx* ctx, int slot, unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out);
 
 #ifdef __cplusplus
 }

@@ -1535,3 +1535,71 @@ def test_normalise_three_and_period_to_phase_chain(ctx):
         phi2 = torch.zeros(n, device="cuda")
         ref.finding_phi(phi2, per2, dims, (1, -2, 1), d)
         assert_bits_equal(phi, phi2, "finding_phi on the normalised period field")
+
+
+# ------------------------------------------------------------------ device-resident min/max and the two-deep job pipeline
+def test_extract_band_raw_dev_equals_host_range(ctx):
+    n = 48
+    f = torch.zeros(n * n * n, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(f, n, n, n, n * n * n, 3)
+    dims = (n, n, n)
+    lo, hi = g.minmax(ctx, f)
+    mv = max_verts_for(dims)
+    m1, m2 = g.MeshBuffers(mv), g.MeshBuffers(mv)
+    a1, t1 = g.extract_band_raw(ctx, f, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, (0.5, 0.5, 0.5), (1, 2, 3), m1.pos, m1.norm, mv)
+    dmm = torch.tensor([lo, hi], dtype=torch.float32, device="cuda")
+    a2, t2 = g.extract_band_raw_dev(ctx, f, dmm, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, (0.5, 0.5, 0.5), (1, 2, 3), m2.pos, m2.norm, mv)
+    assert (a1, t1) == (a2, t2) and t1 > 0
+    assert_bits_equal(m1.pos[:t1], m2.pos[:t1], "band_raw_dev pos")
+    assert_bits_equal(m1.norm[:t1], m2.norm[:t1], "band_raw_dev norm")
+    a3, t3 = g.extract_band_raw_dev(ctx, f, dmm, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, (0.5, 0.5, 0.5), (1, 2, 3), None, None, 0, count_only=True)
+    assert (a3, t3) == (a1, t1)
+
+
+@pytest.mark.parametrize("which", ["exact", "fast"])
+def test_job_pipeline_submit_wait_equals_blocking_calls(ctx, fctx, which):
+    """gcb_svl_lattice_host_submit / _wait: jobs alternating between the two slots (own control-grid scratch per slot, shared field
+    scratch) return the blocking call's counts, min/max and mesh, whatever the overlap between one job's copies and the other's kernels."""
+    c = ctx if which == "exact" else fctx
+    cfg = cases.SVL4
+    phi, coef = cases.svl_inputs(cfg)
+    dims = cfg["fdims"]
+    fx, fy, fz = dims
+    mv = max_verts_for(dims)
+    jobs = []
+    for j in range(4):   # four different jobs: phases shifted, coefficients scaled
+        p = (phi + np.float32(0.37 * j)).astype(np.float32)
+        cf = [(a * (1.0 + 0.1 * j), b * (1.0 - 0.05 * j)) for a, b in coef]
+        jobs.append((torch.from_numpy(p).pin_memory(), cf))
+    svl = torch.zeros(fx * fy * fz, device="cuda")
+    scratch = [torch.zeros(phi.shape, device="cuda"), torch.zeros(phi.shape, device="cuda")]
+    want = []
+    for hp, cf in jobs:
+        mesh = g.MeshBuffers(mv)
+        a, t, mm = g.svl_lattice_host(c, hp, scratch[0], svl, cf, cfg["cdims"], dims, cfg["d"], cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, cfg["d"], (0, 0, 0),
+                                      mesh.pos, mesh.norm, mv)
+        assert t > 0
+        want.append((a, t, mm, mesh))
+    meshes = [g.MeshBuffers(mv) for _ in jobs]   # own mesh per job so that every result can be compared afterwards
+    def submit(j):
+        hp, cf = jobs[j]
+        g.svl_lattice_host_submit(c, j % 2, hp, scratch[j % 2], svl, cf, cfg["cdims"], dims, cfg["d"], cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, cfg["d"], (0, 0, 0),
+                                  meshes[j].pos, meshes[j].norm, mv)
+    got = []
+    submit(0)
+    for j in range(1, len(jobs)):
+        submit(j)
+        got.append(g.svl_lattice_host_wait(c, (j - 1) % 2))
+    got.append(g.svl_lattice_host_wait(c, (len(jobs) - 1) % 2))
+    for j, ((a, t, mm, mesh), (a2, t2, mm2)) in enumerate(zip(want, got)):
+        assert (a, t, mm) == (a2, t2, mm2), "job %d" % j
+        assert_bits_equal(mesh.pos[:t], meshes[j].pos[:t], "pipelined job %d pos" % j)
+        assert_bits_equal(mesh.norm[:t], meshes[j].norm[:t], "pipelined job %d norm" % j)
+    assert len({w[1] for w in want}) > 1   # the jobs really differ
+    # protocol errors: waiting on an empty slot, submitting into a busy one
+    with pytest.raises(RuntimeError):
+        g.svl_lattice_host_wait(c, 0)
+    submit(0)
+    with pytest.raises(RuntimeError):
+        submit(0)
+    g.svl_lattice_host_wait(c, 0)

@@ -51,6 +51,8 @@ def _worker(rank, world, port, out):
     slab = np.ascontiguousarray(f[z0:z1 + 1])
     lo_l, hi_l = orc.minmax(slab)
     lo, hi = sharding.allreduce_minmax(dist, torch.tensor([lo_l, hi_l], dtype=torch.float32))
+    dev_pair = sharding.allreduce_minmax_device(dist, torch.tensor([lo_l, hi_l], dtype=torch.float32))   # the sync-free variant bench.py uses
+    assert (float(dev_pair[0]), float(dev_pair[1])) == (lo, hi)
     r = _band_raw_slab(slab, z0, N, lo, hi)
     per_rank, voff, aoff, totals = sharding.gather_counts(dist, r["active"], r["total"])
     np.savez(os.path.join(out, "rank%d.npz" % rank), pos=r["pos"][:r["total"]], norm=r["norm"][:r["total"]],
