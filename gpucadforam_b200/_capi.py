@@ -99,10 +99,26 @@ SIGNATURES = {
     "gcb_minmax": (I, [P, P, C.c_size_t, PF, PF]),
     "gcb_extract_band_raw": (I, [P, P, F, F, F, F, F, Uint3, Slab, Float3, Float3, P, P, ULL, P, I, PULL, PULL]),
     "gcb_extract_band_raw_dev": (I, [P, P, P, F, F, F, Uint3, Slab, Float3, Float3, P, P, ULL, P, I, PULL, PULL]),
+    "gcb_band_lattice_from_raw": (I, [P, P, Uint3, F, F, F, Float3, Float3, P, P, ULL, P, PULL, PULL, PF]),
+    "gcb_tpms_lattice": (I, [P, P, U, Uint3, F, F, F, Float3, Float3, P, P, ULL, P, PULL, PULL, PF]),
+    "gcb_density_surface": (I, [P, P, I, I, I, P, I, I, I, F, F, F, F, Float3, Float3, P, P, ULL, P, PULL, PULL]),
     "gcb_svl_lattice_host_submit": (I, [P, I, P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL]),
     "gcb_svl_lattice_host_wait": (I, [P, I, PULL, PULL, PF]),
     "gcb_svl_lattice": (I, [P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),
     "gcb_svl_lattice_host": (I, [P, P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),
+    "gcb_multi_create": (I, [C.POINTER(P), I, C.POINTER(I)]),
+    "gcb_multi_destroy": (I, [P]),
+    "gcb_multi_size": (I, [P]),
+    "gcb_multi_ctx": (P, [P, I]),
+    "gcb_multi_device": (I, [P, I]),
+    "gcb_multi_last_error": (C.c_char_p, [P]),
+    "gcb_multi_last_ms": (F, [P]),
+    "gcb_slab_bounds": (I, [U, I, I, U, PU, PU]),
+    "gcb_control_slab": (I, [U, U, I, I, C.POINTER(I), C.POINTER(I)]),
+    "gcb_multi_svl_lattice": (I, [P, C.POINTER(P), C.POINTER(P), I, PF, I, I, C.POINTER(I), C.POINTER(I), I, I, U, F, F, F, F, F, F, Float3, Float3,
+                                  C.POINTER(P), C.POINTER(P), PULL, I, PULL, PULL, PULL, PF]),
+    "gcb_multi_computeIsosurface_2": (I, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P), Uint3, Float3, Float3, F, F, C.POINTER(P), C.POINTER(P), PULL, C.POINTER(P),
+                                          PULL, PULL, PULL, PULL]),
 }
 
 GCB_OPT_FILL_STAGE_ARRAYS = 1

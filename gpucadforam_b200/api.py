@@ -390,6 +390,32 @@ def extract_band_raw_dev(ctx, d_field, d_minmax, isoValue, isovalue1, isovalue2,
     return act.value, tot.value
 
 
+def band_lattice_from_raw(ctx, d_raw_field, gridSize, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos, norm, maxVerts, comp=None):
+    """normalise_buffer -> normalise_four -> latticeone on a raw field, fused (gcb_band_lattice_from_raw): (active, verts, (a, b, a2, b2))."""
+    act, tot = C.c_ulonglong(0), C.c_ulonglong(0)
+    rg = (C.c_float * 4)()
+    ctx.check(lib().gcb_band_lattice_from_raw(ctx._h, _ptr(d_raw_field), _u3(gridSize), isoValue, isovalue1, isovalue2, _f3(voxelSize), _f3(gridcenter), _ptr(pos),
+                                              _ptr(norm), maxVerts, _ptr(comp), C.byref(act), C.byref(tot), rg))
+    return act.value, tot.value, tuple(rg)
+
+
+def tpms_lattice(ctx, d_field_scratch, lattice_type_index, gridSize, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos, norm, maxVerts, comp=None):
+    """BASELINE config 1 in one call (gcb_tpms_lattice): create_lattice + both normalisations + latticeone."""
+    act, tot = C.c_ulonglong(0), C.c_ulonglong(0)
+    rg = (C.c_float * 4)()
+    ctx.check(lib().gcb_tpms_lattice(ctx._h, _ptr(d_field_scratch), int(lattice_type_index), _u3(gridSize), isoValue, isovalue1, isovalue2, _f3(voxelSize),
+                                     _f3(gridcenter), _ptr(pos), _ptr(norm), maxVerts, _ptr(comp), C.byref(act), C.byref(tot), rg))
+    return act.value, tot.value, tuple(rg)
+
+
+def density_surface(ctx, d_coarse, cdims, d_density_fine, fdims, d, isoValue, voxelSize, gridcenter, pos, norm, maxVerts, comp=None):
+    """BASELINE config 5 in one call (gcb_density_surface): 2x upsample of the coarse density + computeIsosurface_2 semantics."""
+    act, tot = C.c_ulonglong(0), C.c_ulonglong(0)
+    ctx.check(lib().gcb_density_surface(ctx._h, _ptr(d_coarse), cdims[0], cdims[1], cdims[2], _ptr(d_density_fine), fdims[0], fdims[1], fdims[2], d[0], d[1], d[2],
+                                        isoValue, _f3(voxelSize), _f3(gridcenter), _ptr(pos), _ptr(norm), maxVerts, _ptr(comp), C.byref(act), C.byref(tot)))
+    return act.value, tot.value
+
+
 def svl_lattice_host_submit(ctx, slot, h_phi, d_phi_scratch, d_svl_scratch, coef, cdims, fdims, d, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos,
                             norm, maxVerts):
     """Enqueue one host-input job in pipeline slot 0 / 1 (gcb_svl_lattice_host_submit); returns immediately."""

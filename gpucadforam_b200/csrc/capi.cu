@@ -19,7 +19,6 @@ int fail_msg(Ctx* c, const std::string& msg) {
     return 1;
 }
 
-static inline float3 f3(gcb_float3 v) { return make_float3(v.x, v.y, v.z); }
 
 // Legacy extraction: optional byte-granular memset of Isosurface.cu:120-121, then the fused kernel.
 static int run_legacy(Ctx* c, McArgs& a, void* pos, void* norm, unsigned maxVerts, unsigned* d_verts, unsigned* d_vertsScan, unsigned* d_occ,
@@ -50,14 +49,6 @@ static int run_legacy(Ctx* c, McArgs& a, void* pos, void* norm, unsigned maxVert
     return 0;
 }
 
-static void base_args(McArgs& a, int mode, gcb_uint3 gridSize, gcb_float3 voxelSize, gcb_float3 gridcenter, float iso) {
-    memset(&a, 0, sizeof a);
-    a.mode = mode;
-    a.nx = gridSize.x; a.ny = gridSize.y; a.nz = gridSize.z;
-    a.voxel = f3(voxelSize);
-    a.center = f3(gridcenter);
-    a.iso = iso;
-}
 
 } // namespace gcb
 
@@ -93,7 +84,7 @@ int gcb_destroy(gcb_ctx* ctx) {
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};  // leave the caller's current device as it was
     cudaSetDevice(C->device);
     cudaFree(C->d_status); cudaFree(C->d_tile_counter); cudaFree(C->d_totals); cudaFreeHost(C->h_totals);
-    cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef);
+    cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef); cudaFree(C->d_range4);
     cudaFree(C->d_tri); cudaFree(C->d_nverts);
     if (C->copy_stream) { cudaStreamDestroy(C->copy_stream); for (int i = 0; i < Ctx::kBatches; ++i) cudaEventDestroy(C->copy_ev[i]); }
     if (C->aux_stream) { cudaStreamDestroy(C->aux_stream); cudaEventDestroy(C->aux_ev[0]); cudaEventDestroy(C->aux_ev[1]); }
@@ -496,7 +487,7 @@ int gcb_svl_field(gcb_ctx* ctx, float* d_svl, const float* d_phi, int nh, const 
     return 0;
 }
 
-static int extract_band_raw_impl(Ctx* C, const float* d_field, float a, float b, const float* d_ab, float isoValue, float isovalue1, float isovalue2,
+int gcb_internal_extract_band_raw(Ctx* C, const float* d_field, float a, float b, const float* d_ab, float isoValue, float isovalue1, float isovalue2,
                                  gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
                                  unsigned long long maxVerts, unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels,
                                  unsigned long long* totalVerts, unsigned long long* h_totals_async) {
@@ -524,7 +515,7 @@ int gcb_extract_band_raw(gcb_ctx* ctx, const float* d_field, float a, float b, f
                          gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
                          unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels, unsigned long long* totalVerts) {
     CTX(ctx);
-    return extract_band_raw_impl(C, d_field, a, b, nullptr, isoValue, isovalue1, isovalue2, gridSizeLocal, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+    return gcb_internal_extract_band_raw(C, d_field, a, b, nullptr, isoValue, isovalue1, isovalue2, gridSizeLocal, slab, voxelSize, gridcenter, pos, norm, maxVerts,
                                  d_compVoxelArray, count_only, activeVoxels, totalVerts, nullptr);
 }
 int gcb_extract_band_raw_dev(gcb_ctx* ctx, const float* d_field, const float* d_minmax, float isoValue, float isovalue1, float isovalue2,
@@ -533,7 +524,7 @@ int gcb_extract_band_raw_dev(gcb_ctx* ctx, const float* d_field, const float* d_
                              unsigned long long* totalVerts) {
     CTX(ctx);
     if (!d_minmax) return fail_msg(C, "extract_band_raw_dev: null min/max pointer");
-    return extract_band_raw_impl(C, d_field, 0.f, 0.f, d_minmax, isoValue, isovalue1, isovalue2, gridSizeLocal, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+    return gcb_internal_extract_band_raw(C, d_field, 0.f, 0.f, d_minmax, isoValue, isovalue1, isovalue2, gridSizeLocal, slab, voxelSize, gridcenter, pos, norm, maxVerts,
                                  d_compVoxelArray, count_only, activeVoxels, totalVerts, nullptr);
 }
 
@@ -546,7 +537,7 @@ int gcb_svl_lattice(gcb_ctx* ctx, float* d_svl_scratch, const float* d_phi, int 
     if (int r = gcb_svl_field(ctx, d_svl_scratch, d_phi, nh, coef_host, cx, cy, cz, 0, NX2, NY2, NZ2, slab, dx, dy, dz, 0, C->d_minmax)) return r;
     if (minmax_out) GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
     gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
-    if (int r = extract_band_raw_impl(C, d_svl_scratch, 0.f, 0.f, C->d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+    if (int r = gcb_internal_extract_band_raw(C, d_svl_scratch, 0.f, 0.f, C->d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
                                       nullptr, 0, activeVoxels, totalVerts, nullptr))
         return r;
     if (minmax_out) { minmax_out[0] = C->h_minmax[0]; minmax_out[1] = C->h_minmax[1]; }
@@ -665,10 +656,91 @@ int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch,
         return r;
     if (minmax_out) GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, C->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
     gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
-    if (int r = extract_band_raw_impl(C, d_svl_scratch, 0.f, 0.f, C->d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+    if (int r = gcb_internal_extract_band_raw(C, d_svl_scratch, 0.f, 0.f, C->d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
                                       nullptr, 0, activeVoxels, totalVerts, nullptr))
         return r;
     if (minmax_out) { minmax_out[0] = C->h_minmax[0]; minmax_out[1] = C->h_minmax[1]; }
+    return 0;
+}
+
+// ------------------------------------------------------------------ fused unit-lattice path (BASELINE config 1)
+// Multitopo::display_unit_lattice (main.cu:4113-4132): create_lattice -> GPU_buffer_normalise_buffer -> GPU_buffer_normalise_four ->
+// computeIsosurface_latticeone, four blocking calls with two full min/max passes and three intermediate fields.  Here: the raw
+// field once (with its TRUE range reduced on the fly), four derived range numbers in device memory, and the band-raw extraction
+// applying both normalisations to the staged values -- one synchronisation, for the counts.
+static int band_lattice_two_stage(Ctx* C, const float* d_field, gcb_uint3 gridSize, float isoValue, float isovalue1, float isovalue2, gcb_float3 voxelSize,
+                                  gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned int* d_comp,
+                                  unsigned long long* activeVoxels, unsigned long long* totalVerts, float* ranges_out) {
+    unsigned* tmm = reinterpret_cast<unsigned*>(C->d_range4);
+    float* ab4 = C->d_range4 + 2;
+    if (int r = k_two_stage_range(C, tmm, ab4)) return r;
+    if (ranges_out) GCB_CHECK(C, cudaMemcpyAsync(C->h_minmax, ab4, 4 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
+    McArgs A;
+    base_args(A, M_BAND_RAW, gridSize, voxelSize, gridcenter, isoValue);
+    A.iso1 = isovalue1; A.iso2 = isovalue2;
+    A.f0 = d_field;
+    A.d_ab = ab4;
+    A.two_stage = 1;
+    A.gz0 = 0; A.gnz = gridSize.z;
+    A.pos = (float4*)pos; A.norm = (float4*)norm;
+    A.max_verts = maxVerts;
+    A.comp = d_comp;
+    unsigned long long act = 0, verts = 0;
+    if (int r = launch_extract(C, A, &act, &verts)) return r;
+    if (activeVoxels) *activeVoxels = act;
+    if (totalVerts) *totalVerts = verts;
+    if (ranges_out) for (int i = 0; i < 4; ++i) ranges_out[i] = C->h_minmax[i];
+    return 0;
+}
+static int range4_init(Ctx* C) {
+    if (!C->d_range4) GCB_CHECK(C, cudaMalloc(&C->d_range4, 32));
+    return 0;
+}
+int gcb_band_lattice_from_raw(gcb_ctx* ctx, const float* d_raw_field, gcb_uint3 gridSize, float isoValue, float isovalue1, float isovalue2, gcb_float3 voxelSize,
+                              gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned int* d_compVoxelArray,
+                              unsigned long long* activeVoxels, unsigned long long* totalVerts, float* ranges_out) {
+    CTX(ctx);
+    if (!d_raw_field) return fail_msg(C, "band_lattice_from_raw: null field");
+    if (int r = range4_init(C)) return r;
+    if (int r = k_true_minmax(C, d_raw_field, (size_t)gridSize.x * gridSize.y * gridSize.z, reinterpret_cast<unsigned*>(C->d_range4))) return r;
+    return band_lattice_two_stage(C, d_raw_field, gridSize, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos, norm, maxVerts, d_compVoxelArray, activeVoxels,
+                                  totalVerts, ranges_out);
+}
+int gcb_tpms_lattice(gcb_ctx* ctx, float* d_field_scratch, unsigned int lattice_type_index, gcb_uint3 gridSize, float isoValue, float isovalue1, float isovalue2,
+                     gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned int* d_compVoxelArray,
+                     unsigned long long* activeVoxels, unsigned long long* totalVerts, float* ranges_out) {
+    CTX(ctx);
+    if (!d_field_scratch) return fail_msg(C, "tpms_lattice: null field scratch");
+    if (lattice_type_index > 5u) return fail_msg(C, "tpms_lattice: lattice type must be 0..5");
+    if (int r = range4_init(C)) return r;
+    if (int r = k_create_lattice(C, d_field_scratch, gridSize.x, gridSize.y, gridSize.z, lattice_type_index, reinterpret_cast<unsigned*>(C->d_range4))) return r;
+    return band_lattice_two_stage(C, d_field_scratch, gridSize, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos, norm, maxVerts, d_compVoxelArray,
+                                  activeVoxels, totalVerts, ranges_out);
+}
+
+// ------------------------------------------------------------------ fused density-surface path (BASELINE config 5)
+// Multitopo::toprun (main.cu:3060-3109): copytotexture + updateTexture + refine (2x trilinear upsample of the coarse density) +
+// computeIsosurface_2 with an all-zero vol_topo / d_result.  Here the upsample reads the caller's coarse grid where it lies (no
+// staging copies) and the extraction skips the 16-byte grid_points stream and the colour field it would read as zeros.
+int gcb_density_surface(gcb_ctx* ctx, const float* d_coarse, int cx, int cy, int cz, float* d_density_fine, int NX2, int NY2, int NZ2, float dx, float dy, float dz,
+                        float isoValue, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
+                        unsigned int* d_compVoxelArray, unsigned long long* activeVoxels, unsigned long long* totalVerts) {
+    CTX(ctx);
+    if (!d_coarse || !d_density_fine) return fail_msg(C, "density_surface: null density buffer");
+    if (int r = k_refine(C, d_coarse, cx, cy, cz, d_density_fine, NX2, NY2, NZ2, dx, dy, dz)) return r;
+    McArgs A;
+    gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
+    base_args(A, M_TOPO, gs, voxelSize, gridcenter, isoValue);
+    A.iso1 = 0.f;           // isovalue1 of the reference call; vol_topo.val == 0 never passes `val < 0`
+    A.f0 = d_density_fine;
+    A.gz0 = 0; A.gnz = gs.z;
+    A.pos = (float4*)pos; A.norm = (float4*)norm;
+    A.max_verts = maxVerts;
+    A.comp = d_compVoxelArray;
+    unsigned long long act = 0, verts = 0;
+    if (int r = launch_extract(C, A, &act, &verts)) return r;
+    if (activeVoxels) *activeVoxels = act;
+    if (totalVerts) *totalVerts = verts;
     return 0;
 }
 
@@ -699,7 +771,7 @@ int gcb_svl_lattice_host_submit(gcb_ctx* ctx, int slot, const float* h_phi, floa
     GCB_CHECK(C, cudaEventRecord(S.field_done, C->stream));
     GCB_CHECK(C, cudaMemcpyAsync(S.h_minmax, S.d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
     gcb_uint3 gs{(unsigned)NX2, (unsigned)NY2, (unsigned)NZ2};
-    if (int r = extract_band_raw_impl(C, d_svl_scratch, 0.f, 0.f, S.d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
+    if (int r = gcb_internal_extract_band_raw(C, d_svl_scratch, 0.f, 0.f, S.d_minmax, isoValue, isovalue1, isovalue2, gs, slab, voxelSize, gridcenter, pos, norm, maxVerts,
                                       nullptr, 0, nullptr, nullptr, S.h_totals))
         return r;
     GCB_CHECK(C, cudaEventRecord(S.job_done, C->stream));

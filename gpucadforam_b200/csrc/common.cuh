@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -49,8 +50,13 @@ struct McArgs {
     const GridPoint* gp2;  // vol_topo (region)
     TriangleMetadata* meta;  // region + show_region: one record per triangle
     const float4* disp;    // topo displaced positions
+    const float* f0_top;   // stored-field sharding: local point layer nz - 1 of f0 / f1 / gp when it is held by the upper neighbour
+    const float* f1_top;   //   (pointer to the start of that layer; null = the layer is part of the local arrays)
+    const GridPoint* gp_top;
+    unsigned long long top_begin;  // (nz - 1) * nx * ny
     float na, nb;          // M_BAND_RAW: k = (f - na) / (nb - na)
     const float* d_ab;     // M_BAND_RAW: {na, nb} in device memory (overrides na / nb when non-null)
+    int two_stage;         // M_BAND_RAW with d_ab: d_ab[2..3] = {a2, b2}, second normalisation k <- (k - a2) / (b2 - a2)
     uint32_t gz0, gnz;     // global z offset of local point layer 0, global number of point layers
     float4* pos;
     float4* norm;
@@ -87,6 +93,7 @@ struct Ctx {
     unsigned long long* h_totals = nullptr;  // pinned
     // reductions
     float* d_minmax = nullptr;               // 2 floats (ordered-int encoded during reduction)
+    float* d_range4 = nullptr;               // fused normalise-twice paths: 2 raw words (true min / max) + {a, b, a2, b2}
     float* h_minmax = nullptr;               // pinned
     // control grid ("texture")
     float* d_tex = nullptr;
@@ -125,6 +132,16 @@ int fail_msg(Ctx* c, const std::string& msg);
         if (e_ != cudaSuccess) return gcb::fail((c), #call, e_);    \
     } while (0)
 
+static inline float3 f3(gcb_float3 v) { return make_float3(v.x, v.y, v.z); }
+inline void base_args(McArgs& a, int mode, gcb_uint3 gridSize, gcb_float3 voxelSize, gcb_float3 gridcenter, float iso) {
+    memset(&a, 0, sizeof a);
+    a.mode = mode;
+    a.nx = gridSize.x; a.ny = gridSize.y; a.nz = gridSize.z;
+    a.voxel = f3(voxelSize);
+    a.center = f3(gridcenter);
+    a.iso = iso;
+}
+
 // ---- launchers implemented in the .cu files ----
 // h_totals_async != null: enqueue only (kernel + D2H of {active, vertices} into that pinned slot), no synchronisation
 int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long long* verts, unsigned long long* h_totals_async = nullptr);
@@ -132,7 +149,9 @@ void host_tables(unsigned int* tri, unsigned int* nverts);
 int upload_tables_legacy(Ctx* c);
 
 // fields.cu
-int k_create_lattice(Ctx* c, float* out, unsigned nx, unsigned ny, unsigned nz, unsigned type);
+int k_create_lattice(Ctx* c, float* out, unsigned nx, unsigned ny, unsigned nz, unsigned type, unsigned* d_true_minmax = nullptr);
+int k_true_minmax(Ctx* c, const float* in, size_t n, unsigned* d_true_minmax);
+int k_two_stage_range(Ctx* c, const unsigned* d_true_minmax, float* d_ab4);
 int k_unit_spectrum(Ctx* c, const float* f, int nx, int ny, int nz, int range, float2* out);
 int k_sphere(Ctx* c, float* out, float3 center, float radius, float thickness, int nx, int ny, int nz, float dx, float dy, float dz, bool shell);
 int k_line(Ctx* c, float* out, float3 center, float3 axis, float radius, float tr, float ta, int nx, int ny, int nz, float dx, float dy, float dz, bool disc);
@@ -199,6 +218,12 @@ __device__ __forceinline__ void point_xyz(size_t i, const Grid3& g, int& x, int&
         x = (int)(i % g.nx);
     }
 }
+
+// capi.cu: band-raw extraction with all knobs; h_totals_async != null = enqueue only (multi.cu)
+extern "C" int gcb_internal_extract_band_raw(Ctx* C, const float* d_field, float a, float b, const float* d_ab, float isoValue, float isovalue1, float isovalue2,
+                                             gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
+                                             unsigned long long maxVerts, unsigned int* d_compVoxelArray, int count_only, unsigned long long* activeVoxels,
+                                             unsigned long long* totalVerts, unsigned long long* h_totals_async);
 
 // phase_solve.cu
 int k_finding_phi(Ctx* c, float* phi_all, const float* period, const int* ijk_host, int nharm, int nx, int ny, int nz, float dx, float dy, float dz, int latticetype,

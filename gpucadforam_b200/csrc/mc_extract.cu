@@ -244,7 +244,11 @@ __device__ __forceinline__ float t_analysis(float iso, float f0, float f1, float
 // bit for every n whose remainder cannot underflow; tiny/zero numerators, tiny/huge quotients and inf/nan take the IEEE
 // division.  Checked exhaustively (all 2^32 numerators for 118 divisors incl. all-ones mantissas): tools/div_check.cu,
 // profiles/r01_div_check.txt.
-struct UniformDiv { float d, y; bool ok; float a; };  // a: the offset subtracted before the division (M_BAND_RAW: the field minimum)
+struct UniformDiv {
+    float d, y; bool ok;
+    float a;                   // the offset subtracted before the division (M_BAND_RAW: the field minimum)
+    bool two; float a2, d2;    // optional second normalisation k <- (k - a2) / d2 (the legacy normalise_buffer + normalise_four sequence)
+};
 __device__ __forceinline__ UniformDiv make_uniform_div(float d) {
     UniformDiv u;
     u.d = d;
@@ -262,18 +266,24 @@ __device__ __forceinline__ float div_by_uniform(float n, const UniformDiv& u) {
     return q2;
 }
 
+// Stored fields under z-slab sharding: a rank may hold only its OWNED point layers, the +z halo layer (local layer nz - 1) then
+// lives in the upper neighbour's memory (`*_top` = start of that layer, a peer-mapped pointer over NVLink or an ordinary one).
+template <class T>
+__device__ __forceinline__ const T* at_point(const T* base, const T* top, size_t gi, size_t top_begin) {
+    return (top && gi >= top_begin) ? top + (gi - top_begin) : base + gi;
+}
 // What one point needs from global memory besides the TMA-staged field: fetched ahead of use (stage_fetch), turned into
 // {value, bits} later (stage_point), so a warp keeps the loads of its next 128 points in flight while it evaluates the current ones.
 template <int MODE>
 __device__ __forceinline__ void stage_fetch(const McArgs& A, size_t gi, float& a, float& b) {
-    if (MODE == M_LATTICE_ONE || MODE == M_LATTICE) a = __ldg(A.f1 + gi);  // mask `vol`
+    if (MODE == M_LATTICE_ONE || MODE == M_LATTICE) a = __ldg(at_point(A.f1, A.f1_top, gi, A.top_begin));  // mask `vol`
     else if (MODE == M_REGION) {
         a = A.gp2 ? (float)A.gp2[gi].val : 0.f;  // sampleVolume_2 :98-108
         b = A.gp ? (float)A.gp[gi].val : 0.f;
-    } else if (MODE == M_TOPO) a = A.gp ? (float)A.gp[gi].val : 0.f;
+    } else if (MODE == M_TOPO) a = A.gp ? (float)at_point(A.gp, A.gp_top, gi, A.top_begin)->val : 0.f;
     else if (MODE == M_CSG) {
-        a = A.gp ? (float)A.gp[gi].val : 0.f;
-        if ((A.flags & (F_FIXED | F_DYNAMIC)) && A.f1) b = __ldg(A.f1 + gi);
+        a = A.gp ? (float)at_point(A.gp, A.gp_top, gi, A.top_begin)->val : 0.f;
+        if ((A.flags & (F_FIXED | F_DYNAMIC)) && A.f1) b = __ldg(at_point(A.f1, A.f1_top, gi, A.top_begin));
     }
 }
 template <int MODE>
@@ -286,6 +296,7 @@ __device__ __forceinline__ void stage_point(const McArgs& A, const UniformDiv& n
     } else if (MODE == M_BAND_RAW) {
         // device_bufferfour (Gratings.cu:1089-1134) fused; domain faces use GLOBAL coordinates
         float k = div_by_uniform(__fsub_rn(raw, nd.a), nd);
+        if (nd.two) k = __fdiv_rn(__fsub_rn(k, nd.a2), nd.d2);
         float m;
         if (row_face || x == 0 || x == A.nx - 1) { m = 0.0f; k = 0.0f; }
         else m = ((k >= A.iso1) && (k <= A.iso2)) ? 1.0f : 0.0f;
@@ -400,7 +411,7 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
             const size_t gb = ((size_t)(z + zb) * A.ny + y + ((cb >> 1) & 1u)) * A.nx + x + (cb & 1u);
             float et = 0.f;
             if (own && A.gp) {
-                const GridPoint g = A.gp[ga];
+                const GridPoint g = *at_point(A.gp, A.gp_top, ga, A.top_begin);
                 const uint32_t ax = edge_axis(e);
                 et = ax == 0 ? g.t_x : ax == 1 ? g.t_y : g.t_z;
             }
@@ -408,15 +419,17 @@ __device__ __forceinline__ void emit_triangle(const McArgs& A, const Smem& S, ui
             float3 qa = pa, qb = pb;
             if (MODE == M_TOPO) {
                 t = t_analysis(A.iso, fa, fb, et);
-                w[k] = A.f1 ? __ldg(A.f1 + ga) : 0.f;  // *field_val = r0 (:1797)
+                w[k] = A.f1 ? __ldg(at_point(A.f1, A.f1_top, ga, A.top_begin)) : 0.f;  // *field_val = r0 (:1797)
                 if (A.flags & F_DISP) {
                     const float4 d0 = A.disp[ga], d1 = A.disp[gb];
                     qa = make_float3(d0.x, d0.y, d0.z);
                     qb = make_float3(d1.x, d1.y, d1.z);
                 }
             } else if (A.flags & F_MAKE_REGION) t = et;
-            else if (A.flags & F_FIXED) t = t_fixed(A.iso, A.iso1, A.iso2, fa, fb, __ldg(A.f1 + ga), __ldg(A.f1 + gb));
-            else if (A.flags & F_DYNAMIC) t = t_primitive_one(A.iso1, A.iso2, __ldg(A.f1 + ga), __ldg(A.f1 + gb), et);
+            else if (A.flags & F_FIXED)
+                t = t_fixed(A.iso, A.iso1, A.iso2, fa, fb, __ldg(at_point(A.f1, A.f1_top, ga, A.top_begin)), __ldg(at_point(A.f1, A.f1_top, gb, A.top_begin)));
+            else if (A.flags & F_DYNAMIC)
+                t = t_primitive_one(A.iso1, A.iso2, __ldg(at_point(A.f1, A.f1_top, ga, A.top_begin)), __ldg(at_point(A.f1, A.f1_top, gb, A.top_begin)), et);
             else t = t_primitive(A.iso, fa, fb, et);
             v[k] = lerp3(qa, qb, t);
         }
@@ -538,6 +551,13 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
     if (MODE == M_BAND_RAW && A.d_ab) { na = __ldg(A.d_ab); nb = __ldg(A.d_ab + 1); }
     UniformDiv nd = make_uniform_div(__fsub_rn(nb, na));
     nd.a = na;
+    nd.two = false; nd.a2 = 0.f; nd.d2 = 1.f;
+    if (MODE == M_BAND_RAW && A.d_ab && A.two_stage) {
+        // {a2, b2}: range of the once-normalised field (d_ab[2..3]); (k - 0) / 1 is the identity, the usual case
+        const float a2 = __ldg(A.d_ab + 2), b2 = __ldg(A.d_ab + 3);
+        nd.two = !(a2 == 0.f && b2 == 1.f);
+        nd.a2 = a2; nd.d2 = __fsub_rn(b2, a2);
+    }
     const uint32_t ppr = A.ppr, cpr = A.cpr;
     const uint32_t plane_words = 2u * R1 * ppr * 4u;  // words per bit plane
     constexpr bool tma = TMA;
@@ -552,6 +572,7 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
         const uint32_t rows = min(A.rows_per_tile, A.cy - y0);
         const uint32_t npts = (rows + 1) * A.nx;   // staged points per slice
         const size_t g0 = (size_t)z * slice_pts + (size_t)y0 * A.nx;  // first staged point, slice z
+        const bool top_peer = A.f0_top != nullptr && z + 2u == A.nz;    // slice z + 1 is the +z halo layer held by the upper neighbour
 
         // ---- 1. stage-in
         if (TMA) {
@@ -559,7 +580,9 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
                 fence_proxy_async();  // generic-proxy accesses of the previous tile precede the async writes
                 mbar_expect_tx(S.mbar, 2u * npts * 4u);
                 tma_bulk_g2s(S.val[0], A.f0 + g0, npts * 4u, S.mbar);
-                tma_bulk_g2s(S.val[1], A.f0 + g0 + slice_pts, npts * 4u, S.mbar);
+                // slice z + 1: the rank's own layer, or -- for the last cell layer of a slab that holds owned layers only -- the first
+                // owned layer of the upper neighbour, read where it lies (peer memory over NVLink): no halo copy, no exchange step
+                tma_bulk_g2s(S.val[1], top_peer ? A.f0_top + (size_t)y0 * A.nx : A.f0 + g0 + slice_pts, npts * 4u, S.mbar);
             }
             mbar_wait(S.mbar, parity);
             parity ^= 1u;
@@ -597,6 +620,10 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
                         if (!fast) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) kk[u] = div_by_uniform(nn[u], nd);
+                        }
+                        if (nd.two) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) kk[u] = __fdiv_rn(__fsub_rn(kk[u], nd.a2), nd.d2);
                         }
                         // device_bufferfour (Gratings.cu:1089-1134): band mask, the six domain faces forced to k = 0, m = 0
                         bool m[4];
@@ -656,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, ModeTraits<MODE>::kMinBlocks) mc_fus
             const uint32_t x_ = 128u * (fk) + 32u * u + lane;                                               \
             RAW[u] = 0.f; FA[u] = 0.f; FB[u] = 0.f;                                                         \
             if (x_ < A.nx) {                                                                                \
-                RAW[u] = tma ? sv_[x_] : (A.f0 ? __ldg(A.f0 + grow_ + x_) : 0.f);                           \
+                RAW[u] = tma ? sv_[x_] : (A.f0 ? __ldg(((s_ && top_peer) ? A.f0_top + (size_t)(y0 + rr_) * A.nx : A.f0 + grow_) + x_) : 0.f); \
                 stage_fetch<MODE>(A, grow_ + x_, FA[u], FB[u]);                                             \
             }                                                                                               \
         }                                                                                                   \
@@ -1001,7 +1028,10 @@ int launch_extract(Ctx* c, McArgs& a, unsigned long long* active, unsigned long 
         a.snap_thr = thr;
     }
     // TMA bulk copies need 16-byte aligned global addresses and sizes
-    a.use_tma = !(c->options & GCB_OPT_NO_TMA) && a.f0 && (a.nx % 4 == 0) && (((uintptr_t)a.f0 & 15) == 0);
+    a.use_tma = !(c->options & GCB_OPT_NO_TMA) && a.f0 && (a.nx % 4 == 0) && (((uintptr_t)a.f0 & 15) == 0) && (((uintptr_t)a.f0_top & 15) == 0);
+    a.top_begin = (unsigned long long)(a.nz - 1) * a.nx * a.ny;
+    if ((a.f0_top || a.f1_top || a.gp_top) && (a.mode == M_REGION || a.mode == M_BAND_RAW || (a.flags & F_DISP) || a.f2))
+        return fail_msg(c, "peer-held halo layer: supported for the latticeone / CSG / topo inputs f0, f1 and grid_points only");
 
     // one scratch allocation, cleared by ONE memset per launch: [totals (2 words) | tile counter | pad | status_a | status_v]
     const size_t need = 4 + 2 * (size_t)a.num_tiles;

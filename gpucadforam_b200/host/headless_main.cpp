@@ -8,7 +8,14 @@
 // and the fused entry point for config 3 (spatial_lattice_run, main.cu:3904-4037).  Buffers are plain cudaMalloc
 // allocations with the layouts of vulkan_create_lattice_buffers / initMC_two (main.cu:2125-2161, :2714-2814).
 //
-//   gpucad_headless <config 1|2|3|5> [N] [out.obj]
+// Modes 4 and 5 take a third argument G and run the sharded path from ONE process on G ranks (gcb_multi_*, csrc/multi.cu; ranks
+// are mapped round-robin onto the visible GPUs, so G > #GPUs still works: several slabs per device):
+//   4 N G   BASELINE config 4 in miniature: the SVL lattice of config 3 on N^3, z-slabs, P2P min/max exchange
+//   5 N G   BASELINE config 5 on several GPUs: STORED density + grid_points + colour field, owned layers only per rank, the +z halo
+//           layer staged from the neighbour's memory by the extraction kernel
+// and compare the concatenated rank meshes with the single-rank mesh byte for byte ("PARITY OK").
+//
+//   gpucad_headless <config 1|2|3|5> [N] [out.obj]        gpucad_headless <4|5> N G
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -44,9 +51,154 @@ struct Mc {  // initMC_two
 
 static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b); return ms; }
 
+// ------------------------------------------------------------------ sharded modes (one process, G ranks)
+static void mcheck(gcb_multi* m, int rc, const char* what) {
+    if (rc != 0) { fprintf(stderr, "gpucad_b200 multi: %s failed: %s\n", what, gcb_multi_last_error(m)); exit(EXIT_FAILURE); }
+}
+static gcb_multi* make_multi(int G) {
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    std::vector<int> devs(G);
+    for (int r = 0; r < G; ++r) devs[r] = r % ndev;
+    gcb_multi* m = nullptr;
+    if (gcb_multi_create(&m, G, devs.data()) != 0) { fprintf(stderr, "gcb_multi_create failed\n"); exit(EXIT_FAILURE); }
+    return m;
+}
+struct HostMesh { std::vector<float> pos, norm; std::vector<unsigned> comp; unsigned long long active = 0, verts = 0; float ms = 0; };
+
+// SVL lattice on G ranks; the same synthetic phases / coefficients as mode 3
+static HostMesh svl_sharded(int N, int G) {
+    const int R = 4, C = N / R, NH = 62;
+    std::vector<float> phi((size_t)NH * C * C * C), coef(2 * NH);
+    int h = 0;
+    for (int k = -2; k <= 2 && h < NH; ++k) for (int j = -2; j <= 2 && h < NH; ++j) for (int i = -2; i <= 2 && h < NH; ++i, ++h) {
+        coef[2 * h] = 0.05f * (1 + (h % 5)); coef[2 * h + 1] = 0.03f * ((h % 3) - 1);
+        for (int z = 0; z < C; ++z) for (int y = 0; y < C; ++y) for (int x = 0; x < C; ++x)
+            phi[(((size_t)h * C + z) * C + y) * C + x] = 6.2831853f / 10.0f * (i * (x - C / 2.0f) + j * (y - C / 2.0f) + k * (z - C / 2.0f)) + 0.01f * x * y / C;
+    }
+    gcb_multi* m = make_multi(G);
+    std::vector<float*> d_svl(G), d_phi(G);
+    std::vector<const float*> d_phi_c(G);
+    std::vector<int> czl(G), cz0(G);
+    std::vector<unsigned> z0(G), z1(G);
+    for (int r = 0; r < G; ++r) {
+        gcb_slab_bounds((unsigned)N, G, r, 2, &z0[r], &z1[r]);
+        int c0, c1;
+        gcb_control_slab(z0[r], z1[r], R, C, &c0, &c1);
+        cz0[r] = c0; czl[r] = c1 - c0 + 1;
+        CK(cudaSetDevice(gcb_multi_device(m, r)));
+        const size_t per = (size_t)czl[r] * C * C;
+        CK(cudaMalloc(&d_phi[r], (size_t)NH * per * 4));
+        for (int hh = 0; hh < NH; ++hh)   // planes c0 .. c1 of every harmonic, back to back
+            CK(cudaMemcpy(d_phi[r] + (size_t)hh * per, phi.data() + ((size_t)hh * C + c0) * C * C, per * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&d_svl[r], (size_t)N * N * (z1[r] - z0[r] + 1) * 4));
+        d_phi_c[r] = d_phi[r];
+    }
+    const gcb_float3 vs{0.25f, 0.25f, 0.25f}, gc{0, 0, 0};
+    std::vector<unsigned long long> act(G), verts(G), off(G), cap(G);
+    float mm[2];
+    mcheck(m, gcb_multi_svl_lattice(m, d_svl.data(), d_phi_c.data(), NH, coef.data(), C, C, czl.data(), cz0.data(), N, N, (unsigned)N, 0.25f, 0.25f, 0.25f, 0.25f,
+                                    0.20f, 0.30f, vs, gc, nullptr, nullptr, nullptr, 1, act.data(), verts.data(), off.data(), mm), "multi_svl_lattice(count)");
+    std::vector<void*> pos(G), norm(G);
+    for (int r = 0; r < G; ++r) {
+        cap[r] = verts[r] + 3;   // count-then-allocate; +3: the `index < maxVerts - 3` guard
+        CK(cudaSetDevice(gcb_multi_device(m, r)));
+        CK(cudaMalloc(&pos[r], cap[r] * 16)); CK(cudaMalloc(&norm[r], cap[r] * 16));
+    }
+    HostMesh out;
+    for (int rep = 0; rep < 3; ++rep) {
+        mcheck(m, gcb_multi_svl_lattice(m, d_svl.data(), d_phi_c.data(), NH, coef.data(), C, C, czl.data(), cz0.data(), N, N, (unsigned)N, 0.25f, 0.25f, 0.25f, 0.25f,
+                                        0.20f, 0.30f, vs, gc, pos.data(), norm.data(), cap.data(), 0, act.data(), verts.data(), off.data(), mm), "multi_svl_lattice");
+        out.ms = gcb_multi_last_ms(m);
+    }
+    for (int r = 0; r < G; ++r) { out.active += act[r]; out.verts += verts[r]; }
+    out.pos.resize(out.verts * 4); out.norm.resize(out.verts * 4);
+    for (int r = 0; r < G; ++r) {
+        CK(cudaSetDevice(gcb_multi_device(m, r)));
+        CK(cudaMemcpy(out.pos.data() + off[r] * 4, pos[r], verts[r] * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out.norm.data() + off[r] * 4, norm[r], verts[r] * 16, cudaMemcpyDeviceToHost));
+        cudaFree(pos[r]); cudaFree(norm[r]); cudaFree(d_svl[r]); cudaFree(d_phi[r]);
+    }
+    printf("  %d rank(s): activeVoxels=%llu totalVerts=%llu  field min/max %g %g  %.3f ms (max over ranks)\n", G, out.active, out.verts, mm[0], mm[1], out.ms);
+    gcb_multi_destroy(m);
+    return out;
+}
+
+// stored fields on G ranks: density + grid_points (stored crossing parameters, a solid patch) + colour field
+static HostMesh density_sharded(int N, int G) {
+    const int nx = N, ny = N / 2, nz = N / 2;
+    const size_t layer = (size_t)nx * ny, n = layer * nz;
+    std::vector<float> dens(n), result(n);
+    std::vector<grid_points> gp(n);
+    for (int z = 0; z < nz; ++z) for (int y = 0; y < ny; ++y) for (int x = 0; x < nx; ++x) {
+        const size_t i = ((size_t)z * ny + y) * nx + x;
+        const float v = 0.5f + 0.5f * sinf(0.105f * x) * sinf(0.085f * y + 0.4f) * cosf(0.095f * z);
+        dens[i] = 0.07f + 0.93f * v * v;
+        result[i] = 0.001f * (float)((x * 7 + y * 13 + z * 29) % 997);
+        gp[i].val = ((x + 2 * y + 3 * z) % 41 == 0) ? -1 : 0;
+        gp[i].t_x = ((x * 3 + z) % 5 == 0) ? 0.25f + 0.5f * (float)((y + z) % 3) / 3.0f : 0.0f;
+        gp[i].t_y = ((y * 5 + x) % 7 == 0) ? 0.6f : 0.0f;
+        gp[i].t_z = ((z * 11 + y) % 4 == 0) ? 0.1f + 0.2f * (float)(x % 4) : 0.0f;
+    }
+    gcb_multi* m = make_multi(G);
+    std::vector<float*> d_dens(G), d_res(G);
+    std::vector<gcb_grid_points*> d_gp(G);
+    std::vector<unsigned*> d_comp(G);
+    std::vector<void*> pos(G), norm(G);
+    std::vector<unsigned long long> cap(G), act(G), verts(G), off(G), aoff(G);
+    std::vector<unsigned> z0(G), z1(G);
+    for (int r = 0; r < G; ++r) {
+        gcb_slab_bounds((unsigned)nz, G, r, 2, &z0[r], &z1[r]);
+        const size_t owned = (size_t)(z1[r] - z0[r] + (r == G - 1 ? 1 : 0)) * layer;   // OWNED layers only; the last rank owns its final layer too
+        CK(cudaSetDevice(gcb_multi_device(m, r)));
+        CK(cudaMalloc(&d_dens[r], owned * 4)); CK(cudaMalloc(&d_res[r], owned * 4)); CK(cudaMalloc(&d_gp[r], owned * sizeof(grid_points)));
+        CK(cudaMemcpy(d_dens[r], dens.data() + z0[r] * layer, owned * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_res[r], result.data() + z0[r] * layer, owned * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_gp[r], gp.data() + z0[r] * layer, owned * sizeof(grid_points), cudaMemcpyHostToDevice));
+        cap[r] = (unsigned long long)(z1[r] - z0[r]) * layer * 4 + 300000;
+        CK(cudaMalloc(&pos[r], cap[r] * 16)); CK(cudaMalloc(&norm[r], cap[r] * 16));
+        CK(cudaMalloc(&d_comp[r], (size_t)(z1[r] - z0[r]) * (nx - 1) * (ny - 1) * 4));
+    }
+    const gcb_uint3 gs{(unsigned)nx, (unsigned)ny, (unsigned)nz};
+    const gcb_float3 vs{0.5f, 0.5f, 0.5f}, gc{(float)nx / 4, 1.5f, (float)nz / 4 + 0.5f};
+    HostMesh out;
+    for (int rep = 0; rep < 3; ++rep) {
+        mcheck(m, gcb_multi_computeIsosurface_2(m, d_gp.data(), d_dens.data(), d_res.data(), gs, vs, gc, 0.4f, 0.0f, pos.data(), norm.data(), cap.data(), d_comp.data(),
+                                                act.data(), verts.data(), off.data(), aoff.data()), "multi_computeIsosurface_2");
+        out.ms = gcb_multi_last_ms(m);
+    }
+    for (int r = 0; r < G; ++r) { out.active += act[r]; out.verts += verts[r]; }
+    out.pos.resize(out.verts * 4); out.norm.resize(out.verts * 4); out.comp.resize(out.active);
+    for (int r = 0; r < G; ++r) {
+        CK(cudaSetDevice(gcb_multi_device(m, r)));
+        CK(cudaMemcpy(out.pos.data() + off[r] * 4, pos[r], verts[r] * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out.norm.data() + off[r] * 4, norm[r], verts[r] * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out.comp.data() + aoff[r], d_comp[r], act[r] * 4, cudaMemcpyDeviceToHost));
+        cudaFree(pos[r]); cudaFree(norm[r]); cudaFree(d_comp[r]); cudaFree(d_dens[r]); cudaFree(d_res[r]); cudaFree(d_gp[r]);
+    }
+    printf("  %d rank(s): activeVoxels=%llu totalVerts=%llu  %.3f ms (max over ranks)\n", G, out.active, out.verts, out.ms);
+    gcb_multi_destroy(m);
+    return out;
+}
+
+static int sharded_mode(int config, int N, int G) {
+    if (G < 1 || G > 16) { fprintf(stderr, "G must be 1..16\n"); return 2; }
+    printf("config %d sharded: N=%d, %d rank(s) vs 1 rank\n", config, N, G);
+    const HostMesh one = config == 4 ? svl_sharded(N, 1) : density_sharded(N, 1);
+    const HostMesh many = config == 4 ? svl_sharded(N, G) : density_sharded(N, G);
+    const bool ok = one.active == many.active && one.verts == many.verts && one.verts > 0 &&
+                    memcmp(one.pos.data(), many.pos.data(), one.pos.size() * 4) == 0 && memcmp(one.norm.data(), many.norm.data(), one.norm.size() * 4) == 0 &&
+                    one.comp == many.comp;
+    printf("%s: concatenated meshes of %d ranks %s the single-rank mesh (%llu vertices, %zu bytes compared); 1 rank %.3f ms, %d ranks %.3f ms\n",
+           ok ? "PARITY OK" : "PARITY FAIL", G, ok ? "equal" : "DIFFER from", one.verts, one.pos.size() * 8, one.ms, G, many.ms);
+    return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     const int config = argc > 1 ? atoi(argv[1]) : 1;
     const int N = argc > 2 ? atoi(argv[2]) : (config == 1 ? 128 : 256);
+    if (config == 4 || (config == 5 && argc > 3 && atoi(argv[3]) > 0 && strchr(argv[3], '.') == nullptr))
+        return sharded_mode(config, N, argc > 3 ? atoi(argv[3]) : 2);
     const char* obj = argc > 3 ? argv[3] : nullptr;
     Isosurface isosurf;
     Gratings lattice;
@@ -160,7 +312,7 @@ int main(int argc, char** argv) {
         ms = elapsed(e0, e1);
         d_pos = mc.d_pos;
     } else {
-        fprintf(stderr, "usage: gpucad_headless <1|2|3|5> [N] [out.obj]\n");
+        fprintf(stderr, "usage: gpucad_headless <1|2|3|5> [N] [out.obj]   |   gpucad_headless <4|5> N G\n");
         return 2;
     }
     printf("config %d N=%d: activeVoxels=%u totalVerts=%u triangles=%u  %.3f ms  (%.1f Mvoxel/s)\n", config, N, active, total, total / 3, ms,

@@ -291,6 +291,29 @@ int gcb_svl_lattice_host(gcb_ctx* ctx, const float* h_phi, float* d_phi_scratch,
     float isovalue2, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
     unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out);
 
+/* Fused unit-lattice path (BASELINE config 1; Multitopo::display_unit_lattice, main.cu:4113-4132): the composition
+ *   GPU_buffer_normalise_buffer(f, f) -> GPU_buffer_normalise_four(f, mask, k, isovalue1, isovalue2) ->
+ *   computeIsosurface_latticeone(mask, ..., k, isovalue1, isovalue2)
+ * on a RAW field in one call: one reduction of the field's true range, both normalisations applied inside the extraction kernel,
+ * one synchronisation.  Counts and mesh are bit-identical to that composition.  ranges_out (host float[4], optional):
+ * {a, b} of the first normalisation, {a2, b2} of the second.  d_compVoxelArray may be NULL. */
+int gcb_band_lattice_from_raw(gcb_ctx* ctx, const float* d_raw_field, gcb_uint3 gridSize, float isoValue, float isovalue1, float isovalue2,
+    gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts, unsigned int* d_compVoxelArray,
+    unsigned long long* activeVoxels, unsigned long long* totalVerts, float* ranges_out);
+/* ... with Fft_lattice::create_lattice in front: the unit cell of TPMS type 0..5 is written to d_field_scratch (device float[N]) and
+ * its range reduced by the same kernel. */
+int gcb_tpms_lattice(gcb_ctx* ctx, float* d_field_scratch, unsigned int lattice_type_index, gcb_uint3 gridSize, float isoValue, float isovalue1,
+    float isovalue2, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
+    unsigned int* d_compVoxelArray, unsigned long long* activeVoxels, unsigned long long* totalVerts, float* ranges_out);
+
+/* Fused density-surface path (BASELINE config 5; Multitopo::toprun, main.cu:3060-3109): Interpolations::copytotexture + updateTexture +
+ * Gratings::refine + Isosurface::computeIsosurface_2 with an all-zero vol_topo / d_result, in one call and one synchronisation.
+ * d_coarse: device float[cz][cy][cx]; d_density_fine: device float[NZ2*NY2*NX2], receives the upsampled density (as refine leaves it).
+ * Counts and mesh equal that sequence bit for bit (norm.w = 0). */
+int gcb_density_surface(gcb_ctx* ctx, const float* d_coarse, int cx, int cy, int cz, float* d_density_fine, int NX2, int NY2, int NZ2, float dx, float dy,
+    float dz, float isoValue, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
+    unsigned int* d_compVoxelArray, unsigned long long* activeVoxels, unsigned long long* totalVerts);
+
 /* Two-deep job pipeline of gcb_svl_lattice_host: _submit only enqueues (H2D copies on the library's copy stream, field,
  * reduction, extraction and the read-back of the counts on the context's stream) and returns; _wait blocks until that slot's job
  * is complete and hands back its counts.  With jobs alternating between slot 0 and slot 1, the control grids of job i+1 cross
@@ -302,6 +325,44 @@ int gcb_svl_lattice_host_submit(gcb_ctx* ctx, int slot, const float* h_phi, floa
     int cx, int cy, int cz, int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2,
     gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts);
 int gcb_svl_lattice_host_wait(gcb_ctx* ctx, int slot, unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out);
+
+/* ------------------------------------------------------------------ several GPUs from one host process (z-slab sharding)
+ * The reference is single-GPU; the scheme is BASELINE.json's: rank r owns cell layers [z0_r, z1_r) (gcb_slab_bounds, cuts aligned
+ * to 2), holds / evaluates point layers z0_r .. z1_r, the global min/max joins the ranks between field and extraction, counts are
+ * exclusive-scanned into global vertex offsets, and the rank meshes concatenated in rank order equal the single-GPU mesh byte for
+ * byte.  gcb_multi_* owns one context + one stream per rank and enables peer access between the devices; `devices` may name the same
+ * device more than once (slabs processed on one GPU, e.g. for tests).  Per-rank arguments are HOST arrays of n entries whose
+ * elements are device pointers ON that rank's device.  All work is enqueued without host synchronisation; the calls return after
+ * the counts of every rank have arrived. */
+typedef struct gcb_multi gcb_multi;
+int gcb_multi_create(gcb_multi** m, int n, const int* devices);
+int gcb_multi_destroy(gcb_multi* m);
+int gcb_multi_size(gcb_multi* m);
+gcb_ctx* gcb_multi_ctx(gcb_multi* m, int rank);      /* the rank's context (its stream is a non-blocking stream of the rank's device) */
+int gcb_multi_device(gcb_multi* m, int rank);
+const char* gcb_multi_last_error(gcb_multi* m);
+float gcb_multi_last_ms(gcb_multi* m);               /* device time of the last sharded call: max over ranks of (first launch .. counts) */
+/* cell layers [z0, z1) of `rank` of a grid with gnz point layers; same cuts as gpucadforam_b200/sharding.py slab_bounds */
+int gcb_slab_bounds(unsigned int gnz, int world, int rank, unsigned int align, unsigned int* z0, unsigned int* z1);
+/* control planes [c0, c1] a fine slab with point layers z0 .. z1 samples at upsampling ratio `ratio` */
+int gcb_control_slab(unsigned int z0, unsigned int z1, int ratio, int cz_global, int* c0, int* c1);
+
+/* BASELINE configs 3 / 4 on n ranks: gcb_svl_lattice sharded.  d_phi[r]: rank r's control slab (planes cz0[r] .. cz0[r] + cz_local[r] - 1
+ * of all harmonics), d_svl[r]: field scratch of NX2 * NY2 * (z1_r - z0_r + 1) floats.  The min/max exchange is a one-warp kernel per
+ * rank reading every rank's pair through peer-mapped pointers.  count_only != 0: counts only (pos / norm / max_verts may be NULL). */
+int gcb_multi_svl_lattice(gcb_multi* m, float* const* d_svl, const float* const* d_phi, int nh, const float* coef_host, int cx, int cy,
+    const int* cz_local, const int* cz0, int NX2, int NY2, unsigned int gnz, float dx, float dy, float dz, float isoValue, float isovalue1,
+    float isovalue2, gcb_float3 voxelSize, gcb_float3 gridcenter, void* const* pos, void* const* norm, const unsigned long long* max_verts,
+    int count_only, unsigned long long* active, unsigned long long* verts, unsigned long long* vert_offsets, float* minmax_out);
+
+/* Isosurface::computeIsosurface_2 on STORED fields sharded over n ranks (BASELINE config 5 on several GPUs).  Rank r's arrays hold its
+ * OWNED point layers only -- z0_r .. z1_r - 1, the last rank also its final layer; the +z halo layer is not copied: the extraction
+ * kernel stages it from the upper neighbour's arrays where they lie (peer memory over NVLink).  vol_topo / d_result may be NULL
+ * (treated as zeros).  Vertex z and d_compVoxelArray ids are global. */
+int gcb_multi_computeIsosurface_2(gcb_multi* m, gcb_grid_points* const* vol_topo, float* const* vol_two, float* const* d_result,
+    gcb_uint3 gridSizeGlobal, gcb_float3 voxelSize, gcb_float3 gridcenter, float isoValue, float isovalue1, void* const* pos, void* const* norm,
+    const unsigned long long* max_verts, unsigned int* const* d_compVoxelArray, unsigned long long* active, unsigned long long* verts,
+    unsigned long long* vert_offsets, unsigned long long* active_offsets);
 
 #ifdef __cplusplus
 }

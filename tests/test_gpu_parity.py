@@ -748,6 +748,8 @@ def _run_headless(*args):
     assert os.path.exists(exe), "gpucad_headless not built (make -C gpucadforam_b200/csrc headless)"
     out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+    if args and str(args[0]) == "4" or (len(args) > 2 and str(args[0]) == "5" and str(args[2]).isdigit()):
+        return out.stdout   # sharded modes: the harness does its own byte comparison and prints the verdict
     m = re.search(r"activeVoxels=(\d+) totalVerts=(\d+) triangles=(\d+)", out.stdout)
     assert m, out.stdout
     return int(m.group(1)), int(m.group(2)), int(m.group(3))
@@ -1603,3 +1605,92 @@ def test_job_pipeline_submit_wait_equals_blocking_calls(ctx, fctx, which):
     with pytest.raises(RuntimeError):
         submit(0)
     g.svl_lattice_host_wait(c, 0)
+
+
+# ------------------------------------------------------------------ fused unit-lattice entry points (BASELINE config 1)
+def _legacy_unit_lattice(ctx, f_raw, n, vox, cen, mv):
+    """normalise_buffer -> normalise_four -> latticeone on a copy of the raw field (main.cu:4113-4132)."""
+    f = f_raw.clone()
+    lat = g.Gratings(ctx)
+    lat.GPU_buffer_normalise_buffer(f, f, f.numel())
+    mask, k = torch.zeros_like(f), torch.zeros_like(f)
+    lat.GPU_buffer_normalise_four(f, mask, k, f.numel(), n, n, n, cases.BAND_LO, cases.BAND_HI)
+    scr, mesh = g.Scratch((n - 1) ** 3), g.MeshBuffers(mv)
+    a, t = g.Isosurface(ctx).computeIsosurface_latticeone(mask, mesh.pos, mesh.norm, cases.ISO_MASK, scr, (n, n, n), vox, cen, mv, k, cases.BAND_LO, cases.BAND_HI)
+    return a, t, mesh, scr
+
+
+@pytest.mark.parametrize("n", [32, 61])
+@pytest.mark.parametrize("typ", cases.TPMS_TYPES)
+def test_tpms_lattice_fused_equals_legacy_sequence(ctx, typ, n):
+    """gcb_tpms_lattice == create_lattice + GPU_buffer_normalise_buffer + GPU_buffer_normalise_four + computeIsosurface_latticeone, bit for bit
+    (n = 61: the reference's own unit-cell size, rows not 16-byte aligned -> LDG stage path)."""
+    vox, cen = (1.0, 1.0, 1.0), (0.0, 0.0, 0.0)
+    mv = max_verts_for((n, n, n))
+    raw = torch.zeros(n ** 3, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(raw, n, n, n, n ** 3, typ)
+    a, t, mesh, scr = _legacy_unit_lattice(ctx, raw, n, vox, cen, mv)
+    f2, mesh2 = torch.zeros(n ** 3, device="cuda"), g.MeshBuffers(mv)
+    comp = torch.zeros((n - 1) ** 3, dtype=torch.int32, device="cuda")
+    a2, t2, rg = g.tpms_lattice(ctx, f2, typ, (n, n, n), cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, vox, cen, mesh2.pos, mesh2.norm, mv, comp=comp)
+    assert_bits_equal(f2, raw, "tpms_lattice raw field")
+    lo, hi = orc.minmax(raw.cpu().numpy())
+    assert rg[:2] == (lo, hi)
+    assert (a, t) == (a2, t2)
+    assert torch.equal(comp[:a], scr.compVoxelArray[:a])
+    assert_bits_equal(mesh.pos[:t], mesh2.pos[:t], "tpms_lattice pos")
+    assert_bits_equal(mesh.norm[:t], mesh2.norm[:t], "tpms_lattice norm")
+
+
+@pytest.mark.parametrize("kind", ["mixed_sign", "all_negative", "all_positive", "negative_offset"])
+def test_band_lattice_from_raw_two_stage_normalisation(ctx, kind):
+    """The second normalisation is the identity only when the once-normalised field spans exactly [0, 1]; an all-negative field (max
+    clamped to 0) makes it live.  gcb_band_lattice_from_raw must follow the legacy sequence bit for bit in every case."""
+    n = 40
+    vox, cen = (0.5, 0.5, 0.5), (2.0, -1.0, 0.5)
+    mv = max_verts_for((n, n, n))
+    raw = torch.zeros(n ** 3, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(raw, n, n, n, n ** 3, 0)
+    raw = {"mixed_sign": raw, "all_negative": raw - 3.25, "all_positive": raw + 2.5, "negative_offset": raw * 0.37 - 1.9}[kind].contiguous()
+    a, t, mesh, scr = _legacy_unit_lattice(ctx, raw, n, vox, cen, mv)
+    mesh2 = g.MeshBuffers(mv)
+    a2, t2, rg = g.band_lattice_from_raw(ctx, raw, (n, n, n), cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, vox, cen, mesh2.pos, mesh2.norm, mv)
+    if kind in ("all_negative", "negative_offset"):
+        assert rg[1] == 0.0 and 0.0 < rg[3] < 1.0       # b clamped to 0, b2 below 1: second stage live
+    else:
+        assert rg[2:] == (0.0, 1.0)
+    assert (a, t) == (a2, t2) and t > 0
+    assert_bits_equal(mesh.pos[:t], mesh2.pos[:t], "band_lattice_from_raw pos (%s)" % kind)
+    assert_bits_equal(mesh.norm[:t], mesh2.norm[:t], "band_lattice_from_raw norm (%s)" % kind)
+
+
+def test_density_surface_fused_equals_legacy_sequence(ctx):
+    """gcb_density_surface == copytotexture + updateTexture + refine + computeIsosurface_2 with zero vol_topo / d_result (config 5 in miniature)."""
+    T = cases.TOPO
+    fx, fy, fz = T["fdims"]
+    npts = fx * fy * fz
+    coarse = dev(cases.topo_coarse(T).reshape(-1))
+    dens = _upsample(ctx, T, cases.topo_coarse(T))
+    mv = max_verts_for(T["fdims"])
+    scr, mesh = g.Scratch((fx - 1) * (fy - 1) * (fz - 1)), g.MeshBuffers(mv)
+    a, t = g.Isosurface(ctx).computeIsosurface_2(mesh.pos, mesh.norm, T["iso"], scr, T["fdims"], T["d"], (1.5, 0, -2), mv, gp_zeros(npts), dens, 0.0,
+                                                 torch.zeros(npts, device="cuda"))
+    dens2, mesh2 = torch.zeros(npts, device="cuda"), g.MeshBuffers(mv)
+    comp = torch.zeros((fx - 1) * (fy - 1) * (fz - 1), dtype=torch.int32, device="cuda")
+    a2, t2 = g.density_surface(ctx, coarse, T["cdims"], dens2, T["fdims"], T["d"], T["iso"], T["d"], (1.5, 0, -2), mesh2.pos, mesh2.norm, mv, comp=comp)
+    assert_bits_equal(dens, dens2, "density_surface: upsampled density")
+    assert (a, t) == (a2, t2) and t > 0
+    assert torch.equal(comp[:a], scr.compVoxelArray[:a])
+    assert_bits_equal(mesh.pos[:t], mesh2.pos[:t], "density_surface pos")
+    assert_bits_equal(mesh.norm[:t], mesh2.norm[:t], "density_surface norm")
+
+
+# ------------------------------------------------------------------ C++ multi-GPU host (csrc/multi.cu, host/headless_main.cpp modes 4 / 5)
+@pytest.mark.parametrize("mode,n,ranks", [(4, 64, 2), (4, 64, 3), (4, 96, 5), (5, 64, 2), (5, 96, 3), (5, 64, 4)])
+def test_cpp_multi_rank_host_concatenation_equals_single_rank(mode, n, ranks):
+    """One process, `ranks` contexts (round-robin over the visible GPUs; on a 1-GPU box all on device 0): mode 4 = sharded SVL lattice with
+    the P2P min/max exchange kernel, mode 5 = STORED density / grid_points / colour field with owned layers only per rank and the halo
+    layer staged from the neighbour's buffers by the extraction kernel.  The harness compares the concatenated rank meshes (and the
+    compacted global cell ids in mode 5) with the single-rank result byte for byte."""
+    out = _run_headless(str(mode), str(n), str(ranks))
+    assert "PARITY OK" in out, out

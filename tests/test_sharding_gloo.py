@@ -218,3 +218,22 @@ def test_empty_slab_fails_on_every_rank_instead_of_hanging(tmp_path):
     s.close()
     mp.spawn(_empty_slab_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert [open(os.path.join(str(tmp_path), "empty%d.txt" % r)).read() for r in range(world)] == ["ValueError"] * world
+
+
+def test_cpp_slab_bounds_equal_the_python_ones():
+    """gcb_slab_bounds / gcb_control_slab (csrc/multi.cu, the C++ multi-GPU host) cut exactly like sharding.slab_bounds / control_slab
+    (ties of the even split included: Python's round() and nearbyint() both round half to even)."""
+    import ctypes as C
+    from gpucadforam_b200 import _capi
+    lib = _capi.load()
+    for gnz in (5, 17, 40, 41, 129, 385, 513, 2048, 2049):
+        for world in (1, 2, 3, 4, 5, 7, 8, 16):
+            for align in (1, 2, 4):
+                for rank in range(world):
+                    z0, z1 = C.c_uint(0), C.c_uint(0)
+                    assert lib.gcb_slab_bounds(gnz, world, rank, align, C.byref(z0), C.byref(z1)) == 0
+                    assert (z0.value, z1.value) == sharding.slab_bounds(gnz, world, rank, align), (gnz, world, rank, align)
+    for (z0, z1, ratio, czg) in ((0, 64, 4, 128), (64, 127, 4, 32), (10, 33, 2, 17), (0, 511, 4, 128)):
+        c0, c1 = C.c_int(0), C.c_int(0)
+        assert lib.gcb_control_slab(z0, z1, ratio, czg, C.byref(c0), C.byref(c1)) == 0
+        assert (c0.value, c1.value) == sharding.control_slab(z0, z1, ratio, czg)
