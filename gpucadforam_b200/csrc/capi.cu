@@ -84,7 +84,7 @@ int gcb_destroy(gcb_ctx* ctx) {
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};  // leave the caller's current device as it was
     cudaSetDevice(C->device);
     cudaFree(C->d_status); cudaFree(C->d_tile_counter); cudaFree(C->d_totals); cudaFreeHost(C->h_totals);
-    cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef); cudaFree(C->d_range4);
+    cudaFree(C->d_minmax); cudaFreeHost(C->h_minmax); cudaFree(C->d_tex); cudaFree(C->d_coef); cudaFree(C->d_range4); cudaFree(C->d_tab);
     cudaFree(C->d_tri); cudaFree(C->d_nverts);
     if (C->copy_stream) { cudaStreamDestroy(C->copy_stream); for (int i = 0; i < Ctx::kBatches; ++i) cudaEventDestroy(C->copy_ev[i]); }
     if (C->aux_stream) { cudaStreamDestroy(C->aux_stream); cudaEventDestroy(C->aux_ev[0]); cudaEventDestroy(C->aux_ev[1]); }

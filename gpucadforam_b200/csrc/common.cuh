@@ -93,6 +93,7 @@ struct Ctx {
     unsigned long long* h_totals = nullptr;  // pinned
     // reductions
     float* d_minmax = nullptr;               // 2 floats (ordered-int encoded during reduction)
+    float* d_tab = nullptr; size_t tab_cap = 0;  // separable-primitive tables (fields.cu line_tab_kernel)
     float* d_range4 = nullptr;               // fused normalise-twice paths: 2 raw words (true min / max) + {a, b, a2, b2}
     float* h_minmax = nullptr;               // pinned
     // control grid ("texture")

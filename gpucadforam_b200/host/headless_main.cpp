@@ -15,7 +15,10 @@
 //           layer staged from the neighbour's memory by the extraction kernel
 // and compare the concatenated rank meshes with the single-rank mesh byte for byte ("PARITY OK").
 //
-//   gpucad_headless <config 1|2|3|5> [N] [out.obj]        gpucad_headless <4|5> N G
+// `3 N --full [out.obj]` runs the WHOLE lattice workflow through the C ABI: unit cell -> spectrum -> period field -> phase solve ->
+// field -> mesh -> .obj (Multitopo::unit_lattice + spatial_lattice_run).
+//
+//   gpucad_headless <config 1|2|3|5> [N] [out.obj]        gpucad_headless <4|5> N G        gpucad_headless 3 N --full [out.obj]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -181,6 +184,58 @@ static HostMesh density_sharded(int N, int G) {
     return out;
 }
 
+// ------------------------------------------------------------------ mode 3 --full: the whole SVL workflow through the C ABI
+// Multitopo::unit_lattice (main.cu:3577-3706) + spatial_lattice_run (:3904-4037): unit cell -> spectrum -> period field -> normalise_three
+// -> phase solve of all 62 harmonics -> fused field + extraction on the 2x refined grid (the app's own ratio) -> .obj.
+static int full_workflow(int N, const char* obj) {
+    const int NU = 61, NH = 62, C = N / 2;   // unit cell size of the reference (main.cu:582), control grid = coarse grid of the app
+    const size_t nc = (size_t)C * C * C, nf = (size_t)N * N * N;
+    gcb_ctx* ctx = gpucad::ctx();
+    cudaEvent_t ev[8];
+    for (auto& e : ev) cudaEventCreate(&e);
+    float *d_cell, *d_spec, *d_period, *d_phi, *d_svl;
+    CK(cudaMalloc(&d_cell, (size_t)NU * NU * NU * 4)); CK(cudaMalloc(&d_spec, 125 * 8)); CK(cudaMalloc(&d_period, nc * 4));
+    CK(cudaMalloc(&d_phi, (size_t)NH * nc * 4)); CK(cudaMalloc(&d_svl, nf * 4));
+    std::vector<int> ijk;
+    for (int k = -2; k <= 2; ++k) for (int j = -2; j <= 2; ++j) for (int i = -2; i <= 2; ++i) if ((int)ijk.size() < 3 * NH) { ijk.push_back(i); ijk.push_back(j); ijk.push_back(k); }
+    cudaEventRecord(ev[0]);
+    gpucad::check(gcb_create_lattice(ctx, d_cell, NU, NU, NU, NU * NU * NU, 0), "create_lattice");
+    gpucad::check(gcb_unit_lattice_spectrum(ctx, d_cell, NU, NU, NU, 2, d_spec), "unit_lattice_spectrum");
+    std::vector<float> spec(250);
+    CK(cudaMemcpy(spec.data(), d_spec, 250 * 4, cudaMemcpyDeviceToHost));
+    cudaEventRecord(ev[1]);
+    gpucad::check(gcb_period_data(ctx, d_period, C, C, C, 1.f, 1.f, 1.f, C / 2.0f, C / 2.0f, C / 2.0f, 'z'), "period_data");
+    gpucad::check(gcb_GPU_buffer_normalise_three(ctx, d_period, d_period, nc, (float)(C / 10), (float)(C / 4)), "normalise_three");
+    cudaEventRecord(ev[2]);
+    std::vector<int> fi(NH);
+    std::vector<float> fr(NH);
+    gpucad::check(gcb_svl_phase_solve(ctx, d_phi, d_period, NH, ijk.data(), C, C, C, 1.f, 1.f, 1.f, 'r', 2, 8.f, 8.f, 8.f, 8.f, 0.5f, 0.05f, 0, 500, 0.01f, fi.data(), fr.data()),
+                  "svl_phase_solve");
+    cudaEventRecord(ev[3]);
+    unsigned long long a64 = 0, t64 = 0;
+    float mm[2];
+    const gcb_float3 vs{0.5f, 0.5f, 0.5f}, gc{0, 0, 0};
+    gpucad::check(gcb_svl_lattice(ctx, d_svl, d_phi, NH, spec.data(), C, C, C, N, N, N, 0.5f, 0.5f, 0.5f, 0.25f, 0.20f, 0.30f, vs, gc, nullptr, nullptr, 3, &a64, &t64, mm),
+                  "svl_lattice(count)");
+    float4 *pos, *norm;
+    CK(cudaMalloc(&pos, (t64 + 3) * 16)); CK(cudaMalloc(&norm, (t64 + 3) * 16));
+    cudaEventRecord(ev[4]);
+    gpucad::check(gcb_svl_lattice(ctx, d_svl, d_phi, NH, spec.data(), C, C, C, N, N, N, 0.5f, 0.5f, 0.5f, 0.25f, 0.20f, 0.30f, vs, gc, pos, norm, t64 + 3, &a64, &t64, mm),
+                  "svl_lattice");
+    cudaEventRecord(ev[5]);
+    long iters = 0;
+    for (int h = 0; h < NH; ++h) iters += fi[h];
+    printf("config 3 --full N=%d (control %d^3): unit cell + spectrum %.3f ms, period field %.3f ms, phase solve %.3f ms (%ld CG iterations over %d harmonics), "
+           "field + extraction %.3f ms\n", N, C, elapsed(ev[0], ev[1]), elapsed(ev[1], ev[2]), elapsed(ev[2], ev[3]), iters, NH, elapsed(ev[4], ev[5]));
+    printf("config 3 N=%d: activeVoxels=%llu totalVerts=%llu triangles=%llu  %.3f ms  (field min/max %g %g)\n", N, a64, t64, t64 / 3,
+           elapsed(ev[0], ev[3]) + elapsed(ev[4], ev[5]), mm[0], mm[1]);
+    if (obj && t64) {
+        gpucad::check(gcb_file_write_obj(ctx, pos, (unsigned)t64, obj), "file_write_obj");
+        printf("wrote %s\n", obj);
+    }
+    return 0;
+}
+
 static int sharded_mode(int config, int N, int G) {
     if (G < 1 || G > 16) { fprintf(stderr, "G must be 1..16\n"); return 2; }
     printf("config %d sharded: N=%d, %d rank(s) vs 1 rank\n", config, N, G);
@@ -200,6 +255,13 @@ int main(int argc, char** argv) {
     if (config == 4 || (config == 5 && argc > 3 && atoi(argv[3]) > 0 && strchr(argv[3], '.') == nullptr))
         return sharded_mode(config, N, argc > 3 ? atoi(argv[3]) : 2);
     const char* obj = argc > 3 ? argv[3] : nullptr;
+    if (config == 3)
+        for (int i = 2; i < argc; ++i)
+            if (!strcmp(argv[i], "--full")) {
+                const char* o = nullptr;
+                for (int j = 3; j < argc; ++j) if (j != i) o = argv[j];
+                return full_workflow(N, o);
+            }
     Isosurface isosurf;
     Gratings lattice;
     Fft_lattice fftlattice;

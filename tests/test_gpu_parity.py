@@ -1694,3 +1694,120 @@ def test_cpp_multi_rank_host_concatenation_equals_single_rank(mode, n, ranks):
     compacted global cell ids in mode 5) with the single-rank result byte for byte."""
     out = _run_headless(str(mode), str(n), str(ranks))
     assert "PARITY OK" in out, out
+
+
+# ------------------------------------------------------------------ separable sphere / cylinder kernels vs the per-point ones
+@needs_ref
+@pytest.mark.parametrize("dims", [(16, 16, 16), (96, 80, 64), (130, 34, 66)], ids=["small_generic_path", "tables", "tables_ragged"])
+@pytest.mark.parametrize("variant", ["sphere", "sphere_shell", "cylinder", "disc", "cylinder_tilted"])
+def test_sphere_and_cylinder_tables_bit_exact(ctx, dims, variant):
+    """sphere_with_center / distance_from_line tabulate powf(v, 2) per distinct argument (fields.cu sphere_tab_kernel, line_tab_kernel) above
+    32k points and evaluate it per point below: both must equal the reference kernels bit for bit (Modelling.cu:244-361), for general
+    centres, anisotropic spacings and a tilted axis."""
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    if n % 1024:   # 130 x 34 x 66 is not a multiple of 1024: both reference kernels guard tx < size (Modelling.cu:253, :323)
+        assert variant
+    d, c = (0.5, 0.25, 0.75), (1.3, -0.7, 2.1)
+    m = g.Modelling(ctx)
+    mine, theirs = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    if variant.startswith("sphere"):
+        shell = variant == "sphere_shell"
+        m.sphere_with_center(mine, c, 7.25, 1.5, nx, ny, nz, *d, shell)
+        ref.sphere(theirs, c, 7.25, 1.5, dims, d, shell)
+    else:
+        axis = (0.3, -0.2, 0.9) if variant == "cylinder_tilted" else (0.0, 0.0, 1.0)
+        disc = variant == "disc"
+        m.distance_from_line(mine, c, axis, 4.5, 1.5, 11.0, nx, ny, nz, *d, disc)
+        ref.distance_from_line(theirs, c, axis, 4.5, 1.5, 11.0, dims, d, disc)
+    nbad = int((bits(mine) != bits(theirs)).sum())
+    assert nbad == 0, "%s %s: %d of %d words differ from the reference kernel, max %d ulp" % (variant, dims, nbad, n, ulp_diff(mine, theirs))
+
+
+# ------------------------------------------------------------------ the whole SVL workflow through the C ABI vs the reference loop
+@needs_ref
+def test_full_svl_workflow_end_to_end_vs_reference_loop(ctx, tmp_path):
+    """Multitopo::unit_lattice + spatial_lattice_run (main.cu:3577-3706, :3904-4037) end to end through this library -- unit cell ->
+    spectrum -> period field -> normalise_three -> batched phase solve -> fused SVL field + extraction -> .obj -- against the reference's
+    own sequence (period_data, GPU_buffer_normalise_three, 62 x {finding_phi, GPUCG_lattice, copytotexture, updateTexture, grating, svl},
+    GPU_buffer_normalise_four, computeIsosurface_lattice, file_write_obj).  Both arms take the coefficients of gcb_unit_lattice_spectrum
+    (the spectrum is a floating-point row with its own tolerance, test_unit_lattice_spectrum); everything after it is bit for bit."""
+    from gpucadforam_b200 import synth
+    nu = 61
+    cdims, fdims, dc, df = (32, 32, 16), (64, 64, 32), (1.0, 1.0, 1.0), (0.5, 0.5, 0.5)
+    nc, nf = cdims[0] * cdims[1] * cdims[2], fdims[0] * fdims[1] * fdims[2]
+    harm = synth.HARMONICS
+    nh = len(harm)
+    lat = g.Gratings(ctx)
+    # producers
+    cell = torch.zeros(nu ** 3, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(cell, nu, nu, nu, nu ** 3, 0)
+    spec = g.unit_lattice_spectrum(ctx, cell, nu, nu, nu, 2).cpu().numpy()[:nh]
+    coef = [(float(c.real), float(c.imag)) for c in spec]
+    mean = (cdims[0] / 2.0, cdims[1] / 2.0, cdims[2] / 2.0)      # latticetype 'r' (main.cu:3918-3925)
+    a1, b1 = float(cdims[0] // 10), float(cdims[0] // 4)
+    per = torch.zeros(nc, device="cuda")
+    lat.period_data(per, *cdims, *dc, *mean, "z")
+    lat.GPU_buffer_normalise_three(per, per, nc, a1, b1)
+    phi = torch.zeros(nh, nc, device="cuda")
+    fi, fr = g.svl_phase_solve(ctx, phi, per, harm, cdims, dc, latticetype="r", uniform_type=2, iters=500, end_res=0.01)
+    mv = max_verts_for(fdims)
+    svl, mesh = torch.zeros(nf, device="cuda"), g.MeshBuffers(mv)
+    act, tot, mm = g.svl_lattice(ctx, svl, phi, coef, cdims, fdims, df, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, df, (0, 0, 0), mesh.pos, mesh.norm, mv)
+    assert tot > 1000
+    p1 = str(tmp_path / "ours.obj")
+    g.File_output(ctx).file_write_obj(mesh.pos, tot, p1)
+    # the reference's own loop
+    per2 = torch.zeros(nc, device="cuda")
+    ref.period_data(per2, cdims, dc, mean, "z")
+    ref.normalise_three(per2, per2, nc, a1, b1)
+    assert_bits_equal(per, per2, "period field")
+    phi2 = torch.zeros(nh, nc, device="cuda")
+    for h, ijk in enumerate(harm):
+        ref.finding_phi(phi2[h], per2, cdims, ijk, dc, latticetype="r", uniform_type=2)
+        fi_r, fr_r = ref.cg(phi2[h], cdims, 500, 0.01)
+        assert (fi[h], fr[h]) == (fi_r, fr_r), "harmonic %d: CG iterations / residual" % h
+    assert_bits_equal(phi, phi2, "62 phase grids")
+    ref.setup_texture(*cdims)
+    svl2, ga = torch.zeros(nf, device="cuda"), torch.zeros((nf, 2), device="cuda")
+    ref.svl_field(svl2, ga, phi2, nh, dev(np.array(coef, np.float32)), cdims, fdims, df)
+    ref.delete_texture()
+    assert_bits_equal(svl, svl2, "SVL field")
+    mask2, k2 = torch.zeros(nf, device="cuda"), torch.zeros(nf, device="cuda")
+    ref.normalise_four(svl2, mask2, k2, fdims, cases.BAND_LO, cases.BAND_HI)
+    scr2, mesh2 = g.Scratch((fdims[0] - 1) * (fdims[1] - 1) * (fdims[2] - 1)), g.MeshBuffers(mv)
+    a2, t2 = ref.isosurface_lattice(False, False, mask2, mesh2.pos, mesh2.norm, cases.ISO_MASK, fdims, df, (0, 0, 0), scr2, mv, k2, torch.zeros_like(k2),
+                                    cases.BAND_LO, cases.BAND_HI, 0.0, 0.0)
+    assert (act, tot) == (a2, t2)
+    assert_bits_equal(mesh.pos[:tot], mesh2.pos[:tot], "workflow mesh positions")
+    assert_bits_equal(mesh.norm[:tot], mesh2.norm[:tot], "workflow mesh normals")
+    p2 = str(tmp_path / "ref.obj")
+    ref.write_obj(mesh2.pos, t2, p2)
+    assert open(p1, "rb").read() == open(p2, "rb").read(), ".obj bytes"
+
+
+def test_headless_full_workflow_matches_python_driven_calls(ctx, tmp_path):
+    """gpucad_headless 3 N --full: the C++ harness runs unit cell -> spectrum -> period -> phase solve -> field -> mesh -> .obj through the
+    C ABI; the same calls driven from Python must give the same counts and the same .obj bytes."""
+    from gpucadforam_b200 import synth
+    N, C, nu = 64, 32, 61
+    obj = str(tmp_path / "full.obj")
+    act_h, tot_h, tri_h = _run_headless("3", str(N), "--full", obj)
+    lat = g.Gratings(ctx)
+    cell = torch.zeros(nu ** 3, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(cell, nu, nu, nu, nu ** 3, 0)
+    spec = g.unit_lattice_spectrum(ctx, cell, nu, nu, nu, 2).cpu().numpy()[:62]
+    coef = [(float(c.real), float(c.imag)) for c in spec]
+    per = torch.zeros(C ** 3, device="cuda")
+    lat.period_data(per, C, C, C, 1.0, 1.0, 1.0, C / 2.0, C / 2.0, C / 2.0, "z")
+    lat.GPU_buffer_normalise_three(per, per, C ** 3, float(C // 10), float(C // 4))
+    phi = torch.zeros(62, C ** 3, device="cuda")
+    g.svl_phase_solve(ctx, phi, per, synth.HARMONICS, (C, C, C), (1.0, 1.0, 1.0), latticetype="r", uniform_type=2, iters=500, end_res=0.01)
+    mv = max_verts_for((N, N, N))
+    svl, mesh = torch.zeros(N ** 3, device="cuda"), g.MeshBuffers(mv)
+    act, tot, _ = g.svl_lattice(ctx, svl, phi, coef, (C, C, C), (N, N, N), (0.5,) * 3, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, (0.5,) * 3, (0, 0, 0), mesh.pos,
+                                mesh.norm, mv)
+    assert (act, tot, tot // 3) == (act_h, tot_h, tri_h) and tot > 0
+    p2 = str(tmp_path / "py.obj")
+    g.File_output(ctx).file_write_obj(mesh.pos, tot, p2)
+    assert open(obj, "rb").read() == open(p2, "rb").read()
