@@ -10,12 +10,17 @@ extracted with marching cubes.  N > 1 (torchrun, one rank per GPU): weak scaling
 is fine x fine x (fine*N), sharded in z-slabs; one tiny NCCL all-reduce carries the global min/max
 between field evaluation and extraction, vertex offsets come from an all-gather of the counts.
 
-One step = control grids resident in HBM -> field -> min/max -> fused extraction -> counts on the host.
-`value` is voxels (grid points) per second over all ranks; `e2e` is the same step through the
-host-buffer C-ABI entry point (pinned host control grids copied H2D inside the timed region, counts read
-back).  `roofline` describes the fused extraction kernel (HBM-bound: 4 B/point + 32 B/vertex), timed
-with CUDA events on the library's stream during the timed steps; `field_kernel` reports the
-FP32-bound SVL evaluation kernel that dominates the step.
+One step = control grids resident in HBM -> field -> min/max (stays in device memory) -> fused extraction -> counts on the host.
+`value` is voxels (grid points) per second over all ranks, DEFAULT library mode (field bit-identical to the reference kernels).
+`e2e` is the same workload with HOST control grids, every step copying them H2D inside the timed region and reading its counts back:
+on one GPU through the two-deep job pipeline (gcb_svl_lattice_host_submit / _wait; `e2e.blocking_call` = one blocking call per
+step), on N > 1 one blocking sequence per step and rank, with `e2e.h2d_probe` naming the host-side limiter by measurement.
+`roofline` describes the kernel that dominates the step, `roofline_other_kernel` the other one: the SVL field kernel (writes 4 B /
+point: nothing to stream, bound by instruction issue -- reported with the HBM figure the contract asks for AND its actual limiter) and
+the fused extraction kernel (HBM-bound: 4 B/point + 32 B/vertex); both timed with CUDA events on the library's stream in the timed steps.
+Secondary legs in the same line: `fast_field` (GCB_OPT_FAST_FIELD: hardware cosine, stated tolerance), `ratio2` (the app's own upsampling
+ratio), `configs` (BASELINE configs 1, 2, 5 at full size; our side -- the reference kernels' side is in the --impl reference line) and
+`config4` (the 2048-wide grid of BASELINE config 4, z-slab sharded: the full 2048^3 at N >= 4).
 
 `--impl reference` times the reference's OWN CUDA kernels (oracle/_ref/libgpucad_ref.so, the unmodified
 sources compiled for sm_100a) on the same workload on the GPU -- the reference has no CPU path; north_star
