@@ -171,12 +171,13 @@ def workload_config(F, R, NH, gnz, world, strong):
 class SvlLeg:
     """One SVL-lattice workload (configs 3 / 4) on this rank's z-slab: set-up, device-timed steps, end-to-end steps."""
 
-    def __init__(self, env, F, R, NH, gnz, fast=False, spectrum="gyroid"):
+    def __init__(self, env, F, R, NH, gnz, fast=False, spectrum="gyroid", cuts=None):
         torch, g, sharding, synth = env["torch"], env["g"], env["sharding"], env["synth"]
         self.env, self.F, self.R, self.NH, self.gnz, self.fast = env, F, R, NH, gnz, fast
         rank, world, dev = env["rank"], env["world"], env["dev"]
         sharding.validate_slabs(gnz, world)
-        self.z0, self.z1 = sharding.slab_bounds(gnz, world, rank)
+        self.cuts = list(cuts) if cuts else [sharding.slab_bounds(gnz, world, r)[0] for r in range(world)] + [gnz - 1]
+        self.z0, self.z1 = self.cuts[rank], self.cuts[rank + 1]
         self.nzl = self.z1 - self.z0 + 1
         self.d = (1.0 / R,) * 3
         self.cxy, self.czg = F // R, gnz // R
@@ -343,6 +344,30 @@ class SvlLeg:
         torch.cuda.empty_cache()
 
 
+# cost model of the slab balancing (ms per point / per vertex at 512-wide rows, from the kernel times of the N = 1 line): the field
+# kernel and the stage + classify half of the extraction scale with points, the emission with vertices
+COST_PER_POINT = {False: (9.8 + 0.67) / 134.2e6, True: (2.6 + 0.67) / 134.2e6}
+COST_PER_VERTEX = 1.57 / 172.6e6
+
+
+def balanced_leg(env, F, R, NH, gnz, fast):
+    """N > 1: count on the even z-cut, all-gather the counts, re-cut the slabs so that the ESTIMATED cost per rank is even (the lattice's
+    triangle density varies 1.5x along z), and set the leg up again on the new cuts.  Any partition concatenates to the same global
+    mesh; the even cut stays if the re-cut would not change it."""
+    sharding = env["sharding"]
+    leg = SvlLeg(env, F, R, NH, gnz, fast=fast)
+    if env["world"] == 1 or os.environ.get("GCB_BENCH_EVEN_SLABS"):
+        return leg, None
+    per_rank, _, _, _ = sharding.gather_counts(env["dist"], leg.act, leg.tot, device=env["dev"])
+    cuts = sharding.balanced_cuts(gnz, env["world"], leg.cuts, [v for (_, v) in per_rank], COST_PER_POINT[bool(fast)], COST_PER_VERTEX, F * F,
+                                  align=R if R % 2 == 0 else 2)   # cuts on control-cell boundaries: the field kernels' tiles then span one cell in z
+    info = {"even_cut_vertices_per_rank": [v for (_, v) in per_rank], "cell_layer_cuts": cuts}
+    if cuts == leg.cuts:
+        return leg, info
+    leg.free()
+    return SvlLeg(env, F, R, NH, gnz, fast=fast, cuts=cuts), info
+
+
 def h2d_probe(env, nbytes=512 << 20, reps=4):
     """Multi-rank runs: host-to-device bandwidth of one pinned buffer per rank, every rank copying at the same time and rank 0
     alone -- names the limiter of the e2e leg (PCIe links shared behind a switch / host memory) by measurement."""
@@ -426,7 +451,7 @@ def main():
     peak, peak_src = peaks()
 
     # ---- headline leg: BASELINE config 3, exact field (bit-identical to the reference kernels) unless --fast-field
-    leg = SvlLeg(env, F, R, NH, gnz, fast=args.fast_field)
+    leg, balance = balanced_leg(env, F, R, NH, gnz, args.fast_field)
     raw = leg.run(args.steps, args.warmup, e2e=not args.profile, sampler=ClockSampler(local_rank) if rank == 0 else None)
     if args.profile:
         if rank == 0:
@@ -443,8 +468,10 @@ def main():
     if not args.no_extra:
         # ---- fast field mode on the same workload (GCB_OPT_FAST_FIELD; tolerance stated in include/gpucad_b200.h)
         if not args.fast_field:
-            fl = SvlLeg(env, F, R, NH, gnz, fast=True)
+            fl, fbal = balanced_leg(env, F, R, NH, gnz, True)
             extra["fast_field"] = fl.summary(fl.reduce(fl.run(args.steps, args.warmup, e2e=True)), peak)
+            if fbal:
+                extra["fast_field"]["slab_balance"] = fbal
             extra["fast_field"]["note"] = ("GCB_OPT_FAST_FIELD: |c_h| cos(phi_h + arg c_h) with MUFU.COS + packed-fp32 lerps; field within sum|c_h| (ulp(phi)/2 + 4e-6) "
                                            "of the exact field, extraction bit-exact on that field (tests/test_gpu_parity.py::test_svl_field_fast_mode)")
             fl.free()
@@ -507,6 +534,7 @@ def main():
             "field_mode": "fast (GCB_OPT_FAST_FIELD)" if args.fast_field else "exact (field bit-identical to the reference kernels)",
             "triangles_per_s": (red["g_tot"] / 3) / (ms * 1e-3), "triangles": red["g_tot"] // 3, "active_voxels": red["g_act"],
             "per_rank_vertices": red["per_rank_verts"],
+            "slab_balance": balance,
             "e2e": {"value": points / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(phi_elems * 4 * world), "d2h_bytes_per_step": int((16 + 8) * world),
                     "mode": ("two-deep job pipeline (gcb_svl_lattice_host_submit / _wait): every step copies its control grids from pinned host memory and "

@@ -33,6 +33,39 @@ def validate_slabs(gnz, world, align=2):
         raise ValueError("z-slab sharding: %d point layers over %d ranks (alignment %d) leaves ranks %s without a cell layer" % (gnz, world, align, empty))
 
 
+def balanced_cuts(gnz, world, cuts, verts_per_rank, cost_per_point, cost_per_vertex, points_per_layer, align=2):
+    """Slab cuts that equalise the estimated cost per rank instead of the number of layers.  `cuts` (world + 1 cell-layer boundaries)
+    is the partition the counts were taken on and `verts_per_rank` its vertex counts (one count-only pass + the all-gather of the
+    counts); inside a measured slab the vertices are taken as spread evenly over its layers.  cost(layer) = cost_per_point *
+    points_per_layer + cost_per_vertex * vertices(layer).  Pure function of its arguments: every rank computes the same cuts.
+    Interior cuts are multiples of `align`, every slab keeps at least `align` cell layers."""
+    cells = gnz - 1
+    if world == 1:
+        return [0, cells]
+    layer_cost = []
+    for r in range(world):
+        n = cuts[r + 1] - cuts[r]
+        per_layer = cost_per_point * points_per_layer + cost_per_vertex * (verts_per_rank[r] / max(n, 1))
+        layer_cost += [per_layer] * n
+    total = sum(layer_cost)
+    out, acc, z = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while z < cells and acc + layer_cost[z] <= target:
+            acc += layer_cost[z]
+            z += 1
+        # nearest multiple of align to the (fractional) crossing point, kept monotone with room for the remaining ranks
+        frac = (target - acc) / layer_cost[z] if z < cells else 0.0
+        c = int(round((z + frac) / align)) * align
+        c = max(c, out[-1] + align)
+        c = min(c, cells - align * (world - r))
+        out.append(c)
+    out.append(cells)
+    if any(b - a < align for a, b in zip(out[:-1], out[1:])):
+        return list(cuts)   # degenerate (fewer layers than ranks * align): keep the partition that was given
+    return out
+
+
 def control_slab(z0, z1, ratio, czg):
     """Control-grid planes [c0, c1] a fine slab holding point layers z0..z1 samples (trilinear: floor(z/ratio) and +1)."""
     c0 = z0 // ratio

@@ -237,3 +237,29 @@ def test_cpp_slab_bounds_equal_the_python_ones():
         c0, c1 = C.c_int(0), C.c_int(0)
         assert lib.gcb_control_slab(z0, z1, ratio, czg, C.byref(c0), C.byref(c1)) == 0
         assert (c0.value, c1.value) == sharding.control_slab(z0, z1, ratio, czg)
+
+
+def test_balanced_cuts_equalise_cost_and_stay_valid():
+    """sharding.balanced_cuts: with vertex counts that vary 1.5x between the outer and inner slabs (the bench lattice at N = 8), the
+    re-cut partition's estimated cost per rank is within a few percent of the mean, cuts are aligned, monotone and cover the grid."""
+    gnz, world = 4096, 8
+    eq = [sharding.slab_bounds(gnz, world, r)[0] for r in range(world)] + [gnz - 1]
+    verts = [266272662, 222891732, 184530948, 173026026, 172751532, 184811874, 222420294, 265232904]
+    ppl = 512 * 512
+    for (a, b) in ((7.8e-8, 0.9e-8), (2.4e-8, 0.9e-8), (0.0, 1.0)):
+        cuts = sharding.balanced_cuts(gnz, world, eq, verts, a, b, ppl)
+        assert cuts[0] == 0 and cuts[-1] == gnz - 1 and len(cuts) == world + 1
+        assert all(c % 2 == 0 for c in cuts[1:-1]) and all(y - x >= 2 for x, y in zip(cuts[:-1], cuts[1:]))
+
+        def cost(lo, hi):   # the model the function itself uses: vertices spread evenly inside each measured slab
+            t = 0.0
+            for r in range(world):
+                ov = max(0, min(hi, eq[r + 1]) - max(lo, eq[r]))
+                t += ov * (a * ppl + b * verts[r] / (eq[r + 1] - eq[r]))
+            return t
+        costs = [cost(cuts[r], cuts[r + 1]) for r in range(world)]
+        before = [cost(eq[r], eq[r + 1]) for r in range(world)]
+        assert max(costs) / (sum(costs) / world) < 1.02
+        assert max(costs) <= max(before) + 1e-9
+    assert sharding.balanced_cuts(100, 1, [0, 99], [5], 1, 1, 10) == [0, 99]
+    assert sharding.balanced_cuts(9, 4, [0, 2, 4, 6, 8], [1, 100, 1, 1], 0.0, 1.0, 4) == [0, 2, 4, 6, 8]   # no room to move: unchanged
