@@ -263,3 +263,42 @@ def test_balanced_cuts_equalise_cost_and_stay_valid():
         assert max(costs) <= max(before) + 1e-9
     assert sharding.balanced_cuts(100, 1, [0, 99], [5], 1, 1, 10) == [0, 99]
     assert sharding.balanced_cuts(9, 4, [0, 2, 4, 6, 8], [1, 100, 1, 1], 0.0, 1.0, 4) == [0, 2, 4, 6, 8]   # no room to move: unchanged
+
+
+def _balanced_worker(rank, world, port, out):
+    """bench.py's balanced_leg in miniature: count on the even cut, all-gather, re-cut by estimated cost, extract on the new cut."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    f = _field()
+    lo, hi = orc.minmax(f)   # the global range (the all-reduce itself is covered by the test above)
+    even = [sharding.slab_bounds(N, world, r)[0] for r in range(world)] + [N - 1]
+    r0 = _band_raw_slab(np.ascontiguousarray(f[even[rank]:even[rank + 1] + 1]), even[rank], N, lo, hi)
+    per_rank, _, _, _ = sharding.gather_counts(dist, r0["active"], r0["total"])
+    cuts = sharding.balanced_cuts(N, world, even, [v for (_, v) in per_rank], 1e-3, 1.0, N * N)
+    z0, z1 = cuts[rank], cuts[rank + 1]
+    r = _band_raw_slab(np.ascontiguousarray(f[z0:z1 + 1]), z0, N, lo, hi)
+    per_rank2, voff, aoff, totals = sharding.gather_counts(dist, r["active"], r["total"])
+    np.savez(os.path.join(out, "bal%d.npz" % rank), pos=r["pos"][:r["total"]], norm=r["norm"][:r["total"]], voff=voff[rank], totals=np.array(totals),
+             cuts=np.array(cuts), even=np.array(even), before=np.array([v for (_, v) in per_rank]), after=np.array([v for (_, v) in per_rank2]))
+    dist.destroy_process_group()
+
+
+def test_cost_balanced_slabs_still_concatenate_to_the_single_rank_mesh(tmp_path):
+    world = 3
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_balanced_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    f = _field()
+    lo, hi = orc.minmax(f)
+    single = _band_raw_slab(f, 0, N, lo, hi)
+    parts = [np.load(os.path.join(str(tmp_path), "bal%d.npz" % r)) for r in range(world)]
+    t = single["total"]
+    assert all(np.array_equal(p["cuts"], parts[0]["cuts"]) for p in parts)          # every rank derived the same cuts
+    assert tuple(parts[0]["totals"]) == (single["active"], t)
+    assert np.array_equal(np.concatenate([p["pos"] for p in parts]).view(np.uint32), single["pos"][:t].view(np.uint32))
+    assert np.array_equal(np.concatenate([p["norm"] for p in parts]).view(np.uint32), single["norm"][:t].view(np.uint32))
+    before, after = parts[0]["before"], parts[0]["after"]
+    assert after.max() <= before.max()                                                  # the heaviest rank did not get heavier
