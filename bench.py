@@ -330,6 +330,12 @@ class SvlLeg:
                "triangles_per_s": (red["g_tot"] / 3) / (red["ms"] * 1e-3), "active_voxels": red["g_act"],
                "field_kernel_ms": red["fld_ms"], "extract_kernel_ms": red["ext_ms"],
                "extraction_hbm_frac": alg_ext / (red["ext_ms"] * 1e-3) / 1e9 / peak}
+        if self.fast:
+            # the fast field kernel's own roof: one MUFU.COS per (point, harmonic) on the XU pipe, 16 lanes per SM and clock
+            ph = float(F) * F * self.nzl * self.NH
+            xu_peak = 16.0 * 148 * 1965e6
+            out["field_xu_roofline"] = {"bound": "XU (MUFU) pipe", "achieved_cos_per_s": ph / (red["fld_ms"] * 1e-3), "peak_cos_per_s": xu_peak,
+                                        "frac": ph / (red["fld_ms"] * 1e-3) / xu_peak, "note": "peak = 16 lanes x 148 SMs x 1965 MHz; ncu: profiles/r02_ncu_svl_field_fast.txt"}
         if red["e2e_ms"] is not None:
             out["e2e"] = {"value": points / (red["e2e_ms"] * 1e-3), "unit": "voxels/s", "ms_per_step": red["e2e_ms"], "blocking_call_ms": red["e2e_blocking_ms"],
                           "h2d_bytes_per_step": int(self.phi.numel() * 4 * self.env["world"]), "d2h_bytes_per_step": int((16 + 8) * self.env["world"])}
