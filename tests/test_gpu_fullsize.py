@@ -216,3 +216,43 @@ def test_config3_svl_lattice_512_vs_reference_kernels(ctx, spectrum):
     assert_bits_equal(mesh.norm[:tot], mesh2.norm[:tot], "config 3 (%s) norm" % spectrum)
     del mesh, mesh2, scr2, svl, svl2, mask2, k2, zeros
     _free()
+
+
+@needs_ref
+def test_config3_fast_field_mode_512(ctx):
+    """GCB_OPT_FAST_FIELD on the bench workload at full size: the field stays within the stated tolerance of the default (reference-
+    identical) field, and the mesh extracted from THAT field is what the reference's own kernels extract from it, bit for bit --
+    north_star's contract (topology bit-exact given the same fp32 field)."""
+    F, R, NH = 512, 4, 62
+    c, coef, phi = _config3_inputs(F, R, NH)
+    d = (1.0 / R,) * 3
+    n = F ** 3
+    dims = (F, F, F)
+    exact, fast = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    g.svl_field(ctx, exact, phi, coef, (c, c, c), dims, d)
+    fctx = g.Context(0, options=_capi.GCB_OPT_LEGACY_MEMSET | _capi.GCB_OPT_FAST_FIELD)
+    try:
+        probe = g.MeshBuffers(3)
+        a0, t0, mm = g.svl_lattice(fctx, fast, phi, coef, (c, c, c), dims, d, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, d, (0, 0, 0), probe.pos, probe.norm, 3)
+        cap = t0 + 3
+        mesh = g.MeshBuffers(cap)
+        act, tot, _ = g.svl_lattice(fctx, fast, phi, coef, (c, c, c), dims, d, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, d, (0, 0, 0), mesh.pos, mesh.norm, cap)
+    finally:
+        fctx.close()
+    # tolerance: sum_h |c_h| (ulp(max |phi_h|) / 2 + 4e-6)   (include/gpucad_b200.h, GCB_OPT_FAST_FIELD)
+    amax = phi.abs().amax(dim=(1, 2, 3)).cpu().numpy()
+    bound = float(sum(np.hypot(cf[0], cf[1]) * (0.5 * float(np.spacing(np.float32(a))) + 4e-6) for cf, a in zip(coef, amax)))
+    err = float((fast.double() - exact.double()).abs().max())
+    print("512^3 fast field: max |fast - exact| = %.3g (bound %.3g); %d triangles" % (err, bound, tot // 3))
+    assert 0.0 < err <= bound
+    del exact
+    mask2, k2, zeros = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    ref.normalise_four(fast, mask2, k2, dims, cases.BAND_LO, cases.BAND_HI)
+    scr2, mesh2 = g.Scratch((F - 1) ** 3), g.MeshBuffers(cap)
+    a2, t2 = ref.isosurface_lattice(False, True, mask2, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, d, (0, 0, 0), scr2, cap, k2, zeros, cases.BAND_LO, cases.BAND_HI,
+                                    0.0, 0.0)
+    assert (act, tot) == (a2, t2) and tot > 100000000
+    assert_bits_equal(mesh.pos[:tot], mesh2.pos[:tot], "fast field 512^3: pos vs reference kernels on the same field")
+    assert_bits_equal(mesh.norm[:tot], mesh2.norm[:tot], "fast field 512^3: norm")
+    del mesh, mesh2, scr2, mask2, k2, zeros, fast
+    _free()
