@@ -43,11 +43,17 @@ struct Multi {
     std::vector<float*> d_mm_local;   // per rank: {min, max} of its slab (decoded floats)
     std::vector<float*> d_ab;         // per rank: global {min, max}
     std::vector<unsigned long long*> h_totals;  // per rank, pinned: {active, vertices}
+    float* h_mm = nullptr;                      // pinned: global {min, max} for the caller
     std::string err;
     float last_ms = -1.f;
 };
 
 static int mfail(Multi* m, const std::string& s) { m->err = s; return 1; }
+struct DeviceGuard {  // a sharded call hops between devices: leave the caller's current device as it was, on every exit path
+    int prev = -1;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 #define MCK(m, call)                                                                                         \
     do {                                                                                                     \
         cudaError_t e_ = (call);                                                                             \
@@ -145,6 +151,7 @@ int gcb_multi_destroy(gcb_multi* mm) {
         cudaFree(m->d_mm_local[r]); cudaFree(m->d_ab[r]);
         if (m->h_totals[r]) cudaFreeHost(m->h_totals[r]);
     }
+    if (m->h_mm) cudaFreeHost(m->h_mm);
     cudaSetDevice(prev);
     delete m;
     return 0;
@@ -184,8 +191,7 @@ int gcb_multi_svl_lattice(gcb_multi* mm, float* const* d_svl, const float* const
     Multi* m = reinterpret_cast<Multi*>(mm);
     if (!m) return 1;
     if (!d_svl || !d_phi || !cz_local || !cz0 || (!count_only && (!pos || !norm || !max_verts))) return mfail(m, "multi_svl_lattice: null argument array");
-    int prev = 0;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;
     std::vector<unsigned> z0(m->n), z1(m->n);
     for (int r = 0; r < m->n; ++r) {
         slab_cut(gnz, m->n, r, 2u, &z0[r], &z1[r]);
@@ -222,18 +228,17 @@ int gcb_multi_svl_lattice(gcb_multi* mm, float* const* d_svl, const float* const
             return mfail(m, std::string("multi_svl_lattice rank ") + std::to_string(r) + ": " + gcb_last_error(m->ctx[r]));
         MCK(m, cudaEventRecord(m->ev_t1[r], m->stream[r]));
     }
-    float* h_mm = nullptr;
     if (minmax_out) {
         MCK(m, cudaSetDevice(m->dev[0]));
-        MCK(m, cudaMallocHost(&h_mm, 16));
-        MCK(m, cudaMemcpyAsync(h_mm, m->d_ab[0], 2 * sizeof(float), cudaMemcpyDeviceToHost, m->stream[0]));
+        if (!m->h_mm) MCK(m, cudaMallocHost(&m->h_mm, 16));
+        MCK(m, cudaMemcpyAsync(m->h_mm, m->d_ab[0], 2 * sizeof(float), cudaMemcpyDeviceToHost, m->stream[0]));
     }
     const int rc = finish(m, active, verts, vert_offsets, nullptr);
+    if (rc) return rc;
     if (count_only && verts)  // count_only reports the vertex count even when it is zero-active (same as gcb_extract_band_raw)
         for (int r = 0; r < m->n; ++r) verts[r] = m->h_totals[r][1];
-    if (h_mm) { minmax_out[0] = h_mm[0]; minmax_out[1] = h_mm[1]; cudaFreeHost(h_mm); }
-    cudaSetDevice(prev);
-    return rc;
+    if (minmax_out) { minmax_out[0] = m->h_mm[0]; minmax_out[1] = m->h_mm[1]; }
+    return 0;
 }
 
 int gcb_multi_computeIsosurface_2(gcb_multi* mm, gcb_grid_points* const* vol_topo, float* const* vol_two, float* const* d_result, gcb_uint3 gridSizeGlobal,
@@ -243,8 +248,7 @@ int gcb_multi_computeIsosurface_2(gcb_multi* mm, gcb_grid_points* const* vol_top
     Multi* m = reinterpret_cast<Multi*>(mm);
     if (!m) return 1;
     if (!vol_two || !pos || !norm || !max_verts) return mfail(m, "multi_computeIsosurface_2: null argument array");
-    int prev = 0;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;
     const unsigned gnz = gridSizeGlobal.z;
     const size_t layer = (size_t)gridSizeGlobal.x * gridSizeGlobal.y;
     std::vector<unsigned> z0(m->n), z1(m->n);
@@ -286,9 +290,7 @@ int gcb_multi_computeIsosurface_2(gcb_multi* mm, gcb_grid_points* const* vol_top
         MCK(m, cudaEventRecord(m->ev_t1[r], m->stream[r]));
     }
     (void)layer;
-    const int rc = finish(m, active, verts, vert_offsets, active_offsets);
-    cudaSetDevice(prev);
-    return rc;
+    return finish(m, active, verts, vert_offsets, active_offsets);
 }
 
 }  // extern "C"

@@ -1811,3 +1811,72 @@ def test_headless_full_workflow_matches_python_driven_calls(ctx, tmp_path):
     p2 = str(tmp_path / "py.obj")
     g.File_output(ctx).file_write_obj(mesh.pos, tot, p2)
     assert open(obj, "rb").read() == open(p2, "rb").read()
+
+
+# ------------------------------------------------------------------ edge cases of the round-2 entry points
+def test_fused_entry_points_empty_and_degenerate_inputs(ctx):
+    """No surface (band outside the field's range, iso above the density), an all-zero field (0/0 normalisation: NaN everywhere, no mask),
+    and the smallest grid: the fused calls report what the legacy sequences report and write nothing."""
+    n = 24
+    vox, cen = (1.0, 1.0, 1.0), (0.0, 0.0, 0.0)
+    mv = max_verts_for((n, n, n))
+    f, mesh = torch.zeros(n ** 3, device="cuda"), g.MeshBuffers(mv)
+    mesh.pos.fill_(-7.0)
+    a, t, rg = g.tpms_lattice(ctx, f, 0, (n, n, n), cases.ISO_MASK, 5.0, 6.0, vox, cen, mesh.pos, mesh.norm, mv)   # k never reaches 5
+    assert (a, t) == (0, 0) and rg[2:] == (0.0, 1.0)
+    assert bool((mesh.pos == -7.0).all())
+    # all-zero raw field
+    z = torch.zeros(n ** 3, device="cuda")
+    a1, t1, mesh1, _ = _legacy_unit_lattice(ctx, z, n, vox, cen, mv)
+    a2, t2, rg2 = g.band_lattice_from_raw(ctx, z, (n, n, n), cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, vox, cen, mesh.pos, mesh.norm, mv)
+    assert (a1, t1) == (a2, t2) == (0, 0)
+    # a field with a NaN: the legacy sequence and the fused call must agree on the counts (NaN compares false everywhere)
+    raw = torch.zeros(n ** 3, device="cuda")
+    g.Fft_lattice(ctx).create_lattice(raw, n, n, n, n ** 3, 0)
+    raw[n * n * 5 + n * 7 + 9] = float("nan")
+    a3, t3, mesh3, _ = _legacy_unit_lattice(ctx, raw, n, vox, cen, mv)
+    mesh4 = g.MeshBuffers(mv)
+    a4, t4, _ = g.band_lattice_from_raw(ctx, raw, (n, n, n), cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, vox, cen, mesh4.pos, mesh4.norm, mv)
+    assert (a3, t3) == (a4, t4)
+    if t3:
+        assert_bits_equal(mesh3.pos[:t3], mesh4.pos[:t3], "NaN field: pos")
+    # density surface: iso above every density value, and a 2 x 2 x 2 fine grid
+    T = cases.TOPO
+    fx, fy, fz = T["fdims"]
+    coarse = dev(cases.topo_coarse(T).reshape(-1))
+    dens = torch.zeros(fx * fy * fz, device="cuda")
+    a5, t5 = g.density_surface(ctx, coarse, T["cdims"], dens, T["fdims"], T["d"], 7.5, T["d"], (0, 0, 0), mesh.pos, mesh.norm, mv)
+    assert (a5, t5) == (0, 0)
+    tiny = dev(np.array([0.1, 0.9], np.float32))
+    d2 = torch.zeros(8, device="cuda")
+    a6, t6 = g.density_surface(ctx, tiny, (2, 1, 1), d2, (2, 2, 2), (0.5, 0.5, 0.5), 0.4, (1, 1, 1), (0, 0, 0), mesh.pos, mesh.norm, mv)
+    scr = g.Scratch(1)
+    a7, t7 = g.Isosurface(ctx).computeIsosurface_2(mesh4.pos, mesh4.norm, 0.4, scr, (2, 2, 2), (1, 1, 1), (0, 0, 0), mv, gp_zeros(8), d2, 0.0, torch.zeros(8, device="cuda"))
+    assert (a6, t6) == (a7, t7)
+
+
+@pytest.mark.parametrize("dims", [(48, 40, 36), (45, 41, 37), (64, 4, 16)], ids=["vec4_rows", "scalar_rows", "short_rows"])
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_copy_parameter_vector_and_scalar_paths_three_way(ctx, dims, dynamic):
+    """classify_copy_Voxel (MarchingCubes_kernel.cu:158-447): rows that are a multiple of four points take the four-points-per-thread kernel,
+    others the scalar one; both against the oracle bit for bit (all three set operations, two passes for the t averaging, plain and
+    `dynamic` = lattice-band variant) and against the reference kernel when the point count is a multiple of 1024."""
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    rng = np.random.RandomState(17)
+    field = dev((rng.rand(n).astype(np.float32) - 0.5) * 2.0)          # crossings of iso 0 everywhere
+    lat = dev(rng.rand(n).astype(np.float32))                          # crossings of the band [0.2, 0.3] everywhere
+    for kw in (dict(obj_union=True), dict(obj_union=False, obj_diff=True), dict(obj_union=False, obj_intersect=True)):
+        start = np.zeros(n, orc.GP_DTYPE)
+        start["val"] = rng.choice(np.array([-1, 1], np.int32), n)
+        mine = gp_from_numpy(start)
+        host = start.copy()
+        for _ in range(2):
+            g.Isosurface(ctx).copy_parameter(0.0, dims, (0.5, 0.5, 0.5), mine, field, lat, dynamic=dynamic, iso1=0.2, iso2=0.3, **kw)
+            orc.copy_parameter(host, field.cpu().numpy(), lat.cpu().numpy(), dims, 0.0, dynamic=dynamic, iso1=0.2, iso2=0.3, **kw)
+        assert np.array_equal(gp_to_numpy(mine).view(np.uint32), host.view(np.uint32)), "copy_parameter %s dynamic=%s vs oracle" % (kw, dynamic)
+        if HAVE_REF and n % 1024 == 0:
+            theirs = gp_from_numpy(start)
+            for _ in range(2):
+                ref.copy_parameter(theirs, field, lat, dims, (0.5, 0.5, 0.5), 0.0, dynamic=dynamic, iso1=0.2, iso2=0.3, **kw)
+            assert torch.equal(mine, theirs), "copy_parameter %s dynamic=%s vs reference" % (kw, dynamic)
