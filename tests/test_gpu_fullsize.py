@@ -1,8 +1,9 @@
 """BASELINE.json configs 1, 2, 3 and 5 at FULL size under `pytest -m gpu`: this library through the C ABI next to the reference's
 own CUDA kernels (oracle/_ref, the unmodified sources) on identical inputs -- counts, stage state and WHOLE vertex / normal
 buffers bit for bit, `.obj` bytes for config 2 -- plus the CPU oracle where it finishes in seconds (128^3).  Config 4 (2048^3)
-does not fit one test box; its single-GPU building block (a 2048-wide slab) is covered by size-independent properties in
-test_gpu_parity.py (slab concatenation) and by bench.py --strong.
+does not fit one test box; its per-rank building block -- a slab of the 2048 x 2048 x 2048 grid with full-width rows -- is compared
+with the reference kernels at the end of this file, slab concatenation is covered in test_gpu_parity.py and the complete grid by
+bench.py on 8 GPUs (profiles/r02_bench_ours_n8.json).
 
 The reference call sequences replayed here: main.cu:4080-4137 (config 1), :3304-3465 + :4695-4778 (config 2), :3904-4037
 (config 3), :3060-3109 (config 5)."""
@@ -255,4 +256,56 @@ def test_config3_fast_field_mode_512(ctx):
     assert_bits_equal(mesh.pos[:tot], mesh2.pos[:tot], "fast field 512^3: pos vs reference kernels on the same field")
     assert_bits_equal(mesh.norm[:tot], mesh2.norm[:tot], "fast field 512^3: norm")
     del mesh, mesh2, scr2, mask2, k2, zeros, fast
+    _free()
+
+
+# ------------------------------------------------------------------ config 4: one z-slab of the 2048^3 SVL lattice (full-width rows)
+@needs_ref
+@pytest.mark.parametrize("z0", [0, 1020])
+def test_config4_slab_2048_wide_vs_reference_kernels(ctx, z0):
+    """The single-GPU building block of BASELINE config 4: a slab of 9 point layers of the 2048 x 2048 x 2048 lattice (control
+    512^3, ratio 4, 62 harmonics), i.e. the wide-row configuration of both kernels (2048-point rows, 4.2 M points per layer) that
+    the 512^3 tests never reach.  The reference's kernels have no slab notion, so they get the matching LOCAL problem: the control
+    planes the slab samples uploaded as their texture, a 2048 x 2048 x 9 grid.  With d = 1/4 the control coordinate (z0 + z) * d
+    minus the control offset is exact in fp32, hence the field must agree bit for bit; the mesh is then extracted from the slab as
+    a free-standing grid by both."""
+    F, R, NH, NZ = 2048, 4, 62, 9
+    cg = F // R
+    d = (1.0 / R,) * 3
+    dims = (F, F, NZ)
+    n = F * F * NZ
+    from gpucadforam_b200 import sharding
+    c0, c1 = sharding.control_slab(z0, z0 + NZ - 1, R, cg)
+    czl = c1 - c0 + 1
+    coef = synth.gyroid_coefficients()[:NH]
+    phi = synth.phase_grids(cg, cg, czl, device="cuda", z0=c0, cz_total=cg, harmonics=synth.HARMONICS[:NH], periods=F / 40.0)
+    svl = torch.empty(n, device="cuda")
+    mm = torch.zeros(2, device="cuda")
+    g.svl_field(ctx, svl, phi, coef, (cg, cg, czl), dims, d, slab=(z0, F), cz0=c0, d_minmax=mm)
+    # reference: local texture of czl planes, local fine grid
+    dcoef = torch.tensor(np.array(coef, np.float32), device="cuda")
+    svl2 = torch.zeros(n, device="cuda")
+    ga = torch.zeros((n, 2), device="cuda")
+    ref.setup_texture(cg, cg, czl)
+    ref.svl_field(svl2, ga, phi, NH, dcoef, (cg, cg, czl), dims, d)
+    ref.delete_texture()
+    del ga
+    assert_bits_equal(svl, svl2, "config 4 slab z0=%d: field" % z0)
+    lo, hi = float(svl2.min()), float(svl2.max())
+    assert (float(mm[0]), float(mm[1])) == (lo, hi)
+    # extraction of the slab as a free-standing 2048 x 2048 x 9 grid
+    probe = g.MeshBuffers(3)
+    a0, t0 = g.extract_band_raw(ctx, svl, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, d, (0, 0, 0), probe.pos, probe.norm, 3, count_only=True)
+    cap = t0 + 3
+    mesh = g.MeshBuffers(cap)
+    act, tot = g.extract_band_raw(ctx, svl, lo, hi, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, dims, d, (0, 0, 0), mesh.pos, mesh.norm, cap)
+    mask2, k2, zeros = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    ref.normalise_four(svl2, mask2, k2, dims, cases.BAND_LO, cases.BAND_HI)
+    scr2, mesh2 = g.Scratch((F - 1) * (F - 1) * (NZ - 1)), g.MeshBuffers(cap)
+    a2, t2 = ref.isosurface_lattice(False, True, mask2, mesh2.pos, mesh2.norm, cases.ISO_MASK, dims, d, (0, 0, 0), scr2, cap, k2, zeros, cases.BAND_LO,
+                                    cases.BAND_HI, 0.0, 0.0)
+    assert (act, tot) == (a0, t0) == (a2, t2) and tot > 1000000
+    assert_bits_equal(mesh.pos[:tot], mesh2.pos[:tot], "config 4 slab z0=%d: pos" % z0)
+    assert_bits_equal(mesh.norm[:tot], mesh2.norm[:tot], "config 4 slab z0=%d: norm" % z0)
+    del mesh, mesh2, scr2, svl, svl2, mask2, k2, zeros, phi
     _free()
