@@ -98,12 +98,14 @@ def test_primitives(ctx, idx):
 
 
 @needs_ref
-def test_rotated_primitives_general_parameters_bit_exact(ctx):
+@pytest.mark.parametrize("dims", [(24, 20, 28), (22, 20, 28)], ids=["four_points_per_thread", "one_point_per_thread"])
+def test_rotated_primitives_general_parameters_bit_exact(ctx, dims):
     """Random centres, Euler angles and sizes (non-dyadic ratios such as cone height / radius): every rotated primitive must
     reproduce the reference kernel bit for bit -- this is what pins the FMA contraction of the rotation rows and of the
-    cone / frustum tails (a cone with height/radius = 2 hides a fused multiply-subtract, 8/5 does not)."""
+    cone / frustum tails (a cone with height/radius = 2 hides a fused multiply-subtract, 8/5 does not).  Rows that are a multiple of
+    four points take the kernels' four-points-per-thread form, other rows the one-point form: both are pinned."""
     rng = np.random.RandomState(17)
-    dims, d = (24, 20, 28), (0.5, 0.5, 0.5)
+    d = (0.5, 0.5, 0.5)
     nx, ny, nz = dims
     n = nx * ny * nz
     m = g.Modelling(ctx)
