@@ -37,15 +37,19 @@ def ctx():
 
 # ------------------------------------------------------------------ fields
 @needs_ref
+@pytest.mark.parametrize("dims", [(33, 33, 33), (64, 48, 40), (10, 12, 9)], ids=["tables_one_point", "tables_four_points", "per_point_kernel"])
 @pytest.mark.parametrize("typ", cases.TPMS_TYPES)
-def test_create_lattice_matches_reference(ctx, typ):
-    n = 33  # odd, not a multiple of anything
-    mine = torch.zeros(n * n * n, device="cuda")
+def test_create_lattice_matches_reference(ctx, typ, dims):
+    """Types 0-3 above 4096 points take the separable kernel (per-axis sinf / cosf tables, fields.cu create_lattice_tab_kernel), one or four
+    points of a row per thread; small grids and types 4-5 the per-point kernel.  33 is odd, not a multiple of anything."""
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    mine = torch.zeros(n, device="cuda")
     theirs = torch.zeros_like(mine)
-    g.Fft_lattice(ctx).create_lattice(mine, n, n, n, n * n * n, typ)
-    ref.create_lattice(theirs, n, n, n, typ)
-    assert_bits_equal(mine, theirs, "create_lattice type %d" % typ)
-    o = orc.create_lattice(n, n, n, typ).reshape(-1)
+    g.Fft_lattice(ctx).create_lattice(mine, nx, ny, nz, n, typ)
+    ref.create_lattice(theirs, nx, ny, nz, typ)
+    assert_bits_equal(mine, theirs, "create_lattice type %d %s" % (typ, dims))
+    o = orc.create_lattice(nx, ny, nz, typ).reshape(-1)
     assert np.allclose(mine.cpu().numpy(), o, rtol=0, atol=4e-6), "oracle TPMS type %d" % typ
 
 
