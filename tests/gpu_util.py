@@ -28,6 +28,13 @@ def gp_from_numpy(a):
     return torch.from_numpy(np.ascontiguousarray(a).view(np.int32).reshape(-1, 4)).cuda()
 
 
+def ref_field_buffer(n):
+    """Output buffer of n floats for a REFERENCE field kernel: several of them (e.g. implicit_pyramid_frustum_kernel, Modelling.cu:555)
+    write without a `tx < size` guard, i.e. up to the end of their last 1024-thread block -- the tail is allocated so that the
+    reference's overrun stays inside this tensor (compute-sanitizer memcheck flags it otherwise)."""
+    return torch.zeros((n + 1023) // 1024 * 1024 + 1024, device="cuda")[:n]
+
+
 def max_verts_for(dims):
     return max(4 * dims[0] * dims[1] * dims[2], 300000)  # main.cu:2850
 

@@ -95,7 +95,7 @@ def test_primitives(ctx, idx):
     scale = max(1.0, float(np.abs(o).max()))
     assert np.allclose(mine.cpu().numpy(), o, rtol=0, atol=2e-5 * scale), "oracle primitive %s: %g" % (name, np.abs(mine.cpu().numpy() - o).max())
     if HAVE_REF:
-        theirs = torch.zeros_like(mine)
+        theirs = ref_field_buffer(n)
         ref_fn(theirs)
         nbad = int((bits(mine) != bits(theirs)).sum())
         assert nbad == 0, "primitive %s: %d of %d words differ from the reference kernel, max %d ulp" % (name, nbad, n, ulp_diff(mine, theirs))
@@ -128,7 +128,7 @@ def test_rotated_primitives_general_parameters_bit_exact(ctx, dims):
              lambda o: ref.pyramid_frustum(o, c, a, s1, s1 / 2, s5, s3, s3 / 3, dims, d)),
         ]
         for name, mine_fn, ref_fn in pairs:
-            mine, theirs = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+            mine, theirs = torch.zeros(n, device="cuda"), ref_field_buffer(n)
             mine_fn(mine)
             ref_fn(theirs)
             nbad = int((bits(mine) != bits(theirs)).sum())
@@ -1716,7 +1716,7 @@ def test_sphere_and_cylinder_tables_bit_exact(ctx, dims, variant):
         assert variant
     d, c = (0.5, 0.25, 0.75), (1.3, -0.7, 2.1)
     m = g.Modelling(ctx)
-    mine, theirs = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    mine, theirs = torch.zeros(n, device="cuda"), ref_field_buffer(n)
     if variant.startswith("sphere"):
         shell = variant == "sphere_shell"
         m.sphere_with_center(mine, c, 7.25, 1.5, nx, ny, nz, *d, shell)
