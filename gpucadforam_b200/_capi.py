@@ -102,6 +102,7 @@ SIGNATURES = {
     "gcb_band_lattice_from_raw": (I, [P, P, Uint3, F, F, F, Float3, Float3, P, P, ULL, P, PULL, PULL, PF]),
     "gcb_tpms_lattice": (I, [P, P, U, Uint3, F, F, F, Float3, Float3, P, P, ULL, P, PULL, PULL, PF]),
     "gcb_density_surface": (I, [P, P, I, I, I, P, I, I, I, F, F, F, F, Float3, Float3, P, P, ULL, P, PULL, PULL]),
+    "gcb_csg_retain_primitive": (I, [P, I, Float3, Float3, PF, I, I, P, P, I, I, I, F, F, F, F, I, I, I]),
     "gcb_svl_lattice_host_submit": (I, [P, I, P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL]),
     "gcb_svl_lattice_host_wait": (I, [P, I, PULL, PULL, PF]),
     "gcb_svl_lattice": (I, [P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),

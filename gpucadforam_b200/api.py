@@ -416,6 +416,30 @@ def density_surface(ctx, d_coarse, cdims, d_density_fine, fdims, d, isoValue, vo
     return act.value, tot.value
 
 
+# kind -> (gcb_primitive_kind, names of the scalar parameters in the order of the primitive's own entry point, name of the aux vector, flag name)
+_PRIM_KINDS = {
+    "sphere": (0, ("radius", "thickness"), None, "shell"),
+    "line": (1, ("radius", "thickness_radial", "thickness_axial"), "axis", "disc"),
+    "cuboid": (2, ("xw", "yw", "zw"), "angles", None),
+    "cuboid_shell": (3, ("xw", "yw", "zw", "thickness"), "angles", None),
+    "torus": (4, ("torus_radius", "circle_radius"), "angles", None),
+    "cone": (5, ("base_radius", "height"), "angles", None),
+    "cone_frustum": (6, ("top_radius", "bottom_radius", "height"), "angles", None),
+    "pyramid_frustum": (7, ("x_base", "x_top", "y_height", "z_base", "z_top"), "angles", None),
+}
+
+
+def csg_retain_primitive(ctx, kind, vol_one, d_field, dims, d, isoValue, obj_union=True, obj_diff=False, obj_intersect=False, center=(0.0, 0.0, 0.0), **kw):
+    """Primitive + Isosurface::copy_parameter in one call (gcb_csg_retain_primitive).  d_field may be None where the primitive is evaluated
+    inside the retain kernel (sphere, cuboid, cuboid_shell on rows that are a multiple of four points)."""
+    code, names, aux_name, flag_name = _PRIM_KINDS[kind]
+    params = (C.c_float * len(names))(*[float(kw[n]) for n in names])
+    aux = kw.get(aux_name, (0.0, 0.0, 0.0)) if aux_name else (0.0, 0.0, 0.0)
+    flag = int(bool(kw.get(flag_name, False))) if flag_name else 0
+    ctx.check(lib().gcb_csg_retain_primitive(ctx._h, code, _f3(center), _f3(aux), params, len(names), flag, _ptr(d_field), _ptr(vol_one), dims[0], dims[1],
+                                             dims[2], d[0], d[1], d[2], isoValue, int(obj_union), int(obj_diff), int(obj_intersect)))
+
+
 def svl_lattice_host_submit(ctx, slot, h_phi, d_phi_scratch, d_svl_scratch, coef, cdims, fdims, d, isoValue, isovalue1, isovalue2, voxelSize, gridcenter, pos,
                             norm, maxVerts):
     """Enqueue one host-input job in pipeline slot 0 / 1 (gcb_svl_lattice_host_submit); returns immediately."""

@@ -290,6 +290,15 @@ int gcb_copy_parameter(gcb_ctx* ctx, unsigned int* voxel_verts, float isoValue, 
     if (r) return r;
     return field_call_end(C);  // the reference wrapper ends in cudaDeviceSynchronize (:458)
 }
+int gcb_csg_retain_primitive(gcb_ctx* ctx, int kind, gcb_float3 center, gcb_float3 aux, const float* params, int nparams, int flag, float* d_field,
+                             gcb_grid_points* vol_one, int Nx, int Ny, int Nz, float dx, float dy, float dz, float isoValue, int obj_union, int obj_diff,
+                             int obj_intersect) {
+    CTX(ctx);
+    int r = k_csg_retain_primitive(C, kind, f3(center), f3(aux), params, nparams, flag, d_field, (GridPoint*)vol_one, Nx, Ny, Nz, dx, dy, dz, isoValue,
+                                   obj_union != 0, obj_diff != 0, obj_intersect != 0);
+    if (r) return r;
+    return field_call_end(C);
+}
 int gcb_patch_topo_field(gcb_ctx* ctx, float* d_vec1, int Nx, int Ny, int Nz, gcb_grid_points* vol_one) {
     CTX(ctx);
     if (int r = k_patch_topo_field(C, d_vec1, Nx, Ny, Nz, (const GridPoint*)vol_one)) return r;

@@ -174,6 +174,8 @@ int k_svl_field(Ctx* c, float* svl, const float* phi, int nh, const float* d_coe
                 unsigned z0, float dx, float dy, float dz, int accumulate, float* d_minmax_raw);
 int k_minmax_init(Ctx* c, float* d_minmax_raw);
 int k_minmax_decode(Ctx* c, float* d_minmax_raw, float* d_out);
+int k_csg_retain_primitive(Ctx* c, int kind, float3 center, float3 aux, const float* params, int nparams, int flag, float* d_field, GridPoint* vol_one, int nx,
+                           int ny, int nz, float dx, float dy, float dz, float iso, bool u, bool d, bool i);
 int k_copy_parameter(Ctx* c, GridPoint* vol_one, const float* vol_two, const float* vol_lattice, bool dynamic, float iso1, float iso2,
                      unsigned nx, unsigned ny, unsigned nz, float iso, bool u, bool d, bool i);
 int k_primitive_field(Ctx* c, const GridPoint* prim, const float* active, float* isosurf, size_t n, bool fixed, bool dynamic);

@@ -314,6 +314,23 @@ int gcb_density_surface(gcb_ctx* ctx, const float* d_coarse, int cx, int cy, int
     float dz, float isoValue, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts,
     unsigned int* d_compVoxelArray, unsigned long long* activeVoxels, unsigned long long* totalVerts);
 
+/* Fused "add primitive" action (BASELINE config 2; Multitopo::show_model, main.cu:3304-3465): Modelling::<primitive>(d_field, ...) followed
+ * by Isosurface::copy_parameter(..., vol_one, d_field, ..., obj_union, obj_diff, obj_intersect) (fixed / dynamic off) as ONE call.  kind:
+ * gcb_primitive_kind; center / aux (Euler angles; the axis for GCB_PRIM_LINE) / flag (shell, disc) and params[] are the primitive's arguments
+ * in the order of its own gcb_* entry point: sphere {radius, thickness}, line {radius, thickness_radial, thickness_axial}, cuboid {x, y, z
+ * width}, cuboid_shell {x, y, z width, thickness}, torus {torus radius, circle radius}, cone {base radius, height}, cone_frustum {top radius,
+ * bottom radius, height}, pyramid_frustum {x base, x top, y height, z base, z top}.  vol_one and (when given) d_field end up bit for bit
+ * as after the two calls.  Sphere and the two cuboids on grids with Nx a multiple of four are evaluated INSIDE the retain kernel (one
+ * pass, no field round trip; d_field may then be NULL = do not store the field); every other case runs the two kernels back to back
+ * and needs d_field. */
+enum gcb_primitive_kind {
+    GCB_PRIM_SPHERE = 0, GCB_PRIM_LINE = 1, GCB_PRIM_CUBOID = 2, GCB_PRIM_CUBOID_SHELL = 3, GCB_PRIM_TORUS = 4, GCB_PRIM_CONE = 5,
+    GCB_PRIM_CONE_FRUSTUM = 6, GCB_PRIM_PYRAMID_FRUSTUM = 7
+};
+int gcb_csg_retain_primitive(gcb_ctx* ctx, int kind, gcb_float3 center, gcb_float3 aux, const float* params, int nparams, int flag,
+    float* d_field, gcb_grid_points* vol_one, int Nx, int Ny, int Nz, float dx, float dy, float dz, float isoValue, int obj_union, int obj_diff,
+    int obj_intersect);
+
 /* Two-deep job pipeline of gcb_svl_lattice_host: _submit only enqueues (H2D copies on the library's copy stream, field,
  * reduction, extraction and the read-back of the counts on the context's stream) and returns; _wait blocks until that slot's job
  * is complete and hands back its counts.  With jobs alternating between slot 0 and slot 1, the control grids of job i+1 cross

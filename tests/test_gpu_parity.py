@@ -5,6 +5,7 @@
 Bar: stage arrays, counts, cube topology bit-exact; vertex positions / normals bit-exact against the
 reference kernels (same compiler, same expression order) and within 1e-5 relative against the oracle.
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -1886,3 +1887,77 @@ def test_copy_parameter_vector_and_scalar_paths_three_way(ctx, dims, dynamic):
             for _ in range(2):
                 ref.copy_parameter(theirs, field, lat, dims, (0.5, 0.5, 0.5), 0.0, dynamic=dynamic, iso1=0.2, iso2=0.3, **kw)
             assert torch.equal(mine, theirs), "copy_parameter %s dynamic=%s vs reference" % (kw, dynamic)
+
+
+# ------------------------------------------------------------------ primitive + retain in one call (gcb_csg_retain_primitive)
+_RETAIN_PRIMS = [
+    ("sphere", dict(radius=7.25, thickness=1.5, shell=False), lambda m, o, c, a, n, d: m.sphere_with_center(o, c, 7.25, 1.5, *n, *d, False)),
+    ("sphere", dict(radius=7.25, thickness=1.5, shell=True), lambda m, o, c, a, n, d: m.sphere_with_center(o, c, 7.25, 1.5, *n, *d, True)),
+    ("cuboid", dict(xw=13.0, yw=7.5, zw=9.0), lambda m, o, c, a, n, d: m.cuboid(o, c, a, 13.0, 7.5, 9.0, *n, *d)),
+    ("cuboid_shell", dict(xw=13.0, yw=7.5, zw=9.0, thickness=1.25), lambda m, o, c, a, n, d: m.cuboid_shell(o, c, a, 13.0, 7.5, 9.0, 1.25, *n, *d)),
+    ("line", dict(radius=4.5, thickness_radial=1.5, thickness_axial=11.0, disc=True, axis=(0.3, -0.2, 0.9)),
+     lambda m, o, c, a, n, d: m.distance_from_line(o, c, (0.3, -0.2, 0.9), 4.5, 1.5, 11.0, *n, *d, True)),
+    ("torus", dict(torus_radius=6.0, circle_radius=2.0), lambda m, o, c, a, n, d: m.torus_with_center(o, c, a, 6.0, 2.0, *n, *d)),
+    ("cone", dict(base_radius=5.0, height=8.0), lambda m, o, c, a, n, d: m.cone_with_base_radius_height(o, c, a, 5.0, 8.0, *n, *d)),
+    ("cone_frustum", dict(top_radius=2.0, bottom_radius=5.0, height=8.0), lambda m, o, c, a, n, d: m.cone_frustum(o, c, a, 2.0, 5.0, 8.0, *n, *d)),
+    ("pyramid_frustum", dict(x_base=8.0, x_top=4.0, y_height=7.0, z_base=6.0, z_top=3.0),
+     lambda m, o, c, a, n, d: m.pyramid_frustum(o, c, a, 8.0, 4.0, 7.0, 6.0, 3.0, *n, *d)),
+]
+
+
+@pytest.mark.parametrize("dims", [(48, 40, 32), (46, 40, 32)], ids=["rows_of_four", "other_rows"])
+@pytest.mark.parametrize("idx", range(len(_RETAIN_PRIMS)))
+def test_csg_retain_primitive_equals_primitive_then_copy_parameter(ctx, idx, dims):
+    """gcb_csg_retain_primitive == Modelling::<primitive> + Isosurface::copy_parameter, bit for bit in the retained state AND in the field it
+    leaves: sphere and the cuboids on rows of four points are evaluated inside the retain kernel (also without a field buffer), every
+    other case runs the two kernels.  Two primitives in a row per set operation, so that the crossing-parameter averaging (fold) and
+    the val logic see a non-trivial state; sphere / cuboid also against the reference's own two kernels."""
+    kind, kw, legacy = _RETAIN_PRIMS[idx]
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    d, c, ang = (0.5, 0.25, 0.75), (1.3, -0.7, 2.1), (0.3, 0.2, -0.4)
+    m, iso = g.Modelling(ctx), g.Isosurface(ctx)
+    zeros = torch.zeros(n, device="cuda")
+    extra = dict(kw)
+    if kind not in ("sphere", "line"):
+        extra["angles"] = ang
+    fast = kind in ("sphere", "cuboid", "cuboid_shell") and nx % 4 == 0
+    for ops in (dict(obj_union=True), dict(obj_union=False, obj_diff=True), dict(obj_union=False, obj_intersect=True)):
+        a_state, b_state, c_state = gp_zeros(n), gp_zeros(n), gp_zeros(n)
+        fa, fb = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        # a first solid in all three states so that the second operation has something to combine with
+        for st in (a_state, b_state, c_state):
+            m.sphere_with_center(fa, (0.0, 0.0, 0.0), 9.0, 1.0, nx, ny, nz, *d, False)
+            iso.copy_parameter(0.0, dims, d, st, fa, zeros, obj_union=True)
+        legacy(m, fa, c, ang, (nx, ny, nz), d)
+        iso.copy_parameter(0.0, dims, d, a_state, fa, zeros, **ops)
+        g.csg_retain_primitive(ctx, kind, b_state, fb, dims, d, 0.0, center=c, **ops, **extra)
+        assert torch.equal(a_state, b_state), "%s %s %s: retained state differs from the two calls" % (kind, kw, ops)
+        assert_bits_equal(fa, fb, "%s %s: field left by the fused call" % (kind, ops))
+        if fast:
+            g.csg_retain_primitive(ctx, kind, c_state, None, dims, d, 0.0, center=c, **ops, **extra)
+            assert torch.equal(a_state, c_state), "%s %s: state without a field buffer" % (kind, ops)
+        else:
+            with pytest.raises(RuntimeError):
+                g.csg_retain_primitive(ctx, kind, c_state, None, dims, d, 0.0, center=c, **ops, **extra)
+        if HAVE_REF and n % 1024 == 0 and kind in ("sphere", "cuboid"):
+            r_state, fr = gp_zeros(n), ref_field_buffer(n)
+            ref.sphere(fr, (0.0, 0.0, 0.0), 9.0, 1.0, dims, d, False)
+            ref.copy_parameter(r_state, fr, zeros, dims, d, 0.0, obj_union=True)
+            if kind == "sphere":
+                ref.sphere(fr, c, 7.25, 1.5, dims, d, kw["shell"])
+            else:
+                ref.cuboid(fr, c, ang, 13.0, 7.5, 9.0, dims, d)
+            ref.copy_parameter(r_state, fr, zeros, dims, d, 0.0, **ops)
+            assert torch.equal(b_state, r_state), "%s %s: fused call vs the reference's two kernels" % (kind, ops)
+
+
+def test_csg_retain_primitive_argument_errors(ctx):
+    n = 16 * 16 * 16
+    st, f = gp_zeros(n), torch.zeros(n, device="cuda")
+    with pytest.raises(RuntimeError):
+        ctx.check(g.api.lib().gcb_csg_retain_primitive(ctx._h, 9, _capi.Float3(0, 0, 0), _capi.Float3(0, 0, 0), (C.c_float * 2)(1, 1), 2, 0, f.data_ptr(), st.data_ptr(),
+                                                       16, 16, 16, 1.0, 1.0, 1.0, 0.0, 1, 0, 0))
+    with pytest.raises(RuntimeError):   # a cuboid needs three widths
+        ctx.check(g.api.lib().gcb_csg_retain_primitive(ctx._h, 2, _capi.Float3(0, 0, 0), _capi.Float3(0, 0, 0), (C.c_float * 2)(1, 1), 2, 0, f.data_ptr(), st.data_ptr(),
+                                                       16, 16, 16, 1.0, 1.0, 1.0, 0.0, 1, 0, 0))
