@@ -203,6 +203,26 @@ public:
 
 class Gratings : public Interpolations {
 public:
+    int NX = 0, NY = 0, NZ = 0;  // set by the application before the phase solve (main.cu:4182-4186), read by GPUCG_lattice
+    // SVL phase solve (Gratings.h:31-41): period / rotation fields, right-hand side of one harmonic, conjugate gradients
+    void angle_data(float* d_theta, int NX_, int NY_, int NZ_, float dx, float dy, float dz, float mean_x, float mean_y, float mean_z, char axis) {
+        gpucad::check(gcb_angle_data(gpucad::ctx(), d_theta, NX_, NY_, NZ_, dx, dy, dz, mean_x, mean_y, mean_z, axis), "angle_data");
+    }
+    void period_data(float* d_period, int NX_, int NY_, int NZ_, float dx, float dy, float dz, float mean_x, float mean_y, float mean_z, char axis) {
+        gpucad::check(gcb_period_data(gpucad::ctx(), d_period, NX_, NY_, NZ_, dx, dy, dz, mean_x, mean_y, mean_z, axis), "period_data");
+    }
+    void finding_phi(float* d_phi, float* d_period, int x_dim, int y_dim, int z_dim, int i, int j, int k, float dx, float dy, float dz, char latticetype_one,
+                     int unform_type, float const_peirod, float x_period, float y_period, float z_period, float lcon, float lcon_1, bool sinewave_zaxis) {
+        gpucad::check(gcb_finding_phi(gpucad::ctx(), d_phi, d_period, x_dim, y_dim, z_dim, i, j, k, dx, dy, dz, latticetype_one, unform_type, const_peirod, x_period,
+                                      y_period, z_period, lcon, lcon_1, sinewave_zaxis),
+                      "finding_phi");
+    }
+    void GPUCG_lattice(float* d_phi, const int iter, const int OptIter, const float EndRes, int& FinalIter, float& FinalRes) {
+        gpucad::check(gcb_GPUCG_lattice(gpucad::ctx(), d_phi, NX, NY, NZ, iter, OptIter, EndRes, &FinalIter, &FinalRes), "GPUCG_lattice");
+    }
+    void GPU_buffer_normalise_three(float* dataone, float* datatwo, size_t size, float a1, float b1) {
+        gpucad::check(gcb_GPU_buffer_normalise_three(gpucad::ctx(), dataone, datatwo, size, a1, b1), "GPU_buffer_normalise_three");
+    }
     void GPU_buffer_normalise_buffer(float* d_vec1, float* d_vec2, int n) { gpucad::check(gcb_GPU_buffer_normalise_buffer(gpucad::ctx(), d_vec1, d_vec2, n), "GPU_buffer_normalise_buffer"); }
     void GPU_buffer_normalise_four(float* dataone, float* datatwo, float* datathree, size_t size, int Nx, int Ny, int Nz, float isoval_1, float isoval_2) {
         gpucad::check(gcb_GPU_buffer_normalise_four(gpucad::ctx(), dataone, datatwo, datathree, size, Nx, Ny, Nz, isoval_1, isoval_2), "GPU_buffer_normalise_four");

@@ -204,8 +204,9 @@ static int full_workflow(int N, const char* obj) {
     std::vector<float> spec(250);
     CK(cudaMemcpy(spec.data(), d_spec, 250 * 4, cudaMemcpyDeviceToHost));
     cudaEventRecord(ev[1]);
-    gpucad::check(gcb_period_data(ctx, d_period, C, C, C, 1.f, 1.f, 1.f, C / 2.0f, C / 2.0f, C / 2.0f, 'z'), "period_data");
-    gpucad::check(gcb_GPU_buffer_normalise_three(ctx, d_period, d_period, nc, (float)(C / 10), (float)(C / 4)), "normalise_three");
+    Gratings latt;  // the reference's own two calls (main.cu:3927-3931), through the host mirror
+    latt.period_data(d_period, C, C, C, 1.f, 1.f, 1.f, C / 2.0f, C / 2.0f, C / 2.0f, 'z');
+    latt.GPU_buffer_normalise_three(d_period, d_period, nc, (float)(C / 10), (float)(C / 4));
     cudaEventRecord(ev[2]);
     std::vector<int> fi(NH);
     std::vector<float> fr(NH);
