@@ -14,7 +14,8 @@ One step = control grids resident in HBM -> field -> min/max (stays in device me
 `value` is voxels (grid points) per second over all ranks, DEFAULT library mode (field bit-identical to the reference kernels).
 `e2e` is the same workload with HOST control grids, every step copying them H2D inside the timed region and reading its counts back:
 on one GPU through the two-deep job pipeline (gcb_svl_lattice_host_submit / _wait; `e2e.blocking_call` = one blocking call per
-step), on N > 1 one blocking sequence per step and rank, with `e2e.h2d_probe` naming the host-side limiter by measurement.
+step), on N > 1 through the same pipeline in two halves per job (gcb_svl_slab_host_submit_field / _submit_extract around the
+stream-ordered NCCL all-reduce of the range), with `e2e.h2d_probe` naming the host-side limiter by measurement.
 `roofline` describes the kernel that dominates the step, `roofline_other_kernel` the other one: the SVL field kernel (writes 4 B /
 point: nothing to stream, bound by instruction issue -- reported with the HBM figure the contract asks for AND its actual limiter) and
 the fused extraction kernel (HBM-bound: 4 B/point + 32 B/vertex); both timed with CUDA events on the library's stream in the timed steps.
@@ -233,18 +234,34 @@ class SvlLeg:
         return g.extract_band_raw_dev(self.ctx, self.svl, ab, ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap,
                                       slab=(self.z0, self.gnz))
 
+    def ctx_on_torch_stream(self):
+        """The sharded pipeline orders the library's kernels and NCCL's all-reduce on ONE stream: the context was created on the legacy
+        default stream, which is torch's current stream unless somebody switched it."""
+        return self.env["torch"].cuda.current_stream().cuda_stream == 0
+
     def e2e_pipelined(self, steps):
-        """`steps` jobs through the two-deep job pipeline (gcb_svl_lattice_host_submit / _wait): every job copies its control grids from
-        pinned host memory and has its counts read back; job i+1's copies overlap job i's kernels.  Single GPU.  Returns the results."""
-        g, torch = self.env["g"], self.env["torch"]
+        """`steps` jobs through the two-deep job pipeline: every job copies its control grids from pinned host memory and has its counts read
+        back; job i+1's copies overlap job i's kernels.  One rank: gcb_svl_lattice_host_submit / _wait.  Several ranks: the job is enqueued in
+        two halves (gcb_svl_slab_host_submit_field / _submit_extract) with the 2-float NCCL all-reduce of the range between them, all
+        stream-ordered -- the host only waits for the counts of the job before last.  Returns the results."""
+        g, torch, sharding = self.env["g"], self.env["torch"], self.env["sharding"]
         cd = self._host_buffers()
         if not hasattr(self, "phi_scratch2") or self.phi_scratch2 is None:
             self.phi_scratch2 = torch.empty_like(self.phi)
+            self.mm2 = [torch.zeros(2, device=self.env["dev"]) for _ in range(2)]
         scr = [self.phi_scratch, self.phi_scratch2]
+        ab = [None, None]   # keeps the reduced range of each slot's job alive until that job is done
 
         def submit(i):
-            g.svl_lattice_host_submit(self.ctx, i % 2, self.hphi, scr[i % 2], self.svl, self.coef, cd, self.ldims, self.d, ISO_MASK, BAND_LO, BAND_HI, self.d,
-                                      (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap)
+            if self.env["world"] == 1:
+                g.svl_lattice_host_submit(self.ctx, i % 2, self.hphi, scr[i % 2], self.svl, self.coef, cd, self.ldims, self.d, ISO_MASK, BAND_LO, BAND_HI, self.d,
+                                          (0.0, 0.0, 0.0), self.mesh.pos, self.mesh.norm, self.cap)
+                return
+            sl = i % 2
+            g.svl_slab_host_submit_field(self.ctx, sl, self.hphi, scr[sl], self.svl, self.coef, cd, self.ldims, self.d, (self.z0, self.gnz), self.c0, self.mm2[sl])
+            ab[sl] = sharding.allreduce_minmax_device(self.env["dist"], self.mm2[sl])
+            g.svl_slab_host_submit_extract(self.ctx, sl, self.svl, ab[sl], ISO_MASK, BAND_LO, BAND_HI, self.ldims, self.d, (0.0, 0.0, 0.0), self.mesh.pos,
+                                           self.mesh.norm, self.cap, slab=(self.z0, self.gnz))
         res = []
         submit(0)
         for i in range(1, steps):
@@ -293,7 +310,7 @@ class SvlLeg:
             e1.record()
             env["barrier"]()
             out["e2e_ms"] = out["e2e_blocking_ms"] = e0.elapsed_time(e1) / steps
-            if env["world"] == 1:
+            if env["world"] == 1 or self.ctx_on_torch_stream():
                 assert all(r == (self.act, self.tot) for r in self.e2e_pipelined(3))
                 env["barrier"]()
                 e0.record()
@@ -301,6 +318,7 @@ class SvlLeg:
                 e1.record()
                 env["barrier"]()
                 out["e2e_ms"] = e0.elapsed_time(e1) / steps
+                out["e2e_pipelined"] = True
         return out
 
     def reduce(self, r):
@@ -559,9 +577,11 @@ def main():
                     "h2d_bytes_per_step": int(phi_elems * 4 * world), "d2h_bytes_per_step": int((16 + 8) * world),
                     "mode": ("two-deep job pipeline (gcb_svl_lattice_host_submit / _wait): every step copies its control grids from pinned host memory and "
                              "reads its counts back; step i+1's copies overlap step i's kernels") if world == 1 else
+                            ("two-deep job pipeline per rank (gcb_svl_slab_host_submit_field -> NCCL all-reduce of the range, stream-ordered -> "
+                             "gcb_svl_slab_host_submit_extract; _wait one job later): step i+1's copies overlap step i's kernels") if raw.get("e2e_pipelined") else
                             "one blocking sequence per step and rank (host control grids -> field -> NCCL min/max on the device -> extraction -> counts)",
                     "blocking_call": {"ms_per_step": red["e2e_blocking_ms"], "value": points / (red["e2e_blocking_ms"] * 1e-3),
-                                      "note": "gcb_svl_lattice_host, one call per step, nothing overlapped across steps"},
+                                      "note": "one blocking call sequence per step, nothing overlapped across steps"},
                     "note": "control grids copied from pinned host memory each step; counts and min/max read back; the mesh stays in device memory "
                             "as in the reference (Vulkan-exported vertex buffers)",
                     "host_cpus_bound_rank0": affinity},

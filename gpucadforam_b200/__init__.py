@@ -10,7 +10,7 @@ Importing the package without the built library raises ImportError -- there is n
 """
 from . import _capi
 from .api import (Context, Isosurface, Modelling, Fft_lattice, Gratings, File_output, MeshBuffers, Scratch,
-                  svl_lattice, svl_lattice_host, svl_lattice_host_submit, svl_lattice_host_wait, extract_band_raw, extract_band_raw_dev, band_lattice_from_raw, tpms_lattice, density_surface, csg_retain_primitive, svl_field, svl_field_host, minmax, unit_lattice_spectrum, finding_phi, GPUCG_lattice, svl_phase_solve)
+                  svl_lattice, svl_lattice_host, svl_lattice_host_submit, svl_lattice_host_wait, svl_slab_host_submit_field, svl_slab_host_submit_extract, extract_band_raw, extract_band_raw_dev, band_lattice_from_raw, tpms_lattice, density_surface, csg_retain_primitive, svl_field, svl_field_host, minmax, unit_lattice_spectrum, finding_phi, GPUCG_lattice, svl_phase_solve)
 
 __all__ = ["Context", "Isosurface", "Modelling", "Fft_lattice", "Gratings", "File_output", "MeshBuffers", "Scratch",
-           "svl_lattice", "svl_lattice_host", "svl_lattice_host_submit", "svl_lattice_host_wait", "extract_band_raw", "extract_band_raw_dev", "band_lattice_from_raw", "tpms_lattice", "density_surface", "csg_retain_primitive", "svl_field", "svl_field_host", "minmax", "unit_lattice_spectrum", "finding_phi", "GPUCG_lattice", "svl_phase_solve", "_capi"]
+           "svl_lattice", "svl_lattice_host", "svl_lattice_host_submit", "svl_lattice_host_wait", "svl_slab_host_submit_field", "svl_slab_host_submit_extract", "extract_band_raw", "extract_band_raw_dev", "band_lattice_from_raw", "tpms_lattice", "density_surface", "csg_retain_primitive", "svl_field", "svl_field_host", "minmax", "unit_lattice_spectrum", "finding_phi", "GPUCG_lattice", "svl_phase_solve", "_capi"]

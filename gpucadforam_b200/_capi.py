@@ -105,6 +105,8 @@ SIGNATURES = {
     "gcb_csg_retain_primitive": (I, [P, I, Float3, Float3, PF, I, I, P, P, I, I, I, F, F, F, F, I, I, I]),
     "gcb_svl_lattice_host_submit": (I, [P, I, P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL]),
     "gcb_svl_lattice_host_wait": (I, [P, I, PULL, PULL, PF]),
+    "gcb_svl_slab_host_submit_field": (I, [P, I, P, P, P, I, PF, I, I, I, I, I, I, I, Slab, F, F, F, P]),
+    "gcb_svl_slab_host_submit_extract": (I, [P, I, P, P, F, F, F, Uint3, Slab, Float3, Float3, P, P, ULL]),
     "gcb_svl_lattice": (I, [P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),
     "gcb_svl_lattice_host": (I, [P, P, P, P, I, PF, I, I, I, I, I, I, F, F, F, F, F, F, Float3, Float3, P, P, ULL, PULL, PULL, PF]),
     "gcb_multi_create": (I, [C.POINTER(P), I, C.POINTER(I)]),

@@ -449,6 +449,21 @@ def svl_lattice_host_submit(ctx, slot, h_phi, d_phi_scratch, d_svl_scratch, coef
                                                 isovalue1, isovalue2, _f3(voxelSize), _f3(gridcenter), _ptr(pos), _ptr(norm), maxVerts))
 
 
+def svl_slab_host_submit_field(ctx, slot, h_phi, d_phi_scratch, d_svl_scratch, coef, cdims, fdims, d, slab, cz0, d_minmax):
+    """First half of a sharded pipeline job (gcb_svl_slab_host_submit_field): upload + field of this rank's slab, local {min, max} -> d_minmax."""
+    assert not h_phi.is_cuda and h_phi.is_contiguous()
+    ctx.check(lib().gcb_svl_slab_host_submit_field(ctx._h, int(slot), C.c_void_p(h_phi.data_ptr()), _ptr(d_phi_scratch), _ptr(d_svl_scratch), len(coef),
+                                                   _coef_array(coef), cdims[0], cdims[1], cdims[2], cz0, fdims[0], fdims[1], fdims[2], Slab(slab[0], slab[1] or fdims[2]),
+                                                   d[0], d[1], d[2], _ptr(d_minmax)))
+
+
+def svl_slab_host_submit_extract(ctx, slot, d_svl_scratch, d_ab, isoValue, isovalue1, isovalue2, gridSizeLocal, voxelSize, gridcenter, pos, norm, maxVerts,
+                                 slab=(0, 0)):
+    """Second half (gcb_svl_slab_host_submit_extract): extraction with the range over all ranks read from d_ab; svl_lattice_host_wait completes it."""
+    ctx.check(lib().gcb_svl_slab_host_submit_extract(ctx._h, int(slot), _ptr(d_svl_scratch), _ptr(d_ab), isoValue, isovalue1, isovalue2, _u3(gridSizeLocal),
+                                                     Slab(slab[0], slab[1] or gridSizeLocal[2]), _f3(voxelSize), _f3(gridcenter), _ptr(pos), _ptr(norm), maxVerts))
+
+
 def svl_lattice_host_wait(ctx, slot):
     """Block until the job in `slot` is complete: (activeVoxels, totalVerts, (min, max))."""
     act, tot = C.c_ulonglong(0), C.c_ulonglong(0)

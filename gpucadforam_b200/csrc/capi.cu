@@ -769,7 +769,7 @@ int gcb_svl_lattice_host_submit(gcb_ctx* ctx, int slot, const float* h_phi, floa
     CTX(ctx);
     if (slot < 0 || slot > 1) return fail_msg(C, "svl_lattice_host_submit: slot must be 0 or 1");
     Ctx::Slot& S = C->slot[slot];
-    if (S.busy) return fail_msg(C, "svl_lattice_host_submit: slot still holds an unfinished job (call gcb_svl_lattice_host_wait first)");
+    if (S.busy || S.field_pending) return fail_msg(C, "svl_lattice_host_submit: slot still holds an unfinished job (call gcb_svl_lattice_host_wait first)");
     if (int r = slot_init(C, S)) return r;
     gcb_slab slab{0u, (unsigned)NZ2};
     // the control grids of this job are copied while the previous job (other slot, other scratch) computes: the copy stream only
@@ -784,6 +784,40 @@ int gcb_svl_lattice_host_submit(gcb_ctx* ctx, int slot, const float* h_phi, floa
                                       nullptr, 0, nullptr, nullptr, S.h_totals))
         return r;
     GCB_CHECK(C, cudaEventRecord(S.job_done, C->stream));
+    S.busy = true;
+    return 0;
+}
+// The same pipeline for one z-slab of a sharded job: the range of the whole field only exists after an exchange between the ranks, so the
+// job is enqueued in two halves with the caller's (stream-ordered) reduction in between.
+int gcb_svl_slab_host_submit_field(gcb_ctx* ctx, int slot, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host, int cx,
+                                   int cy, int cz_local, int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_minmax) {
+    CTX(ctx);
+    if (slot < 0 || slot > 1) return fail_msg(C, "svl_slab_host_submit_field: slot must be 0 or 1");
+    if (!d_minmax) return fail_msg(C, "svl_slab_host_submit_field: d_minmax (device float[2]) is required");
+    Ctx::Slot& S = C->slot[slot];
+    if (S.busy || S.field_pending) return fail_msg(C, "svl_slab_host_submit_field: slot still holds an unfinished job");
+    if (int r = slot_init(C, S)) return r;
+    if (int r = svl_field_host_impl(ctx, C, d_svl_scratch, h_phi, d_phi_scratch, nh, coef_host, cx, cy, cz_local, cz0, NX2, NY2, NZ2_local, slab, dx, dy, dz, S.d_minmax,
+                                    d_minmax, S.field_done))
+        return r;
+    GCB_CHECK(C, cudaEventRecord(S.field_done, C->stream));
+    S.field_pending = true;
+    return 0;
+}
+int gcb_svl_slab_host_submit_extract(gcb_ctx* ctx, int slot, const float* d_svl_scratch, const float* d_ab, float isoValue, float isovalue1, float isovalue2,
+                                     gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
+                                     unsigned long long maxVerts) {
+    CTX(ctx);
+    if (slot < 0 || slot > 1) return fail_msg(C, "svl_slab_host_submit_extract: slot must be 0 or 1");
+    if (!d_ab) return fail_msg(C, "svl_slab_host_submit_extract: d_ab (device float[2], the range over all ranks) is required");
+    Ctx::Slot& S = C->slot[slot];
+    if (!S.field_pending) return fail_msg(C, "svl_slab_host_submit_extract: no field submitted in this slot");
+    if (int r = gcb_internal_extract_band_raw(C, d_svl_scratch, 0.f, 0.f, d_ab, isoValue, isovalue1, isovalue2, gridSizeLocal, slab, voxelSize, gridcenter, pos, norm,
+                                              maxVerts, nullptr, 0, nullptr, nullptr, S.h_totals))
+        return r;
+    GCB_CHECK(C, cudaMemcpyAsync(S.h_minmax, d_ab, 2 * sizeof(float), cudaMemcpyDeviceToHost, C->stream));
+    GCB_CHECK(C, cudaEventRecord(S.job_done, C->stream));
+    S.field_pending = false;
     S.busy = true;
     return 0;
 }

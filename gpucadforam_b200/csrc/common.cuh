@@ -121,7 +121,8 @@ struct Ctx {
         float* h_minmax = nullptr;               // pinned: {min, max}
         float* d_minmax = nullptr;               // device: 2 words raw (ordered-int) + 2 floats decoded
         cudaEvent_t field_done = nullptr, job_done = nullptr;
-        bool busy = false;
+        bool busy = false;           // a complete job is enqueued: _wait may be called
+        bool field_pending = false;  // sharded job: the field half is enqueued, the extraction half is not yet
     } slot[2];
 };
 

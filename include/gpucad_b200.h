@@ -342,6 +342,17 @@ int gcb_svl_lattice_host_submit(gcb_ctx* ctx, int slot, const float* h_phi, floa
     int cx, int cy, int cz, int NX2, int NY2, int NZ2, float dx, float dy, float dz, float isoValue, float isovalue1, float isovalue2,
     gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm, unsigned long long maxVerts);
 int gcb_svl_lattice_host_wait(gcb_ctx* ctx, int slot, unsigned long long* activeVoxels, unsigned long long* totalVerts, float* minmax_out);
+/* The job pipeline for ONE z-slab of a sharded lattice (one process per GPU): the normalisation range is the range over ALL ranks, so a
+ * job is enqueued in two halves.  _submit_field: H2D copies of the rank's control planes + field of the slab + its local {min, max} into
+ * d_minmax (device float[2], the caller's).  The caller then reduces d_minmax over the ranks ON THE CONTEXT'S STREAM (e.g. an NCCL
+ * all-reduce, which is stream-ordered: no host synchronisation) into d_ab and calls _submit_extract, which enqueues the extraction with
+ * the range read from d_ab and the read-back of the counts.  gcb_svl_lattice_host_wait(slot) completes the job (minmax_out = the
+ * contents of d_ab).  Arguments as gcb_svl_field_host / gcb_extract_band_raw_dev; the same buffer rules as above. */
+int gcb_svl_slab_host_submit_field(gcb_ctx* ctx, int slot, const float* h_phi, float* d_phi_scratch, float* d_svl_scratch, int nh, const float* coef_host,
+    int cx, int cy, int cz_local, int cz0, int NX2, int NY2, int NZ2_local, gcb_slab slab, float dx, float dy, float dz, float* d_minmax);
+int gcb_svl_slab_host_submit_extract(gcb_ctx* ctx, int slot, const float* d_svl_scratch, const float* d_ab, float isoValue, float isovalue1,
+    float isovalue2, gcb_uint3 gridSizeLocal, gcb_slab slab, gcb_float3 voxelSize, gcb_float3 gridcenter, void* pos, void* norm,
+    unsigned long long maxVerts);
 
 /* ------------------------------------------------------------------ several GPUs from one host process (z-slab sharding)
  * The reference is single-GPU; the scheme is BASELINE.json's: rank r owns cell layers [z0_r, z1_r) (gcb_slab_bounds, cuts aligned

@@ -1961,3 +1961,85 @@ def test_csg_retain_primitive_argument_errors(ctx):
     with pytest.raises(RuntimeError):   # a cuboid needs three widths
         ctx.check(g.api.lib().gcb_csg_retain_primitive(ctx._h, 2, _capi.Float3(0, 0, 0), _capi.Float3(0, 0, 0), (C.c_float * 2)(1, 1), 2, 0, f.data_ptr(), st.data_ptr(),
                                                        16, 16, 16, 1.0, 1.0, 1.0, 0.0, 1, 0, 0))
+
+
+def test_slab_job_pipeline_two_ranks_on_one_gpu_equals_single_pass(ctx):
+    """gcb_svl_slab_host_submit_field / _submit_extract: the sharded form of the job pipeline.  Two "ranks" (two contexts on this GPU, each with
+    its own z-slab, host control planes and slots) run three jobs each through the two halves, with the range reduced between them on the
+    device (here: an elementwise min / max of the two ranks' pairs on the same stream, the role NCCL's all-reduce has in bench.py).  The
+    concatenated rank meshes must equal the single-pass mesh of every job."""
+    from gpucadforam_b200 import sharding
+    cfg = cases.SVL4
+    phi, coef = cases.svl_inputs(cfg)
+    dims, cdims, d = cfg["fdims"], cfg["cdims"], cfg["d"]
+    fx, fy, fz = dims
+    R = int(round(1.0 / d[2]))
+    mv = max_verts_for(dims)
+    world = 2
+    ctxs = [ctx, g.Context(0, options=_capi.GCB_OPT_LEGACY_MEMSET)]
+    try:
+        jobs = [(phi + np.float32(0.21 * j)).astype(np.float32) for j in range(3)]
+        want = []
+        svl_full, scratch_full = torch.zeros(fx * fy * fz, device="cuda"), torch.zeros(phi.shape, device="cuda")
+        for p in jobs:
+            mesh = g.MeshBuffers(mv)
+            a, t, mm = g.svl_lattice_host(ctx, torch.from_numpy(p).pin_memory(), scratch_full, svl_full, coef, cdims, dims, d, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI,
+                                          d, (0, 0, 0), mesh.pos, mesh.norm, mv)
+            want.append((a, t, mm, mesh))
+        # per-rank state
+        rk = []
+        for r in range(world):
+            z0, z1 = sharding.slab_bounds(fz, world, r)
+            c0, c1 = sharding.control_slab(z0, z1, R, cdims[2])
+            nzl = z1 - z0 + 1
+            rk.append(dict(z0=z0, nzl=nzl, c0=c0, czl=c1 - c0 + 1, svl=torch.zeros(fx * fy * nzl, device="cuda"),
+                           scr=[torch.zeros((phi.shape[0], c1 - c0 + 1, cdims[1], cdims[0]), device="cuda") for _ in range(2)],
+                           mm=[torch.zeros(2, device="cuda") for _ in range(2)],
+                           hphi=[torch.from_numpy(np.ascontiguousarray(p[:, c0:c1 + 1])).pin_memory() for p in jobs],
+                           meshes=[g.MeshBuffers(mv) for _ in jobs]))
+        keep = {}
+
+        def submit(j):
+            sl = j % 2
+            for r, s in enumerate(rk):
+                g.svl_slab_host_submit_field(ctxs[r], sl, s["hphi"][j], s["scr"][sl], s["svl"], coef, (cdims[0], cdims[1], s["czl"]), (fx, fy, s["nzl"]), d,
+                                             (s["z0"], fz), s["c0"], s["mm"][sl])
+            # the exchange: both contexts run on the legacy default stream, so these torch ops are ordered behind both fields
+            ab = torch.stack([torch.minimum(rk[0]["mm"][sl][0], rk[1]["mm"][sl][0]), torch.maximum(rk[0]["mm"][sl][1], rk[1]["mm"][sl][1])])
+            keep[sl] = ab
+            for r, s in enumerate(rk):
+                g.svl_slab_host_submit_extract(ctxs[r], sl, s["svl"], ab, cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, (fx, fy, s["nzl"]), d, (0, 0, 0),
+                                               s["meshes"][j].pos, s["meshes"][j].norm, mv, slab=(s["z0"], fz))
+
+        def wait(j):
+            return [g.svl_lattice_host_wait(ctxs[r], j % 2) for r in range(world)]
+
+        got = []
+        submit(0)
+        for j in range(1, len(jobs)):
+            submit(j)
+            got.append(wait(j - 1))
+        got.append(wait(len(jobs) - 1))
+        for j, ((a, t, mm, mesh), per_rank) in enumerate(zip(want, got)):
+            assert sum(x[0] for x in per_rank) == a and sum(x[1] for x in per_rank) == t, "job %d counts" % j
+            assert all(x[2] == mm for x in per_rank), "job %d: range handed back by _wait" % j
+            off = 0
+            for r, (ar, tr, _) in enumerate(per_rank):
+                assert_bits_equal(mesh.pos[off:off + tr], rk[r]["meshes"][j].pos[:tr], "slab pipeline job %d rank %d pos" % (j, r))
+                assert_bits_equal(mesh.norm[off:off + tr], rk[r]["meshes"][j].norm[:tr], "slab pipeline job %d rank %d norm" % (j, r))
+                off += tr
+        # protocol: the extraction half needs a pending field half, and a slot takes one job at a time
+        with pytest.raises(RuntimeError):
+            g.svl_slab_host_submit_extract(ctxs[0], 0, rk[0]["svl"], keep[0], cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, (fx, fy, rk[0]["nzl"]), d, (0, 0, 0),
+                                           rk[0]["meshes"][0].pos, rk[0]["meshes"][0].norm, mv, slab=(rk[0]["z0"], fz))
+        s = rk[0]
+        g.svl_slab_host_submit_field(ctxs[0], 0, s["hphi"][0], s["scr"][0], s["svl"], coef, (cdims[0], cdims[1], s["czl"]), (fx, fy, s["nzl"]), d, (s["z0"], fz), s["c0"],
+                                     s["mm"][0])
+        with pytest.raises(RuntimeError):
+            g.svl_slab_host_submit_field(ctxs[0], 0, s["hphi"][0], s["scr"][0], s["svl"], coef, (cdims[0], cdims[1], s["czl"]), (fx, fy, s["nzl"]), d, (s["z0"], fz),
+                                         s["c0"], s["mm"][0])
+        g.svl_slab_host_submit_extract(ctxs[0], 0, s["svl"], keep[0], cases.ISO_MASK, cases.BAND_LO, cases.BAND_HI, (fx, fy, s["nzl"]), d, (0, 0, 0), s["meshes"][0].pos,
+                                       s["meshes"][0].norm, mv, slab=(s["z0"], fz))
+        g.svl_lattice_host_wait(ctxs[0], 0)
+    finally:
+        ctxs[1].close()
