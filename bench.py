@@ -16,6 +16,7 @@ One step = control grids resident in HBM -> field -> min/max (stays in device me
 on one GPU through the two-deep job pipeline (gcb_svl_lattice_host_submit / _wait; `e2e.blocking_call` = one blocking call per
 step), on N > 1 through the same pipeline in two halves per job (gcb_svl_slab_host_submit_field / _submit_extract around the
 stream-ordered NCCL all-reduce of the range), with `e2e.h2d_probe` naming the host-side limiter by measurement.
+`workflow` (N = 1, both arms) is the whole lattice job with the producer on the device: period field -> phase solve -> field -> mesh.
 `roofline` describes the kernel that dominates the step, `roofline_other_kernel` the other one: the SVL field kernel (writes 4 B /
 point: nothing to stream, bound by instruction issue -- reported with the HBM figure the contract asks for AND its actual limiter) and
 the fused extraction kernel (HBM-bound: 4 B/point + 32 B/vertex); both timed with CUDA events on the library's stream in the timed steps.
@@ -368,6 +369,56 @@ class SvlLeg:
         torch.cuda.empty_cache()
 
 
+def workflow_leg(env, F, R, NH, reps=2):
+    """The lattice workflow with the producer ON THE DEVICE (Multitopo::spatial_lattice_run, main.cu:3904-4037): period field -> normalise_three ->
+    phase solve of all harmonics on the control grid -> SVL field on the fine grid -> band extraction.  Nothing but the coefficients crosses
+    PCIe; this is where the batched phase solve shows in a whole-job number.  Single rank."""
+    torch, g, synth, ctx = env["torch"], env["g"], env["synth"], env["ctx"]
+    dev = env["dev"]
+    c = F // R
+    nc, d = c ** 3, (1.0 / R,) * 3
+    harm, coef = synth.HARMONICS[:NH], synth.gyroid_coefficients()[:NH]
+    per, phi, svl = torch.zeros(nc, device=dev), torch.zeros(NH, nc, device=dev), torch.empty(F ** 3, device=dev)
+    lat = g.Gratings(ctx)
+    ctx.set_options(0)
+    state = {}
+
+    def job(pos, norm, cap):
+        lat.period_data(per, c, c, c, 1.0, 1.0, 1.0, c / 2.0, c / 2.0, c / 2.0, "z")                    # main.cu:3927-3931
+        lat.GPU_buffer_normalise_three(per, per, nc, float(c // 10), float(c // 4))
+        state["fi"], _ = g.svl_phase_solve(ctx, phi, per, harm, (c, c, c), (1.0, 1.0, 1.0), latticetype="r", uniform_type=2, iters=500, end_res=0.01)
+        return g.svl_lattice(ctx, svl, phi, coef, (c, c, c), (F, F, F), d, ISO_MASK, BAND_LO, BAND_HI, d, (0.0, 0.0, 0.0), pos, norm, cap)
+
+    probe = g.MeshBuffers(3, device=dev)
+    _, tot, _ = job(probe.pos, probe.norm, 3)            # count pass (also the warm-up)
+    mesh = g.MeshBuffers(tot + 3, device=dev)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ms, ps = [], []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e[0].record()
+        lat.period_data(per, c, c, c, 1.0, 1.0, 1.0, c / 2.0, c / 2.0, c / 2.0, "z")
+        lat.GPU_buffer_normalise_three(per, per, nc, float(c // 10), float(c // 4))
+        e[1].record()
+        fi, _ = g.svl_phase_solve(ctx, phi, per, harm, (c, c, c), (1.0, 1.0, 1.0), latticetype="r", uniform_type=2, iters=500, end_res=0.01)
+        e[2].record()
+        act, tot2, _ = g.svl_lattice(ctx, svl, phi, coef, (c, c, c), (F, F, F), d, ISO_MASK, BAND_LO, BAND_HI, d, (0.0, 0.0, 0.0), mesh.pos, mesh.norm, tot + 3)
+        e[3].record()
+        torch.cuda.synchronize()
+        assert tot2 == tot
+        ms.append(e[0].elapsed_time(e[3]))
+        ps.append(e[1].elapsed_time(e[2]))
+    out = {"what": "period field -> normalise_three -> phase solve (%d harmonics, control %d^3, CG <= 500 it, 0.01) -> SVL field + band extraction %d^3; "
+                   "producer on the device, only coefficients cross PCIe" % (NH, c, F),
+           "ms_per_job": min(ms), "phase_solve_ms": min(ps), "field_and_extraction_ms": min(ms) - min(ps), "value": F ** 3 / (min(ms) * 1e-3), "unit": "voxels/s",
+           "cg_iterations_total": int(sum(fi) - len(fi)), "triangles": tot // 3, "active_voxels": act,
+           "note": "the reference's own sequence for the same job is timed in the --impl reference line (`workflow`)"}
+    del per, phi, svl, mesh
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return out
+
+
 # cost model of the slab balancing (ms per point / per vertex at 512-wide rows, from the kernel times of the N = 1 line): the field
 # kernel and the stage + classify half of the extraction scale with points, the emission with vertices
 COST_PER_POINT = {False: (9.8 + 0.67) / 134.2e6, True: (2.6 + 0.67) / 134.2e6}
@@ -524,6 +575,11 @@ def main():
             import config_bench
             extra["configs"] = config_bench.run_ours(g, ctx, args.steps, args.warmup)
             extra["configs"]["note"] = "this library only; the reference kernels' times for the same configs are in the --impl reference line"
+            # ---- the whole lattice workflow with the producer on the device (phase solve -> field -> mesh)
+            try:
+                extra["workflow"] = workflow_leg(env, F, R, NH)
+            except Exception as e:  # noqa: BLE001
+                extra["workflow"] = {"error": str(e)[:200]}
         if not args.strong and F == 512:
             # ---- BASELINE config 4: 2048-wide grid, z-slab sharded.  The 2048^3 mesh alone is ~354 GB (3.7 G triangles x 96 B), so the
             # full grid runs at N >= 4 (<= 106 GB per rank); N = 1 / 2 run the tallest 2048-wide stack of 513 point layers per rank
@@ -705,6 +761,48 @@ def reference_arm(args, torch, rank, world, local_rank):
                                         % (F, "the whole workload" if gnz == F else "1/%d of the workload: one rank's share" % world)},
                 e2e={"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=launches_per_step * args.steps)
     if not args.no_extra and world == 1 and (F, R) == (512, 4):
+        # the whole lattice workflow as the reference runs it (main.cu:3904-4037): period_data, GPU_buffer_normalise_three, per harmonic
+        # finding_phi + host-driven GPUCG_lattice, then the field loop and the extraction timed above.  One job (it takes seconds).
+        try:
+            nc = c ** 3
+            harm = synth.HARMONICS[:NH]
+            per = torch.zeros(nc, device=dev)
+            phi_w = torch.zeros(NH, nc, device=dev)
+            wcap = [0]
+
+            def wjob(count_only):
+                ref.period_data(per, (c, c, c), (1.0, 1.0, 1.0), (c / 2.0,) * 3, "z")
+                ref.normalise_three(per, per, nc, float(c // 10), float(c // 4))
+                its = 0
+                for h in range(NH):
+                    ref.finding_phi(phi_w[h], per, (c, c, c), harm[h], (1.0, 1.0, 1.0), latticetype="r", uniform_type=2)
+                    its += ref.cg(phi_w[h], (c, c, c), 500, 0.01)[0]
+                svl.zero_()
+                ref.svl_field(svl, ga, phi_w, NH, dcoef, (c, c, c), (F, F, F), d)
+                ref.normalise_four(svl, mask, k, (F, F, F), BAND_LO, BAND_HI)
+                if count_only:
+                    return ref.isosurface_lattice(False, fix, mask, tmp.pos, tmp.norm, ISO_MASK, (F, F, F), d, (0, 0, 0), scr, 3, k, zeros, BAND_LO, BAND_HI, 0.0, 0.0), its
+                return ref.isosurface_lattice(False, fix, mask, wmesh.pos, wmesh.norm, ISO_MASK, (F, F, F), d, (0, 0, 0), scr, wcap[0], k, zeros, BAND_LO, BAND_HI,
+                                              0.0, 0.0), its
+            (_, wtot), _ = wjob(True)
+            mesh = None
+            torch.cuda.empty_cache()
+            wcap[0] = wtot + 3
+            wmesh = g.MeshBuffers(wcap[0], device=dev)
+            torch.cuda.synchronize()
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            (wact, wtot2), wits = wjob(False)
+            w1.record()
+            torch.cuda.synchronize()
+            wms = w0.elapsed_time(w1)
+            base["workflow"] = {"what": "period_data -> GPU_buffer_normalise_three -> %d x (finding_phi + GPUCG_lattice) on control %d^3 -> %d x (texture upload, "
+                                        "grating, svl) -> GPU_buffer_normalise_four -> computeIsosurface_lattice %d^3: the reference's kernels and host loops" % (NH, c, NH, F),
+                                "ms_per_job": wms, "value": F ** 3 / (wms * 1e-3), "unit": "voxels/s", "cg_iterations_total": int(wits - NH), "triangles": wtot2 // 3,
+                                "active_voxels": wact}
+            del per, phi_w, wmesh
+        except Exception as e:  # noqa: BLE001
+            base["workflow"] = {"error": str(e)[:200]}
         # the reference kernels on BASELINE configs 1, 2, 5 (the product arm reports its own times for the same configs)
         del svl, ga, mask, k, zeros, scr, mesh, phi
         ref.delete_texture()
